@@ -1,0 +1,218 @@
+"""ctypes wrapper of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package xmipp3_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle_recfourier.so")
+_SRC = os.path.join(_HERE, "recfourier_oracle.cpp")
+
+
+def build(force=False):
+    """Compile the C++ restatement with g++ (no CUDA, no external libraries)."""
+    deps = [_SRC, os.path.join(_HERE, "oracle_abi.h")]
+    if (not force and os.path.exists(_SO)
+            and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps if os.path.exists(d))):
+        return _SO
+    if not os.path.exists(_SRC):
+        if os.path.exists(_SO):
+            return _SO
+        raise RuntimeError("oracle source missing")
+    cmd = ["g++", "-std=c++17", "-O3", "-march=native", "-fPIC", "-shared", "-pthread", "-o", _SO, _SRC]
+    subprocess.check_call(cmd, cwd=_HERE)
+    return _SO
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("img_size", C.c_int32), ("n_sym", C.c_int32),
+        ("pad_proj", C.c_double), ("pad_vol", C.c_double),
+        ("max_resolution", C.c_double),
+        ("blob_radius", C.c_double), ("blob_alpha", C.c_double),
+        ("blob_order", C.c_int32), ("use_ctf", C.c_int32),
+        ("sampling", C.c_double), ("min_ctf", C.c_double),
+        ("phase_flipped", C.c_int32), ("use_weights", C.c_int32),
+        ("n_iter_weight", C.c_int32), ("reserved", C.c_int32),
+        ("sym_matrices", C.POINTER(C.c_double)),
+    ]
+
+
+PARTICLE_FIELDS = ["rot", "tilt", "psi", "shift_x", "shift_y", "weight",
+                   "kV", "defocusU", "defocusV", "defocus_angle", "Cs", "Ca", "espr", "ispr", "alpha",
+                   "DeltaF", "DeltaR", "Q0", "K", "envR0", "envR1", "envR2", "phase_shift", "vpp_radius"]
+PARTICLE_DTYPE = np.dtype([(f, np.float64) for f in PARTICLE_FIELDS])
+
+
+def make_particles(n, **cols):
+    """Structured array of per-particle parameters with the reference's defaults
+    (data/ctf.cpp:365-419: kV 100, K 1, everything else 0; weight 1)."""
+    p = np.zeros(n, dtype=PARTICLE_DTYPE)
+    p["weight"] = 1.0
+    p["kV"] = 100.0
+    p["K"] = 1.0
+    for k, v in cols.items():
+        p[k] = v
+    if "defocusV" not in cols and "defocusU" in cols:
+        p["defocusV"] = p["defocusU"]
+    return p
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orf_create.restype = C.c_void_p
+        L.orf_create.argtypes = [C.POINTER(Config)]
+        L.orf_destroy.argtypes = [C.c_void_p]
+        L.orf_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
+        L.orf_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orf_get_accumulators.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_add_accumulators.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_finalize.argtypes = [C.c_void_p, C.c_void_p]
+        L.orf_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orf_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_apply_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.orf_ctf_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orf_ctf_value.restype = C.c_double
+        L.orf_ctf_value.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orf_euler.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orf_idx2digfreq.restype = C.c_double
+        L.orf_idx2digfreq.argtypes = [C.c_int, C.c_int]
+        for f in ("orf_kaiser_value", "orf_kaiser_fourier_value"):
+            getattr(L, f).restype = C.c_double
+            getattr(L, f).argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+        for f in ("orf_bessi0", "orf_bessj0"):
+            getattr(L, f).restype = C.c_double
+            getattr(L, f).argtypes = [C.c_double]
+        L.orf_fft2_r2c.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orf_fft1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """CPU ProgRecFourier restatement.  Parameters mirror the reference CLI (RF.cpp:42-58)."""
+
+    def __init__(self, img_size, padding=(2.0, 2.0), max_resolution=0.5, blob=(1.9, 0, 15.0),
+                 sym_matrices=None, use_ctf=False, sampling=1.0, min_ctf=0.01, phase_flipped=False,
+                 use_weights=False, n_iter_weight=1):
+        self._L = lib()
+        sm = np.zeros((0, 9)) if sym_matrices is None else np.ascontiguousarray(sym_matrices, dtype=np.float64).reshape(-1, 9)
+        self._sym = sm
+        cfg = Config()
+        cfg.img_size = int(img_size)
+        cfg.n_sym = sm.shape[0]
+        cfg.pad_proj, cfg.pad_vol = float(padding[0]), float(padding[1])
+        cfg.max_resolution = float(max_resolution)
+        cfg.blob_radius, cfg.blob_order, cfg.blob_alpha = float(blob[0]), int(blob[1]), float(blob[2])
+        cfg.use_ctf = int(bool(use_ctf))
+        cfg.sampling = float(sampling)
+        cfg.min_ctf = float(min_ctf)
+        cfg.phase_flipped = int(bool(phase_flipped))
+        cfg.use_weights = int(bool(use_weights))
+        cfg.n_iter_weight = int(n_iter_weight)
+        cfg.sym_matrices = sm.ctypes.data_as(C.POINTER(C.c_double)) if sm.size else None
+        self._cfg = cfg
+        self._h = self._L.orf_create(C.byref(cfg))
+        if not self._h:
+            raise RuntimeError("orf_create failed")
+        n, p, z = C.c_int(), C.c_int(), C.c_int()
+        self._L.orf_dims(self._h, C.byref(n), C.byref(p), C.byref(z))
+        self.N, self.P, self.Z = n.value, p.value, z.value
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orf_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def insert(self, images, particles, threads=1):
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        particles = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+        assert images.shape == (len(particles), self.N, self.N)
+        self._L.orf_insert(self._h, _ptr(images), _ptr(particles), len(particles), int(threads))
+
+    def accumulators(self):
+        Z, X = self.Z, self.Z // 2 + 1
+        V = np.empty((Z, Z, X), dtype=np.complex128)
+        W = np.empty((Z, Z, X), dtype=np.float64)
+        self._L.orf_get_accumulators(self._h, _ptr(V), _ptr(W))
+        return V, W
+
+    def add_accumulators(self, V, W):
+        V = np.ascontiguousarray(V, dtype=np.complex128)
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        self._L.orf_add_accumulators(self._h, _ptr(V), _ptr(W))
+
+    def finalize(self):
+        out = np.empty((self.N,) * 3, dtype=np.float64)
+        self._L.orf_finalize(self._h, _ptr(out))
+        return out
+
+    def tables(self):
+        a = np.empty(10000)
+        b = np.empty(10000)
+        d1, d2 = C.c_double(), C.c_double()
+        self._L.orf_tables(self._h, _ptr(a), _ptr(b), C.byref(d1), C.byref(d2))
+        return a, b, d1.value, d2.value
+
+    def preprocess(self, image, particle):
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        particle = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+        F = np.empty((self.P, self.P // 2 + 1), dtype=np.complex128)
+        A = np.empty((3, 3))
+        self._L.orf_preprocess(self._h, _ptr(image), _ptr(particle), _ptr(F), _ptr(A))
+        return F, A
+
+    def apply_shift(self, image, sx, sy):
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        out = np.empty((self.N, self.N))
+        self._L.orf_apply_shift(self._h, _ptr(image), float(sx), float(sy), _ptr(out))
+        return out
+
+    def ctf_weights(self, particle, i, j):
+        particle = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+        a, b = C.c_double(), C.c_double()
+        self._L.orf_ctf_weights(self._h, _ptr(particle), int(i), int(j), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+
+def ctf_value(particle, X, Y):
+    particle = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+    return lib().orf_ctf_value(_ptr(particle), float(X), float(Y))
+
+
+def euler(rot, tilt, psi):
+    m = np.empty((3, 3))
+    lib().orf_euler(float(rot), float(tilt), float(psi), _ptr(m))
+    return m
+
+
+def fft2_r2c(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    out = np.empty((a.shape[0], a.shape[1] // 2 + 1), dtype=np.complex128)
+    lib().orf_fft2_r2c(_ptr(a), a.shape[0], a.shape[1], _ptr(out))
+    return out
+
+
+def fft1(a, sign=-1):
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    out = np.empty_like(a)
+    lib().orf_fft1(_ptr(a), a.shape[0], int(sign), _ptr(out))
+    return out

@@ -1,0 +1,58 @@
+/* oracle/oracle_abi.h — C ABI of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+ * Mirrors the product ABI in include/recfourier_b200.h but in double precision. */
+#ifndef ORACLE_ABI_H
+#define ORACLE_ABI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int32_t img_size;        /* N (images are N x N float32) */
+    int32_t n_sym;           /* symmetry matrices WITHOUT the identity (SL.trueSymsNo()) */
+    double pad_proj, pad_vol;    /* --padding */
+    double max_resolution;       /* --max_resolution (digital frequency, Nyquist = 0.5) */
+    double blob_radius, blob_alpha;
+    int32_t blob_order;
+    int32_t use_ctf;             /* --useCTF and CTF columns present */
+    double sampling;             /* --sampling */
+    double min_ctf;              /* --minCTF */
+    int32_t phase_flipped;       /* --phaseFlipped */
+    int32_t use_weights;         /* --weight */
+    int32_t n_iter_weight;       /* --iter (0 or 1) */
+    int32_t reserved;
+    const double* sym_matrices;  /* n_sym * 9, row-major 3x3 */
+} orf_config;
+
+typedef struct {
+    double rot, tilt, psi, shift_x, shift_y, weight;
+    /* CTF columns (MDL_CTF_*), data/ctf.cpp:365-419, 1172-1212 */
+    double kV, defocusU, defocusV, defocus_angle, Cs, Ca, espr, ispr, alpha;
+    double DeltaF, DeltaR, Q0, K, envR0, envR1, envR2, phase_shift, vpp_radius;
+} orf_particle;
+
+void* orf_create(const orf_config* cfg);
+void orf_destroy(void* h);
+void orf_dims(void* h, int* N, int* P, int* Z);
+void orf_insert(void* h, const float* imgs, const orf_particle* meta, int n, int threads);
+void orf_get_accumulators(void* h, double* V, double* W);
+void orf_add_accumulators(void* h, const double* V, const double* W);
+void orf_finalize(void* h, double* out);
+void orf_tables(void* h, double* blobTableSqrt, double* fourierBlobTable, double* iDeltaSqrt, double* iDeltaFourier);
+void orf_preprocess(void* h, const float* img, const orf_particle* p, double* F, double* Ainv);
+void orf_apply_shift(void* h, const float* img, double sx, double sy, double* out);
+void orf_ctf_weights(void* h, const orf_particle* p, int i, int j, double* wCTF, double* wMod);
+double orf_ctf_value(const orf_particle* p, double X, double Y);
+void orf_euler(double rot, double tilt, double psi, double* m9);
+double orf_idx2digfreq(int idx, int size);
+double orf_kaiser_value(double r, double a, double alpha, int m);
+double orf_kaiser_fourier_value(double w, double a, double alpha, int m);
+double orf_bessi0(double x);
+double orf_bessj0(double x);
+void orf_fft2_r2c(const double* in, int ny, int nx, double* out);
+void orf_fft1(const double* in, int n, int sign, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
