@@ -24,7 +24,7 @@ def build(force=False):
         if os.path.exists(_SO):
             return _SO
         raise RuntimeError("oracle source missing")
-    cmd = ["g++", "-std=c++17", "-O3", "-march=native", "-fPIC", "-shared", "-pthread", "-o", _SO, _SRC]
+    cmd = ["g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-fPIC", "-shared", "-pthread", "-o", _SO, _SRC]
     subprocess.check_call(cmd, cwd=_HERE)
     return _SO
 

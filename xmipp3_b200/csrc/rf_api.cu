@@ -1,0 +1,792 @@
+// rf_api.cu — handle management and the extern "C" boundary declared in
+// include/recfourier_b200.h.  Host orchestration only; the arithmetic lives in
+// rf_kernels.cuh (device) and rf_host.hpp (double-precision precompute).
+//
+// Stream structure per handle: `copy` stream (H2D of raw particles, double buffered) and
+// `compute` stream (K1a -> cuFFT R2C -> K1b -> K2 -> K2e per chunk), linked by events, so
+// the PCIe transfer of chunk c+1 overlaps the kernels of chunk c.
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/recfourier_b200.h"
+#include "rf_host.hpp"
+#include "rf_kernels.cuh"
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define RFB200_HAVE_NCCL_H 1
+#else
+#define RFB200_HAVE_NCCL_H 0
+#endif
+
+using namespace rfb200;
+
+namespace {
+
+std::mutex g_errMutex;
+std::string g_createError;
+
+struct Stage { enum { H2D, PAD, FFT2D, SLICE, GATHER, EDGE, FINALIZE, REDUCE, COUNT }; };
+
+struct EvPair { int stage; cudaEvent_t a, b; };
+
+struct ParamSlot {      // pinned host staging for one chunk's parameters
+    ImgParams* img = nullptr;
+    CtfConsts* ctf = nullptr;
+    PlaneD* planesD = nullptr;
+    PlaneF* planesF = nullptr;
+    float* planesSoA = nullptr;
+    int* planeImg = nullptr;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+
+#if RFB200_HAVE_NCCL_H
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_ncclOnce;
+void load_nccl() {
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return;
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.Reduce = (decltype(g_nccl.Reduce))dlsym(g_nccl.lib, "ncclReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Reduce && g_nccl.CommDestroy;
+}
+#endif
+
+}  // namespace
+
+struct rfb200_handle_s {
+    rfb200_config cfg{};
+    std::vector<double> sym;        // (n_sym+1) x 9, identity first (R_repository, RF.cpp:272-286)
+    int nSymTot = 1;
+    Geometry geo{};
+    host::Tables tables;
+    std::vector<int> jmax;
+    int iLo = 0, iHi = 0;
+    int chunkImages = 0;            // images per preprocessing chunk
+    std::string err;
+
+    cudaStream_t compute = nullptr, copy = nullptr;
+    // static device data
+    float* dBlobTable = nullptr;
+    int* dJmax = nullptr;
+    int32_t* dTileList = nullptr;
+    int nTiles = 0;
+    EdgeItem* dEdge = nullptr;
+    int32_t* dEdgeGroups = nullptr;
+    int nEdge = 0, nEdgeGroups = 0;
+    int* dTileCounter = nullptr;
+    float* dG = nullptr;
+    // accumulators (blocked layout)
+    float2* dVb = nullptr;
+    float* dWb = nullptr;
+    int64_t nBlocked = 0;
+    // per-chunk buffers
+    float* dRaw[2] = {nullptr, nullptr};
+    cudaEvent_t evH2D[2] = {nullptr, nullptr}, evRawFree[2] = {nullptr, nullptr};
+    bool rawBusy[2] = {false, false};
+    float* dPad = nullptr;
+    float2* dFft = nullptr;
+    float4* dSlices = nullptr;
+    float4* dCol0 = nullptr;
+    ImgParams* dImg = nullptr;
+    CtfConsts* dCtf = nullptr;
+    PlaneD* dPlanesD = nullptr;
+    float* dPlanesSoA = nullptr;
+    int* dPlaneImg = nullptr;
+    ParamSlot slots[2];
+    int slotIdx = 0;
+    std::map<int, cufftHandle> plans2d;
+    // finalize
+    cufftHandle plan3d = 0;
+    bool havePlan3d = false;
+    float2* dNorm = nullptr;
+    float* dVol = nullptr;
+    float* dOut = nullptr;
+    // timings
+    std::vector<EvPair> pending;
+    std::vector<cudaEvent_t> evPool;
+    double ms[Stage::COUNT] = {0};
+    int64_t nImages = 0, nPlanes = 0, nGatherLaunches = 0, nKernelLaunches = 0;
+    int lastChunkImages = 0;
+#if RFB200_HAVE_NCCL_H
+    ncclComm_t comm = nullptr;
+#endif
+    int nRanks = 1, rank = 0;
+    int gatherGrid = 0;             // resident CTAs of the persistent gather: SMs x occupancy
+};
+
+namespace {
+
+#define RF_CUDA(h, call)                                                                      \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (h)->err = buf_;                                                                  \
+            return RFB200_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+#define RF_CUFFT(h, call)                                                                     \
+    do {                                                                                      \
+        cufftResult r_ = (call);                                                              \
+        if (r_ != CUFFT_SUCCESS) {                                                            \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof buf_, "%s failed: cufft error %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
+            (h)->err = buf_;                                                                  \
+            return RFB200_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+int fail(rfb200_handle h, int code, const std::string& msg) {
+    h->err = msg;
+    return code;
+}
+
+cudaEvent_t get_event(rfb200_handle h) {
+    if (!h->evPool.empty()) {
+        cudaEvent_t e = h->evPool.back();
+        h->evPool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {   // records an event pair around a stage on a stream
+    rfb200_handle h; int stage; cudaStream_t s; cudaEvent_t a, b;
+    StageTimer(rfb200_handle h_, int stage_, cudaStream_t s_) : h(h_), stage(stage_), s(s_) {
+        a = get_event(h); b = get_event(h);
+        cudaEventRecord(a, s);
+    }
+    ~StageTimer() {
+        cudaEventRecord(b, s);
+        h->pending.push_back({stage, a, b});
+    }
+};
+void resolve_timings(rfb200_handle h) {
+    for (auto& p : h->pending) {
+        float t = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) h->ms[p.stage] += t;
+        h->evPool.push_back(p.a);
+        h->evPool.push_back(p.b);
+    }
+    h->pending.clear();
+}
+
+template <int K>
+int launch_gather_k(rfb200_handle h, const GatherArgs& a, int grid) {
+    RF_CUDA(h, cudaFuncSetAttribute(k_gather<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
+    k_gather<K><<<grid, kGatherThreads, kGatherSmem, h->compute>>>(a);
+    RF_CUDA(h, cudaGetLastError());
+    return RFB200_OK;
+}
+int launch_gather(rfb200_handle h, const GatherArgs& a, int grid) {
+    switch (h->geo.K) {
+        case 1: return launch_gather_k<1>(h, a, grid);
+        case 2: return launch_gather_k<2>(h, a, grid);
+        case 3: return launch_gather_k<3>(h, a, grid);
+        case 4: return launch_gather_k<4>(h, a, grid);
+        case 5: return launch_gather_k<5>(h, a, grid);
+        case 6: return launch_gather_k<6>(h, a, grid);
+        case 7: return launch_gather_k<7>(h, a, grid);
+        case 8: return launch_gather_k<8>(h, a, grid);
+    }
+    return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
+}
+
+
+int get_plan2d(rfb200_handle h, int batch, cufftHandle* out) {
+    auto it = h->plans2d.find(batch);
+    if (it != h->plans2d.end()) { *out = it->second; return RFB200_OK; }
+    cufftHandle p;
+    int n[2] = {h->geo.P, h->geo.P};
+    RF_CUFFT(h, cufftPlanMany(&p, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, batch));
+    RF_CUFFT(h, cufftSetStream(p, h->compute));
+    h->plans2d[batch] = p;
+    *out = p;
+    return RFB200_OK;
+}
+
+// fill one chunk's parameter slot on the host (double precision) and upload it
+int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, ParamSlot** slotOut, int* nPlanesOut) {
+    ParamSlot& s = h->slots[h->slotIdx];
+    h->slotIdx ^= 1;
+    if (s.used) RF_CUDA(h, cudaEventSynchronize(s.done));
+    const Geometry& g = h->geo;
+    const double pixPerVox = (double)g.P / (double)g.Z;
+    int np = 0;
+    for (int i = 0; i < n; ++i) {
+        const rfb200_particle& p = meta[i];
+        ImgParams q{};
+        double w = h->cfg.use_weights ? p.weight : 1.0;     // RF.cpp:374-381
+        q.weight = (float)w;
+        q.skip = (w == 0.0) ? 1 : 0;                        // RF.cpp:483-484
+        double rx = std::nearbyint(p.shift_x), ry = std::nearbyint(p.shift_y);
+        if (std::fabs(p.shift_x - rx) > 1e-9 || std::fabs(p.shift_y - ry) > 1e-9)
+            return fail(h, RFB200_ERR_UNSUPPORTED, "fractional shiftX/shiftY need the cubic B-spline path, which is not implemented yet");
+        q.shift_x = (int)rx;
+        q.shift_y = (int)ry;
+        s.img[i] = q;
+        if (h->cfg.use_ctf)
+            s.ctf[i] = host::make_ctf(p.kV, p.defocusU, p.defocusV, p.defocus_angle, p.Cs, p.Ca, p.espr, p.ispr, p.alpha, p.DeltaF,
+                                      p.DeltaR, p.Q0, p.K, p.envR0, p.envR1, p.envR2, p.phase_shift, p.vpp_radius);
+        if (q.skip) continue;
+        for (int sIdx = 0; sIdx < h->nSymTot; ++sIdx) {
+            host::make_plane(&h->sym[9 * sIdx], p.rot, p.tilt, p.psi, pixPerVox, i, s.planesD[np], s.planesF[np]);
+            s.planeImg[np] = i;
+            ++np;
+        }
+    }
+    RF_CUDA(h, cudaMemcpyAsync(h->dImg, s.img, sizeof(ImgParams) * n, cudaMemcpyHostToDevice, h->compute));
+    if (h->cfg.use_ctf) RF_CUDA(h, cudaMemcpyAsync(h->dCtf, s.ctf, sizeof(CtfConsts) * n, cudaMemcpyHostToDevice, h->compute));
+    if (np) {
+        RF_CUDA(h, cudaMemcpyAsync(h->dPlanesD, s.planesD, sizeof(PlaneD) * np, cudaMemcpyHostToDevice, h->compute));
+        RF_CUDA(h, cudaMemcpyAsync(h->dPlaneImg, s.planeImg, sizeof(int) * np, cudaMemcpyHostToDevice, h->compute));
+    }
+    s.used = true;
+    *slotOut = &s;
+    *nPlanesOut = np;
+    return RFB200_OK;
+}
+
+// K1a -> cuFFT -> K1b -> K2 (+K2e) for n images whose raw data sit at dRaw (device)
+int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* meta, int n) {
+    const Geometry& g = h->geo;
+    ParamSlot* slot = nullptr;
+    int nPlanes = 0;
+    int rc = upload_chunk_params(h, meta, n, &slot, &nPlanes);
+    if (rc) return rc;
+    {
+        StageTimer t(h, Stage::PAD, h->compute);
+        dim3 grid((g.N * g.N + 255) / 256, n);
+        k_pad_images<<<grid, 256, 0, h->compute>>>(dRaw, h->dPad, h->dImg, g.N, g.P);
+        RF_CUDA(h, cudaGetLastError());
+    }
+    {
+        StageTimer t(h, Stage::FFT2D, h->compute);
+        cufftHandle plan;
+        rc = get_plan2d(h, n, &plan);
+        if (rc) return rc;
+        RF_CUFFT(h, cufftExecR2C(plan, h->dPad, reinterpret_cast<cufftComplex*>(h->dFft)));
+    }
+    {
+        StageTimer t(h, Stage::SLICE, h->compute);
+        SliceParams sp{};
+        sp.P = g.P; sp.Xh = g.P / 2 + 1; sp.iLo = h->iLo; sp.iHi = h->iHi;
+        sp.R = g.R; sp.Rp = g.Rp; sp.side = g.side;
+        sp.useCtf = h->cfg.use_ctf; sp.phaseFlipped = h->cfg.phase_flipped;
+        sp.iTs = 1.0 / h->cfg.sampling;
+        sp.minCtf = h->cfg.min_ctf;
+        sp.invP2 = (float)(1.0 / ((double)g.P * (double)g.P));
+        dim3 grid(((g.R + 1) * (2 * g.R + 1) + 255) / 256, n);
+        k_make_slices<<<grid, 256, 0, h->compute>>>(h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dJmax, sp);
+        RF_CUDA(h, cudaGetLastError());
+    }
+    h->nKernelLaunches += 2;
+    // gather launches over sub-ranges of at most kMaxPlanes planes
+    for (int p0 = 0; p0 < nPlanes; p0 += kMaxPlanes) {
+        int np = std::min(kMaxPlanes, nPlanes - p0);
+        // SoA copy for the culling phase (coalesced by plane index)
+        float* soa = slot->planesSoA;
+        // each sub-range needs its own staging region because the async copies read it later
+        float* soaChunk = soa + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
+        for (int k = 0; k < np; ++k) {
+            const PlaneF& f = slot->planesF[p0 + k];
+            for (int c = 0; c < 3; ++c) {
+                soaChunk[(0 + c) * kMaxPlanes + k] = f.e1[c];
+                soaChunk[(3 + c) * kMaxPlanes + k] = f.e2[c];
+                soaChunk[(6 + c) * kMaxPlanes + k] = f.n[c];
+            }
+        }
+        RF_CUDA(h, cudaMemcpyAsync(h->dPlanesSoA, soaChunk, sizeof(float) * 9 * kMaxPlanes, cudaMemcpyHostToDevice, h->compute));
+        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planes, slot->planesF + p0, sizeof(PlaneF) * np, 0, cudaMemcpyHostToDevice, h->compute));
+        RF_CUDA(h, cudaMemsetAsync(h->dTileCounter, 0, sizeof(int), h->compute));
+        {
+            StageTimer t(h, Stage::GATHER, h->compute);
+            GatherArgs a{};
+            a.geo = g;
+            a.tileList = h->dTileList; a.nTiles = h->nTiles; a.tileCounter = h->dTileCounter;
+            a.blobTable = h->dBlobTable;
+            a.planesD = h->dPlanesD + p0; a.planesSoA = h->dPlanesSoA; a.nPlanes = np;
+            a.slices = h->dSlices; a.sliceStride = (size_t)g.side * g.side;
+            a.Vb = h->dVb; a.Wb = h->dWb;
+            rc = launch_gather(h, a, std::min(h->gatherGrid, h->nTiles));
+            if (rc) return rc;
+        }
+        if (h->nEdge) {
+            StageTimer t(h, Stage::EDGE, h->compute);
+            EdgeArgs e{};
+            e.geo = g;
+            e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
+            e.planesD = h->dPlanesD + p0; e.planeImg = h->dPlaneImg + p0; e.nPlanes = np;
+            e.blobTable = h->dBlobTable; e.slices = h->dSlices; e.col0 = h->dCol0;
+            e.sliceStride = (size_t)g.side * g.side;
+            e.Vb = h->dVb; e.Wb = h->dWb;
+            e.iDeltaD = h->tables.iDeltaSqrt;
+            k_edge<<<(h->nEdgeGroups + 127) / 128, 128, 0, h->compute>>>(e);
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 1;
+        }
+        h->nGatherLaunches += 1;
+        h->nKernelLaunches += 1;
+    }
+    RF_CUDA(h, cudaEventRecord(slot->done, h->compute));
+    h->nImages += n;
+    h->nPlanes += nPlanes;
+    h->lastChunkImages = n;
+    return RFB200_OK;
+}
+
+int validate(const rfb200_config* c, std::string& why) {
+    if (!c) { why = "null config"; return RFB200_ERR_ARG; }
+    if (c->abi_version != RFB200_ABI_VERSION) { why = "abi_version mismatch"; return RFB200_ERR_ARG; }
+    if (c->img_size < 4 || c->img_size > 4096) { why = "img_size out of range"; return RFB200_ERR_ARG; }
+    if (c->pad_proj < 1.0 || c->pad_vol < 1.0) { why = "padding factors must be >= 1"; return RFB200_ERR_ARG; }
+    if (!(c->max_resolution > 0.0) || c->max_resolution > 0.5) { why = "max_resolution must be in (0, 0.5]"; return RFB200_ERR_ARG; }
+    if (!(c->blob_radius > 0.0)) { why = "blob radius must be positive"; return RFB200_ERR_ARG; }
+    if (c->blob_order != 0 && c->blob_order != 2) { why = "blob order must be 0 or 2 (kaiser_Fourier_value, blobs.cpp:146)"; return RFB200_ERR_ARG; }
+    if (c->n_sym < 0 || (c->n_sym > 0 && !c->sym_matrices)) { why = "symmetry matrices missing"; return RFB200_ERR_ARG; }
+    if (c->n_iter_weight < 0) { why = "n_iter_weight must be >= 0"; return RFB200_ERR_ARG; }
+    if (c->n_iter_weight > 1) { why = "--iter > 1 (weight refinement passes) is not implemented on this path yet"; return RFB200_ERR_UNSUPPORTED; }
+    if (c->fast) { why = "--fast is not implemented on this path yet"; return RFB200_ERR_UNSUPPORTED; }
+    if (c->use_ctf && !(c->sampling > 0.0)) { why = "sampling must be positive with use_ctf"; return RFB200_ERR_ARG; }
+    return RFB200_OK;
+}
+
+void free_all(rfb200_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->compute) cudaStreamSynchronize(h->compute);
+    if (h->copy) cudaStreamSynchronize(h->copy);
+    resolve_timings(h);
+    for (auto e : h->evPool) cudaEventDestroy(e);
+    for (auto& kv : h->plans2d) cufftDestroy(kv.second);
+    if (h->havePlan3d) cufftDestroy(h->plan3d);
+    void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dRaw[0], h->dRaw[1],
+                   h->dPad, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlaneImg, h->dNorm,
+                   h->dVol, h->dOut};
+    for (void* p : dev) if (p) cudaFree(p);
+    for (auto& s : h->slots) {
+        void* hp[] = {s.img, s.ctf, s.planesD, s.planesF, s.planesSoA, s.planeImg};
+        for (void* p : hp) if (p) cudaFreeHost(p);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (h->evH2D[i]) cudaEventDestroy(h->evH2D[i]);
+        if (h->evRawFree[i]) cudaEventDestroy(h->evRawFree[i]);
+    }
+#if RFB200_HAVE_NCCL_H
+    if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+#endif
+    if (h->compute) cudaStreamDestroy(h->compute);
+    if (h->copy) cudaStreamDestroy(h->copy);
+    delete h;
+}
+
+int do_create(rfb200_handle h) {
+    const rfb200_config& c = h->cfg;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(h, RFB200_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); this library has no CPU fallback");
+    if (c.device < 0 || c.device >= ndev) return fail(h, RFB200_ERR_ARG, "device ordinal out of range");
+    RF_CUDA(h, cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    RF_CUDA(h, cudaGetDeviceProperties(&prop, c.device));
+
+    // ---- host precompute (double)
+    h->nSymTot = c.n_sym + 1;
+    h->sym.assign((size_t)9 * h->nSymTot, 0.0);
+    h->sym[0] = h->sym[4] = h->sym[8] = 1.0;
+    if (c.n_sym) std::memcpy(&h->sym[9], c.sym_matrices, sizeof(double) * 9 * c.n_sym);
+    h->tables = host::build_tables(c.img_size, c.pad_proj, c.pad_vol, c.blob_radius, c.blob_order, c.blob_alpha);
+    int P = (int)(c.img_size * c.pad_proj);
+    int R = 0;
+    host::build_cutoff(P, c.max_resolution, h->jmax, h->iLo, h->iHi, R);
+    h->geo = host::make_geometry(c.img_size, c.pad_proj, c.pad_vol, c.max_resolution, c.blob_radius, R);
+    Geometry& g = h->geo;
+    if (g.K > kMaxWin) return fail(h, RFB200_ERR_ARG, "blob radius too large for the interpolation window (max 8 pixels)");
+    std::vector<int32_t> tiles = host::build_tile_list(g);
+    std::vector<EdgeItem> edge = host::build_edge_items(g);
+    h->nTiles = (int)tiles.size();
+    h->nEdge = (int)edge.size();
+    double meanF2 = 0;
+    std::vector<float> G = host::build_gridding_table(c.img_size, c.pad_proj, c.pad_vol, h->tables, c.n_iter_weight, &meanF2);
+    std::vector<float> blobF(kBlobTable);
+    for (int i = 0; i < kBlobTable; ++i) blobF[i] = (float)h->tables.blobSqrt[i];
+
+    int maxBatch = c.max_batch > 0 ? c.max_batch : 1024;
+    h->chunkImages = std::min(maxBatch, 1024);
+
+    // ---- streams / events
+    RF_CUDA(h, cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    RF_CUDA(h, cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        RF_CUDA(h, cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming));
+        RF_CUDA(h, cudaEventCreateWithFlags(&h->evRawFree[i], cudaEventDisableTiming));
+    }
+
+    // ---- static device data
+    RF_CUDA(h, cudaMalloc(&h->dBlobTable, sizeof(float) * kBlobTable));
+    RF_CUDA(h, cudaMemcpy(h->dBlobTable, blobF.data(), sizeof(float) * kBlobTable, cudaMemcpyHostToDevice));
+    RF_CUDA(h, cudaMalloc(&h->dJmax, sizeof(int) * h->jmax.size()));
+    RF_CUDA(h, cudaMemcpy(h->dJmax, h->jmax.data(), sizeof(int) * h->jmax.size(), cudaMemcpyHostToDevice));
+    RF_CUDA(h, cudaMalloc(&h->dTileList, sizeof(int32_t) * std::max<size_t>(1, tiles.size())));
+    if (!tiles.empty()) RF_CUDA(h, cudaMemcpy(h->dTileList, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice));
+    if (!edge.empty()) {
+        RF_CUDA(h, cudaMalloc(&h->dEdge, sizeof(EdgeItem) * edge.size()));
+        RF_CUDA(h, cudaMemcpy(h->dEdge, edge.data(), sizeof(EdgeItem) * edge.size(), cudaMemcpyHostToDevice));
+        std::vector<int32_t> starts = host::edge_group_starts(edge);
+        h->nEdgeGroups = (int)starts.size() - 1;
+        RF_CUDA(h, cudaMalloc(&h->dEdgeGroups, sizeof(int32_t) * starts.size()));
+        RF_CUDA(h, cudaMemcpy(h->dEdgeGroups, starts.data(), sizeof(int32_t) * starts.size(), cudaMemcpyHostToDevice));
+    }
+    RF_CUDA(h, cudaMalloc(&h->dTileCounter, sizeof(int)));
+    RF_CUDA(h, cudaMalloc(&h->dG, sizeof(float) * G.size()));
+    RF_CUDA(h, cudaMemcpy(h->dG, G.data(), sizeof(float) * G.size(), cudaMemcpyHostToDevice));
+
+    // ---- accumulators
+    h->nBlocked = (int64_t)g.tx * g.ty * g.tz * kTileVox;
+    RF_CUDA(h, cudaMalloc(&h->dVb, sizeof(float2) * h->nBlocked));
+    RF_CUDA(h, cudaMalloc(&h->dWb, sizeof(float) * h->nBlocked));
+    RF_CUDA(h, cudaMemset(h->dVb, 0, sizeof(float2) * h->nBlocked));
+    RF_CUDA(h, cudaMemset(h->dWb, 0, sizeof(float) * h->nBlocked));
+
+    // ---- per-chunk buffers
+    const size_t CH = h->chunkImages;
+    const size_t nRaw = CH * g.N * g.N, nPad = CH * (size_t)g.P * g.P, nFft = CH * (size_t)g.P * (g.P / 2 + 1);
+    const size_t nSl = CH * (size_t)g.side * g.side, nC0 = CH * (size_t)g.side;
+    for (int i = 0; i < 2; ++i) RF_CUDA(h, cudaMalloc(&h->dRaw[i], sizeof(float) * nRaw));
+    RF_CUDA(h, cudaMalloc(&h->dPad, sizeof(float) * nPad));
+    RF_CUDA(h, cudaMemset(h->dPad, 0, sizeof(float) * nPad));
+    RF_CUDA(h, cudaMalloc(&h->dFft, sizeof(float2) * nFft));
+    RF_CUDA(h, cudaMalloc(&h->dSlices, sizeof(float4) * nSl));
+    RF_CUDA(h, cudaMemset(h->dSlices, 0, sizeof(float4) * nSl));
+    RF_CUDA(h, cudaMalloc(&h->dCol0, sizeof(float4) * nC0));
+    RF_CUDA(h, cudaMemset(h->dCol0, 0, sizeof(float4) * nC0));
+    RF_CUDA(h, cudaMalloc(&h->dImg, sizeof(ImgParams) * CH));
+    RF_CUDA(h, cudaMalloc(&h->dCtf, sizeof(CtfConsts) * CH));
+    const size_t maxPlanes = CH * h->nSymTot;
+    const size_t nSub = (maxPlanes + kMaxPlanes - 1) / kMaxPlanes;
+    RF_CUDA(h, cudaMalloc(&h->dPlanesD, sizeof(PlaneD) * maxPlanes));
+    RF_CUDA(h, cudaMalloc(&h->dPlaneImg, sizeof(int) * maxPlanes));
+    RF_CUDA(h, cudaMalloc(&h->dPlanesSoA, sizeof(float) * 9 * kMaxPlanes));
+    for (auto& s : h->slots) {
+        RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
+        RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));
+        RF_CUDA(h, cudaMallocHost(&s.planesD, sizeof(PlaneD) * maxPlanes));
+        RF_CUDA(h, cudaMallocHost(&s.planesF, sizeof(PlaneF) * maxPlanes));
+        RF_CUDA(h, cudaMallocHost(&s.planesSoA, sizeof(float) * 9 * kMaxPlanes * nSub));
+        RF_CUDA(h, cudaMallocHost(&s.planeImg, sizeof(int) * maxPlanes));
+        RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    // persistent grid: as many CTAs as fit
+    int occ = 0;
+    int rcK = RFB200_OK;
+    switch (g.K) {
+#define OCC_CASE(KK)                                                                                              \
+    case KK:                                                                                                      \
+        RF_CUDA(h, cudaFuncSetAttribute(k_gather<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem)); \
+        RF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather<KK>, kGatherThreads, kGatherSmem));  \
+        break;
+        OCC_CASE(1) OCC_CASE(2) OCC_CASE(3) OCC_CASE(4) OCC_CASE(5) OCC_CASE(6) OCC_CASE(7) OCC_CASE(8)
+#undef OCC_CASE
+        default: rcK = RFB200_ERR_ARG;
+    }
+    if (rcK) return fail(h, rcK, "unsupported interpolation window");
+    if (occ < 1) occ = 1;
+    h->gatherGrid = prop.multiProcessorCount * occ;
+    RF_CUDA(h, cudaDeviceSynchronize());
+    return RFB200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int rfb200_create(const rfb200_config* cfg, rfb200_handle* out) {
+    if (!out) return RFB200_ERR_ARG;
+    *out = nullptr;
+    std::string why;
+    int rc = validate(cfg, why);
+    if (rc) {
+        std::lock_guard<std::mutex> g(g_errMutex);
+        g_createError = why;
+        return rc;
+    }
+    rfb200_handle h = new rfb200_handle_s();
+    h->cfg = *cfg;               // the caller's sym_matrices pointer is only read inside do_create
+    rc = do_create(h);
+    h->cfg.sym_matrices = nullptr;
+    if (rc) {
+        {
+            std::lock_guard<std::mutex> g(g_errMutex);
+            g_createError = h->err;
+        }
+        free_all(h);
+        return rc;
+    }
+    *out = h;
+    return RFB200_OK;
+}
+
+void rfb200_destroy(rfb200_handle h) { free_all(h); }
+
+const char* rfb200_last_error(rfb200_handle h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_errMutex);
+    static thread_local std::string copy;
+    copy = g_createError;
+    return copy.c_str();
+}
+
+int rfb200_get_info(rfb200_handle h, rfb200_info* info) {
+    if (!h || !info) return RFB200_ERR_ARG;
+    const Geometry& g = h->geo;
+    info->N = g.N; info->P = g.P; info->Z = g.Z; info->X = g.X;
+    info->tiles_x = g.tx; info->tiles_y = g.ty; info->tiles_z = g.tz; info->tile = kTile;
+    info->n_blocked = h->nBlocked;
+    info->chunk_images = h->chunkImages;
+    info->n_tiles_active = h->nTiles;
+    info->n_edge_items = h->nEdge;
+    return RFB200_OK;
+}
+
+int rfb200_insert_batch(rfb200_handle h, const float* images, const rfb200_particle* meta, int32_t n) {
+    if (!h || (n > 0 && (!images || !meta)) || n < 0) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    const Geometry& g = h->geo;
+    const size_t imgElems = (size_t)g.N * g.N;
+    int buf = 0;
+    for (int i0 = 0; i0 < n; i0 += h->chunkImages, buf ^= 1) {
+        int cnt = std::min(h->chunkImages, n - i0);
+        if (h->rawBusy[buf]) RF_CUDA(h, cudaStreamWaitEvent(h->copy, h->evRawFree[buf], 0));
+        {
+            StageTimer t(h, Stage::H2D, h->copy);
+            RF_CUDA(h, cudaMemcpyAsync(h->dRaw[buf], images + (size_t)i0 * imgElems, sizeof(float) * imgElems * cnt,
+                                       cudaMemcpyHostToDevice, h->copy));
+        }
+        RF_CUDA(h, cudaEventRecord(h->evH2D[buf], h->copy));
+        RF_CUDA(h, cudaStreamWaitEvent(h->compute, h->evH2D[buf], 0));
+        int rc = process_chunk(h, h->dRaw[buf], meta + i0, cnt);
+        if (rc) return rc;
+        RF_CUDA(h, cudaEventRecord(h->evRawFree[buf], h->compute));
+        h->rawBusy[buf] = true;
+    }
+    // the caller may reuse `images` once every H2D copy has completed
+    RF_CUDA(h, cudaStreamSynchronize(h->copy));
+    return RFB200_OK;
+}
+
+int rfb200_insert_batch_device(rfb200_handle h, const float* d_images, const rfb200_particle* meta, int32_t n) {
+    if (!h || (n > 0 && (!d_images || !meta)) || n < 0) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t imgElems = (size_t)h->geo.N * h->geo.N;
+    for (int i0 = 0; i0 < n; i0 += h->chunkImages) {
+        int cnt = std::min(h->chunkImages, n - i0);
+        int rc = process_chunk(h, d_images + (size_t)i0 * imgElems, meta + i0, cnt);
+        if (rc) return rc;
+    }
+    return RFB200_OK;
+}
+
+int rfb200_sync(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    RF_CUDA(h, cudaStreamSynchronize(h->copy));
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    resolve_timings(h);
+    return RFB200_OK;
+}
+
+int rfb200_reset(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    int rc = rfb200_sync(h);
+    if (rc) return rc;
+    RF_CUDA(h, cudaMemsetAsync(h->dVb, 0, sizeof(float2) * h->nBlocked, h->compute));
+    RF_CUDA(h, cudaMemsetAsync(h->dWb, 0, sizeof(float) * h->nBlocked, h->compute));
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    for (double& m : h->ms) m = 0;
+    h->nImages = h->nPlanes = h->nGatherLaunches = h->nKernelLaunches = 0;
+    return RFB200_OK;
+}
+
+int rfb200_nccl_unique_id(void* id128) {
+#if RFB200_HAVE_NCCL_H
+    if (!id128) return RFB200_ERR_ARG;
+    std::call_once(g_ncclOnce, load_nccl);
+    if (!g_nccl.ok) return RFB200_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return RFB200_ERR_NCCL;
+    std::memcpy(id128, &id, 128);
+    return RFB200_OK;
+#else
+    (void)id128;
+    return RFB200_ERR_NCCL;
+#endif
+}
+
+int rfb200_nccl_init(rfb200_handle h, const void* id128, int32_t n_ranks, int32_t rank) {
+#if RFB200_HAVE_NCCL_H
+    if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return RFB200_ERR_ARG;
+    std::call_once(g_ncclOnce, load_nccl);
+    if (!g_nccl.ok) return fail(h, RFB200_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) return fail(h, RFB200_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    h->nRanks = n_ranks;
+    h->rank = rank;
+    return RFB200_OK;
+#else
+    (void)id128; (void)n_ranks; (void)rank;
+    return h ? fail(h, RFB200_ERR_NCCL, "built without nccl.h") : RFB200_ERR_NCCL;
+#endif
+}
+
+int rfb200_reduce_nccl(rfb200_handle h, int32_t root) {
+#if RFB200_HAVE_NCCL_H
+    if (!h) return RFB200_ERR_ARG;
+    if (!h->comm) return fail(h, RFB200_ERR_STATE, "rfb200_nccl_init has not been called");
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    {
+        StageTimer t(h, Stage::REDUCE, h->compute);
+        ncclResult_t r1 = g_nccl.Reduce(h->dVb, h->dVb, (size_t)h->nBlocked * 2, ncclFloat, ncclSum, root, h->comm, h->compute);
+        ncclResult_t r2 = g_nccl.Reduce(h->dWb, h->dWb, (size_t)h->nBlocked, ncclFloat, ncclSum, root, h->comm, h->compute);
+        if (r1 != ncclSuccess || r2 != ncclSuccess) return fail(h, RFB200_ERR_NCCL, "ncclReduce failed");
+    }
+    return RFB200_OK;
+#else
+    (void)root;
+    return h ? fail(h, RFB200_ERR_NCCL, "built without nccl.h") : RFB200_ERR_NCCL;
+#endif
+}
+
+int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_blocked) {
+    if (!h) return RFB200_ERR_ARG;
+    if (d_V) *d_V = h->dVb;
+    if (d_W) *d_W = h->dWb;
+    if (n_blocked) *n_blocked = h->nBlocked;
+    return RFB200_OK;
+}
+
+int rfb200_export_accumulators(rfb200_handle h, float* V, float* W) {
+    if (!h || !V || !W) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    const Geometry& g = h->geo;
+    size_t total = (size_t)g.Z * g.Z * g.X;
+    float2* dV = nullptr;
+    float* dW = nullptr;
+    RF_CUDA(h, cudaMalloc(&dV, sizeof(float2) * total));
+    RF_CUDA(h, cudaMalloc(&dW, sizeof(float) * total));
+    k_export<<<(unsigned)((total + 255) / 256), 256, 0, h->compute>>>(g, h->dVb, h->dWb, dV, dW);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(V, dV, sizeof(float2) * total, cudaMemcpyDeviceToHost, h->compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(W, dW, sizeof(float) * total, cudaMemcpyDeviceToHost, h->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->compute);
+    cudaFree(dV);
+    cudaFree(dW);
+    if (e != cudaSuccess) return fail(h, RFB200_ERR_CUDA, std::string("export failed: ") + cudaGetErrorString(e));
+    return RFB200_OK;
+}
+
+int rfb200_finalize(rfb200_handle h, float* out) {
+    if (!h || !out) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    const Geometry& g = h->geo;
+    const rfb200_config& c = h->cfg;
+    size_t nHalf = (size_t)g.Z * g.Z * g.X, nVol = (size_t)g.Z * g.Z * g.Z, nOut = (size_t)g.N * g.N * g.N;
+    if (!h->havePlan3d) {
+        RF_CUFFT(h, cufftPlan3d(&h->plan3d, g.Z, g.Z, g.Z, CUFFT_C2R));
+        RF_CUFFT(h, cufftSetStream(h->plan3d, h->compute));
+        h->havePlan3d = true;
+    }
+    if (!h->dNorm) RF_CUDA(h, cudaMalloc(&h->dNorm, sizeof(float2) * nHalf));
+    if (!h->dVol) RF_CUDA(h, cudaMalloc(&h->dVol, sizeof(float) * nVol));
+    if (!h->dOut) RF_CUDA(h, cudaMalloc(&h->dOut, sizeof(float) * nOut));
+    {
+        StageTimer t(h, Stage::FINALIZE, h->compute);
+        NormArgs a{};
+        a.geo = g;
+        a.Vb = h->dVb; a.Wb = h->dWb; a.out = h->dNorm;
+        a.corr = (float)(std::pow(c.pad_proj, 2.0) / (c.img_size * std::pow(c.pad_vol, 3.0)));   // RF.cpp:457-458
+        a.nIterWeight = c.n_iter_weight;
+        k_normalize<<<(unsigned)((nHalf + 255) / 256), 256, 0, h->compute>>>(a);
+        RF_CUDA(h, cudaGetLastError());
+        RF_CUFFT(h, cufftExecC2R(h->plan3d, reinterpret_cast<cufftComplex*>(h->dNorm), h->dVol));
+        k_crop_correct<<<(unsigned)((nOut + 255) / 256), 256, 0, h->compute>>>(h->dVol, h->dG, h->dOut, g.N, g.Z);
+        RF_CUDA(h, cudaGetLastError());
+        RF_CUDA(h, cudaMemcpyAsync(out, h->dOut, sizeof(float) * nOut, cudaMemcpyDeviceToHost, h->compute));
+    }
+    h->nKernelLaunches += 2;
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    resolve_timings(h);
+    return RFB200_OK;
+}
+
+int rfb200_get_timings(rfb200_handle h, rfb200_timings* t) {
+    if (!h || !t) return RFB200_ERR_ARG;
+    int rc = rfb200_sync(h);
+    if (rc) return rc;
+    t->h2d_ms = h->ms[Stage::H2D];
+    t->preprocess_ms = h->ms[Stage::PAD];
+    t->fft2d_ms = h->ms[Stage::FFT2D];
+    t->slice_ms = h->ms[Stage::SLICE];
+    t->gather_ms = h->ms[Stage::GATHER];
+    t->edge_ms = h->ms[Stage::EDGE];
+    t->finalize_ms = h->ms[Stage::FINALIZE];
+    t->reduce_ms = h->ms[Stage::REDUCE];
+    t->images = h->nImages;
+    t->planes = h->nPlanes;
+    t->gather_launches = h->nGatherLaunches;
+    t->kernel_launches = h->nKernelLaunches;
+    return RFB200_OK;
+}
+
+int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radius) {
+    if (!h) return RFB200_ERR_ARG;
+    if (side) *side = h->geo.side;
+    if (apron_radius) *apron_radius = h->geo.Rp;
+    return RFB200_OK;
+}
+
+int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
+    if (!h || !out4 || idx < 0 || idx >= h->lastChunkImages) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    size_t n = (size_t)h->geo.side * h->geo.side;
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    RF_CUDA(h, cudaMemcpy(out4, h->dSlices + (size_t)idx * n, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    return RFB200_OK;
+}
+
+}  // extern "C"

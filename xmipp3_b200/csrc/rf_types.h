@@ -1,0 +1,88 @@
+// rf_types.h — POD types shared by the host code and the CUDA kernels of the
+// B200 direct-Fourier reconstruction path.
+#pragma once
+#include <stdint.h>
+
+namespace rfb200 {
+
+constexpr int kTile = 8;                     // voxels per tile edge (tile = 8^3 = 512 voxels = one CTA)
+constexpr int kTileVox = kTile * kTile * kTile;
+constexpr int kMaxPlanes = 1024;             // (image, symmetry) planes per gather launch; fits __constant__
+constexpr int kBlobTable = 10000;            // BLOB_TABLE_SIZE_SQRT (reconstruct_fourier.h:41-44)
+constexpr int kMaxWin = 8;                   // largest candidate window edge supported by the gather
+
+// One projection plane = one (image, symmetry operator) pair.  M = R_sym * A^T
+// (RF.cpp:936).  A voxel u (centred lattice coords, voxel units) sees the plane at
+//   alpha = u . e1   (pixel units along image x)
+//   beta  = u . e2   (pixel units along image y)
+//   h     = u . n    (voxel units, signed distance to the plane)
+// with e1 = M[:,0]*(P/Z), e2 = M[:,1]*(P/Z), n = M[:,2].
+struct PlaneF {            // 48 B, lives in __constant__ memory
+    float e1[3];
+    float e2[3];
+    float n[3];
+    int32_t img;           // image index inside the chunk
+    float pad0, pad1;
+};
+struct PlaneD {            // 72 B, global memory (tile-origin projections are done in double)
+    double e1[3];
+    double e2[3];
+    double n[3];
+};
+
+// Per-image CTF constants (data/ctf.cpp:645-680, 1392-1404), computed on the host in double.
+struct CtfConsts {
+    double K1, K2, K3, K5, K6, K7, Ksin, Kcos, K;
+    double DeltaR, envR0, envR1, envR2, phase_shift, vpp_radius;
+    double cos2az, sin2az;             // cos/sin of 2*rad_azimuth
+    double defocus_average, defocus_deviation;
+    int32_t has_envelope;              // any of K3,K5,K6,DeltaR,envR* non-zero
+    int32_t has_vpp;                   // round(VPP_radius*1000) != 0
+};
+
+struct ImgParams {         // per image of a chunk
+    float weight;          // 1 or the metadata weight (RF.cpp:374-381)
+    int32_t shift_x;       // integer part of the shift (exact circular shift)
+    int32_t shift_y;
+    float frac_x;          // fractional part (cubic B-spline path), 0 for integer shifts
+    float frac_y;
+    int32_t skip;          // weight == 0 -> image not inserted (RF.cpp:483-484)
+    int32_t pad0, pad1;
+};
+
+// A CTA-level hit: plane `k` intersects the tile.  Tile-origin projection split into
+// integer pixel + fraction so that the per-voxel FP32 arithmetic only sees small numbers.
+struct Hit {
+    int32_t k;             // plane index in the chunk
+    int32_t ja0, jb0;      // rint(alpha0), rint(beta0) of the tile origin
+    float fa, fb;          // alpha0 - ja0, beta0 - jb0   in [-0.5, 0.5]
+    float h0;              // height of the tile origin
+};
+
+// Edge work item: a lattice point that the main gather does not own (orig-only planes
+// x = 0 exception row, x = Z/2, and wrap-around aliases at the Nyquist faces).
+struct EdgeItem {
+    int32_t ux, uy, uz;    // unwrapped lattice point
+    int32_t mode;          // 0: originals + mirrors, 1: originals only
+    int64_t store;         // blocked index of the stored voxel it adds into
+};
+
+struct Geometry {
+    int32_t N, P, Z, X;            // image, padded image, padded volume, Z/2+1
+    int32_t lo, hi;                // centred range of y,z: [lo, hi]
+    int32_t tx, ty, tz;            // tiles per axis
+    int32_t yHalf;                 // rows 1..yHalf of the x=0 plane are pair-averaged (RF.cpp:1190-1195)
+    int32_t R;                     // largest |pixel index| passing the resolution cut-off
+    int32_t Rp;                    // R + apron: slices are (2Rp+1)^2
+    int32_t side;                  // 2Rp+1
+    int32_t K;                     // candidate window edge = floor(2*rho)+1
+    float rho;                     // blob radius in pixel units = r*P/Z
+    float s2;                      // (Z/P)^2: pixel^2 -> voxel^2
+    float r2;                      // blob radius^2 (voxel units)
+    float r;                       // blob radius
+    float iDelta;                  // (T-1)/r^2
+    float reach;                   // maxRes*Z + r: no lattice point farther than this is touched
+    float inplane_reach;           // R + rho (pixel units)
+};
+
+}  // namespace rfb200
