@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — particles/s inserted by the B200 direct-Fourier reconstruction path.
+
+Workload (BASELINE.json `metric`, config[2]): synthetic 256x256 phantom projections with CTF,
+padding 2, C1, blob 1.9/0/15, max_resolution 0.5.  One *step* = one pass of the hot path
+(pad/shift -> cuFFT R2C -> CTF-weighted slices -> voxel-centric gather) over one batch of
+`--batch` particles.  `value` is measured with the batch already resident in HBM; `e2e` goes
+through the C-ABI call with pinned HOST buffers (H2D inside the timed region), reads one 8-byte
+result back per step, and includes the final NCCL reduce (N>1), normalisation, 3-D inverse FFT
+and the D2H copy of the volume.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference ...                     (CPU oracle port on the host cores)
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particles/sec inserted (box 256, pad 2)"
+UNIT = "particles/s"
+SAMPLING = 1.5
+
+
+# ----------------------------------------------------------------------------- work model
+def work_model(box, pad=2.0, max_res=0.5, r=1.9):
+    P = int(box * pad)
+    Z = int(box * pad)
+    i = np.arange(-(P - 1 - P // 2), P // 2 + 1)[:, None] / P
+    j = np.arange(0, P // 2 + 1)[None, :] / P
+    npix = int(((i * i + j * j) <= max_res * max_res).sum())
+    pairs = npix * (4.0 / 3.0) * math.pi * r ** 3
+    nsphere = (2.0 / 3.0) * math.pi * (0.5 * Z + r) ** 3
+    return dict(P=P, Z=Z, npix=npix, pairs=pairs, nsphere=nsphere,
+                k2_bytes_per_particle=npix * 8.0, k2_bytes_per_launch_fixed=24.0 * nsphere,
+                k2_flops_per_particle=12.0 * pairs)
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def euler_batch(rot, tilt, psi):
+    a, b, g = np.radians(rot), np.radians(tilt), np.radians(psi)
+    ca, cb, cg, sa, sb, sg = np.cos(a), np.cos(b), np.cos(g), np.sin(a), np.sin(b), np.sin(g)
+    cc, cs, sc, ss = cb * ca, cb * sa, sb * ca, sb * sa
+    A = np.empty((len(rot), 3, 3))
+    A[:, 0, 0] = cg * cc - sg * sa; A[:, 0, 1] = cg * cs + sg * ca; A[:, 0, 2] = -cg * sb
+    A[:, 1, 0] = -sg * cc - cg * sa; A[:, 1, 1] = -sg * cs + cg * ca; A[:, 1, 2] = sg * sb
+    A[:, 2, 0] = sc; A[:, 2, 1] = ss; A[:, 2, 2] = cb
+    return A
+
+
+def synth_batch_torch(n, box, seed, device, ctf=True):
+    """Gaussian-phantom projections with CTF, generated on `device` with torch (data preparation only)."""
+    import torch
+    from xmipp3_b200 import synth
+    c, s, a = synth.make_phantom(n_gauss=30, box=box, seed=0)
+    rot, tilt, psi = synth.random_orientations(n, seed + 1)
+    A = euler_batch(rot, tilt, psi)
+    pc = np.einsum("bij,gj->bgi", A, c)
+    g = torch.arange(box, device=device, dtype=torch.float32) - box // 2
+    out = torch.empty((n, box, box), device=device, dtype=torch.float32)
+    st = torch.tensor(s, device=device, dtype=torch.float32)
+    amp = torch.tensor(a * s * np.sqrt(2 * np.pi), device=device, dtype=torch.float32)
+    cp = synth.random_ctf_params(n, seed + 3) if ctf else None
+    fr = torch.fft.fftfreq(box, device=device, dtype=torch.float64) / SAMPLING
+    X = fr[None, None, :]
+    Y = fr[None, :, None]
+    for b0 in range(0, n, 256):
+        b1 = min(n, b0 + 256)
+        px = torch.tensor(pc[b0:b1, :, 0], device=device, dtype=torch.float32)
+        py = torch.tensor(pc[b0:b1, :, 1], device=device, dtype=torch.float32)
+        gx = torch.exp(-0.5 * ((g[None, None, :] - px[:, :, None]) / st[None, :, None]) ** 2)
+        gy = torch.exp(-0.5 * ((g[None, None, :] - py[:, :, None]) / st[None, :, None]) ** 2) * amp[None, :, None]
+        img = torch.einsum("bgi,bgj->bij", gy, gx)
+        if ctf:
+            kV = 300.0
+            lam = 12.2643247 / math.sqrt(kV * 1e3 * (1.0 + 0.978466e-6 * kV * 1e3))
+            K1 = math.pi * lam
+            K2 = math.pi / 2 * 2.7e7 * lam ** 3
+            dU = torch.tensor(cp["defocusU"][b0:b1], device=device)[:, None, None]
+            dV = torch.tensor(cp["defocusV"][b0:b1], device=device)[:, None, None]
+            az = torch.deg2rad(torch.tensor(cp["defocus_angle"][b0:b1], device=device))[:, None, None]
+            u2 = X * X + Y * Y
+            ang = torch.atan2(Y, X).expand(1, box, box)
+            deltaf = -(dU + dV) * 0.5 - (dU - dV) * 0.5 * torch.cos(2 * (ang - az))
+            arg = K1 * deltaf * u2 + K2 * u2 * u2
+            q0 = 0.07
+            cval = -(math.sqrt(1 - q0 * q0) * torch.sin(arg) - q0 * torch.cos(arg))
+            img = torch.fft.ifft2(torch.fft.fft2(img.to(torch.float64)) * cval).real.to(torch.float32)
+        out[b0:b1] = img
+    cols = dict(rot=rot, tilt=tilt, psi=psi)
+    if ctf:
+        cols.update(cp)
+    return out, cols
+
+
+def synth_batch_numpy(n, box, seed, ctf=True):
+    from xmipp3_b200 import synth
+    ph = synth.make_phantom(n_gauss=30, box=box, seed=0)
+    rot, tilt, psi = synth.random_orientations(n, seed + 1)
+    img = synth.project(ph, box, rot, tilt, psi)
+    cols = dict(rot=rot, tilt=tilt, psi=psi)
+    if ctf:
+        cp = synth.random_ctf_params(n, seed + 3)
+        img = synth.apply_ctf(img, SAMPLING, **cp)
+        cols.update(cp)
+    return np.ascontiguousarray(img, dtype=np.float32), cols
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def time_oracle(box, n_sample, threads, ctf=True, seed=100):
+    """Time the CPU oracle (port of ProgRecFourier, reference thread scheme) on n_sample particles."""
+    from oracle import oracle as O
+    img, cols = synth_batch_numpy(n_sample, box, seed, ctf)
+    p = O.make_particles(n_sample, **cols)
+    o = O.Oracle(box, use_ctf=ctf, sampling=SAMPLING)
+    o.insert(img[: min(threads, n_sample)], p[: min(threads, n_sample)], threads=threads)   # touch pages, spin up
+    t = time.perf_counter()
+    o.insert(img, p, threads=threads)
+    dt = time.perf_counter() - t
+    return n_sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    box = args.box
+    sample = args.ref_sample
+    img, cols = synth_batch_numpy(sample, box, 100, True)
+    p = O.make_particles(sample, **cols)
+    o = O.Oracle(box, use_ctf=True, sampling=SAMPLING)
+    for _ in range(args.warmup):
+        o.insert(img, p, threads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        o.insert(img, p, threads=cores)
+    dt = time.perf_counter() - t
+    value = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config[2]: %dx%d phantom projections with CTF, padding 2, C1 (CPU arm: %d particles per step)" % (box, box, sample),
+                   "box": box, "padding": 2, "sym": "c1", "ctf": True, "particles_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d particles per step x %d steps, oracle/recfourier_oracle.cpp (double, reference row-scheduler threading, %d threads)" % (sample, args.steps, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--box", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=4096, help="particles per step and per GPU")
+    ap.add_argument("--ref-sample", type=int, default=192, help="particles per step of the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    box, B, K, W = args.box, args.batch, args.steps, args.warmup
+    wm = work_model(box)
+
+    # two distinct device-resident batches (each >> L2) used alternately
+    batches = []
+    for s in range(2):
+        img, cols = synth_batch_torch(B, box, 1000 * rank + 10 * s, dev, ctf=True)
+        batches.append((img, make_particles(B, **cols)))
+    torch.cuda.synchronize()
+
+    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=1024)
+    if world > 1:
+        ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        r.nccl_init(ids[0], world, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        r.sync()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local)
+
+    # ---------------- device-resident throughput ("value")
+    for i in range(W):
+        img, p = batches[i & 1]
+        r.insert_device_ptr(img.data_ptr(), p)
+    barrier()
+    r.reset()
+    barrier()
+    clocks.start()
+    r.timer_start()
+    for i in range(K):
+        img, p = batches[i & 1]
+        r.insert_device_ptr(img.data_ptr(), p)
+    ms = r.timer_stop()
+    barrier()
+    clocks.stop()
+    ms = max_over_ranks(ms)
+    tm = r.timings()
+    value = world * K * B / (ms * 1e-3)
+    launches = int(tm["kernel_launches"])
+
+    # per-kernel roofline of the dominant kernel (k_gather), from CUDA events on its stream
+    g_launches = max(1, int(tm["gather_launches"]))
+    g_ms = tm["gather_ms"] / g_launches
+    imgs_per_launch = K * B / g_launches
+    alg_bytes = imgs_per_launch * wm["k2_bytes_per_particle"] + wm["k2_bytes_per_launch_fixed"]
+    alg_flops = imgs_per_launch * wm["k2_flops_per_particle"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    cs = clocks.summary()
+    sm_mhz = cs.get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    roofline = {"kernel": "k_gather<4>", "bound": "hbm", "achieved": alg_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": alg_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "ms_per_launch": g_ms, "particles_per_launch": imgs_per_launch,
+                "note": "the gather is bound by FP32 issue, not HBM; see fp32"}
+    fp32 = {"achieved": alg_flops / (g_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": alg_flops / (g_ms * 1e-3) / 1e12 / fp32_peak,
+            "peak_source": "148 SM x 128 lanes x 2 x %.0f MHz (median SM clock during the run)" % sm_mhz}
+    stage_ms = {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}
+
+    # ---------------- end to end through the C ABI with pinned host buffers
+    e2e = None
+    extra = {}
+    if not args.no_e2e:
+        host = []
+        for img, p in batches:
+            hbuf = torch.empty(img.shape, dtype=torch.float32, pin_memory=True)
+            hbuf.copy_(img)
+            host.append((hbuf, p))
+        torch.cuda.synchronize()
+        r.reset()
+        r.insert_host_ptr(host[0][0].data_ptr(), host[0][1])
+        r.weight_sum()
+        r.reset()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            hbuf, p = host[i & 1]
+            r.insert_host_ptr(hbuf.data_ptr(), p)
+            r.weight_sum()                       # 8-byte D2H result per step
+        t_ins = time.perf_counter()
+        if world > 1:
+            r.reduce(0)
+            r.sync()
+        t_red = time.perf_counter()
+        vol = r.finalize() if rank == 0 else None
+        if world > 1:
+            dist.barrier()
+        t1 = time.perf_counter()
+        dt = max_over_ranks(t1 - t0)
+        e2e = {"value": world * K * B / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(B * box * box * 4 + B * 24 * 8),
+               "d2h_bytes_per_step": int(8 + (box ** 3 * 4) // K),
+               "includes": "H2D from pinned host memory, per-step 8-byte read-back, final reduce (N>1), normalise + 3-D IFFT + D2H of the volume"}
+        extra = {"e2e_insert_s": t_ins - t0, "e2e_reduce_s": t_red - t_ins, "e2e_finalize_s": t1 - t_red}
+        if rank == 0 and vol is not None:
+            extra["volume_finite"] = bool(np.isfinite(vol).all())
+        launches_e2e = int(r.timings()["kernel_launches"])
+        extra["gpu_launches_e2e"] = launches_e2e
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate0, _ = time_oracle(box, max(2 * cores, 32), cores)
+        n_s = int(min(4000, max(64, rate0 * 15)))
+        rate, dt = time_oracle(box, n_s, cores)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d particles of the same workload in %.1f s (oracle/recfourier_oracle.cpp, double, reference thread scheme)" % (n_s, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections with CTF, padding 2, C1, blob 1.9/0/15, max_resolution 0.5" % (box, box),
+                       "box": box, "padding": 2, "sym": "c1", "ctf": True, "particles_per_step_per_gpu": B,
+                       "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
+                       "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
+                       "stage_ms_per_step": stage_ms},
+            "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu_baseline,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -146,6 +146,21 @@ int rfb200_finalize(rfb200_handle h, float* out);
 
 int rfb200_get_timings(rfb200_handle h, rfb200_timings* t);
 
+/* Device-side stopwatch on the handle's compute stream (CUDA events): start records an event
+ * behind everything queued so far, stop records a second one, waits for it and returns the
+ * elapsed milliseconds.  Work issued through this handle in between (including the H2D copies
+ * it depends on) is what gets measured. */
+int rfb200_timer_start(rfb200_handle h);
+int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms);
+
+/* Sum of the weight accumulator (FP64 reduction on the device, 8-byte read-back): a cheap
+ * per-step result that forces completion of everything inserted so far. */
+int rfb200_weight_sum(rfb200_handle h, double* sum);
+
+/* The CUDA streams the handle launches on (cudaStream_t), for host programs that want to
+ * order their own work against it. */
+int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_stream);
+
 /* Diagnostics used by the parity tests: intermediate products of one particle. */
 /* Full-plane slice of image `idx` of the last chunk: (2*Rp+1)^2 float4 (re, im, m, 0). */
 int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radius);

@@ -114,7 +114,7 @@ def reconstruct(images, rot, tilt, psi, pad=2.0, max_res=0.5, blob=(1.9, 0, 15.0
         keep = (1.0 / Winv) > 1e-3
     corr = pad ** 2 / (N * pad ** 3)
     G = np.where(keep, Vs * corr * Winv, 0)
-    vol = np.fft.irfftn(G, s=(Z, Z, Z)) * Z ** 3          # unnormalised backward transform
+    vol = np.fft.irfftn(G, s=(Z, Z, Z), axes=(0, 1, 2)) * Z ** 3          # unnormalised backward transform
     g = np.arange(N) + (-(N // 2))
     sub = vol[np.ix_(g % Z, g % Z, g % Z)]
     kk, ii, jj = np.meshgrid(g, g, g, indexing="ij")

@@ -393,7 +393,7 @@ struct Oracle {
         if (n == 1) return;
         for (int k = 0; k < n; ++k) c[k * stride] *= lambda;
         // causal init (mirror, full sum with tolerance)
-        double tol = 1e-11;
+        double tol = 2.220446049250313e-16;   // DBL_EPSILON, as xmippCore's produceSplineCoefficients
         int horizon = (int)std::ceil(std::log(tol) / std::log(std::fabs(z1)));
         double sum;
         if (horizon < n) {

@@ -1,0 +1,195 @@
+"""CPU tests: pin the oracle (oracle/recfourier_oracle.cpp) against the reference's own
+known-answer vectors (tests/golden/reference_kats.json) and against independent restatements."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import special
+
+from oracle import mini_oracle as M
+from xmipp3_b200 import geometry, synth
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+
+
+def test_fft_known_answer(oracle_mod):
+    k = GOLD["fft2_r2c"]
+    out = oracle_mod.fft2_r2c(np.array(k["input"], dtype=np.float64))
+    want = np.array(k["output_re"]) + 1j * np.array(k["output_im"])
+    assert np.abs(out - want).max() < k["tolerance"]
+    # and the same convention as numpy: forward, e^{-i..}, scaled by 1/size
+    assert np.abs(out - np.fft.rfft2(np.array(k["input"], dtype=np.float64)) / 9).max() < 1e-14
+
+
+@pytest.mark.parametrize("n", [8, 12, 50, 64, 100, 128, 200, 97])
+def test_fft_vs_numpy(oracle_mod, n):
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    assert np.abs(oracle_mod.fft1(x, -1) - np.fft.fft(x)).max() < 1e-11
+    assert np.abs(oracle_mod.fft1(x, +1) - np.fft.ifft(x) * n).max() < 1e-11
+
+
+def test_idx2digfreq_known_answer(oracle_mod):
+    for idx, size, want in GOLD["fft_idx2digfreq"]["cases"]:
+        assert oracle_mod.lib().orf_idx2digfreq(idx, size) == want
+
+
+def test_euler_known_answer(oracle_mod):
+    k = GOLD["euler_angles2matrix"]
+    m = oracle_mod.euler(*k["angles"])
+    assert np.abs(m - np.array(k["matrix"])).max() < k["tolerance"]
+    assert np.abs(geometry.euler_matrix(*k["angles"]) - np.array(k["matrix"])).max() < k["tolerance"]
+
+
+def test_euler_zyz_grid(oracle_mod):
+    # test_euler_main.cpp:26-56 compares Euler_angles2matrix with an independent ZYZ composition on a
+    # 30-degree grid; mini_oracle.euler is such a composition.
+    for rot in range(0, 360, 30):
+        for tilt in range(0, 360, 30):
+            for psi in range(0, 360, 30):
+                a = oracle_mod.euler(rot, tilt, psi)
+                assert np.abs(a - M.euler(rot, tilt, psi)).max() < 1e-6
+                assert np.abs(a @ a.T - np.eye(3)).max() < 1e-12
+
+
+def test_symmetry_counts():
+    for name, want in GOLD["symmetry_counts"]["cases"].items():
+        assert geometry.point_group_matrices(name).shape[0] == want
+    assert geometry.point_group_matrices("c1").shape[0] == 0
+    assert geometry.point_group_matrices("c5").shape[0] == 4
+    assert geometry.point_group_matrices("d7").shape[0] == 13          # BASELINE config 4: 14 insertions
+    assert geometry.point_group_matrices("t").shape[0] == 11
+    assert geometry.point_group_matrices("o").shape[0] == 23
+    assert geometry.point_group_matrices("i1").shape[0] == 59
+    for name in ("d7", "o", "i2"):
+        for m in geometry.point_group_matrices(name):
+            assert np.abs(m @ m.T - np.eye(3)).max() < 1e-6
+            assert abs(np.linalg.det(m) - 1) < 1e-6
+
+
+def test_bessel_and_kaiser(oracle_mod):
+    L = oracle_mod.lib()
+    for x in (0.0, 0.5, 3.0, 3.75, 7.0, 15.0):
+        assert abs(L.orf_bessi0(x) / special.i0(x) - 1) < 1e-6      # NR polynomial accuracy
+    for x in (0.0, 1.0, 7.9, 8.1, 30.0):
+        assert abs(L.orf_bessj0(x) - special.j0(x)) < 1e-7
+    for r in (0.0, 0.7, 1.5, 1.9):
+        assert abs(L.orf_kaiser_value(r, 1.9, 15.0, 0) - special.i0(15 * np.sqrt(1 - (r / 1.9) ** 2)) / special.i0(15)) < 1e-6
+    assert L.orf_kaiser_value(1.91, 1.9, 15.0, 0) == 0.0
+
+
+def test_tables_vs_independent(oracle_mod):
+    o = oracle_mod.Oracle(16)
+    tab, ftab, idelta, idf = o.tables()
+    r, alpha = 1.9, 15.0
+    assert abs(idelta - 9999 / (r * r)) < 1e-9
+    iw0 = 1.0 / M._kaiser_fourier(0.0, r, alpha)
+    for i in (0, 1, 100, 5000, 9999):
+        assert abs(tab[i] - M._kaiser_value(r * np.sqrt(i / 9999.0), r, alpha) * iw0) < 2e-6 * tab[0]
+    dF = (np.sqrt(3.0) * 16 / 2) / 9999
+    for i in (0, 10, 5000, 9999):
+        want = M._kaiser_fourier(dF * i, r / 32.0, alpha) * 32.0 ** 3 * iw0
+        assert abs(ftab[i] - want) < 2e-6 * abs(ftab[0])
+    assert abs(ftab[0] - 1.0) < 1e-9     # the interpolation kernel integrates to one (RF.cpp:237-238)
+
+
+def test_oracle_matches_mini_oracle(oracle_mod):
+    N, n = 8, 10
+    d = synth.make_dataset(n, N, seed=5)
+    p = oracle_mod.make_particles(n, rot=d["rot"], tilt=d["tilt"], psi=d["psi"])
+    o = oracle_mod.Oracle(N)
+    o.insert(d["images"], p, threads=1)
+    V, W = o.accumulators()
+    V2, W2 = M.reconstruct(d["images"].astype(np.float64), d["rot"], d["tilt"], d["psi"], return_accumulators=True)
+    assert np.abs(V - V2).max() < 1e-6 * np.abs(V2).max()
+    assert np.abs(W - W2).max() < 1e-6 * np.abs(W2).max()
+    vol = o.finalize()
+    vol2 = M.reconstruct(d["images"].astype(np.float64), d["rot"], d["tilt"], d["psi"])
+    assert synth.rel_l2(vol, vol2) < 1e-7
+
+
+def test_oracle_symmetry_and_weights_vs_mini(oracle_mod):
+    N, n = 8, 4
+    d = synth.make_dataset(n, N, seed=6)
+    mats = geometry.point_group_matrices("c3")
+    w = np.array([1.0, 0.5, 0.0, 2.0])
+    p = oracle_mod.make_particles(n, rot=d["rot"], tilt=d["tilt"], psi=d["psi"], weight=w)
+    o = oracle_mod.Oracle(N, sym_matrices=mats, use_weights=True)
+    o.insert(d["images"], p, threads=1)
+    V, W = o.accumulators()
+    V2, W2 = M.reconstruct(d["images"].astype(np.float64), d["rot"], d["tilt"], d["psi"], sym=list(mats), weights=w,
+                           return_accumulators=True)
+    assert np.abs(V - V2).max() < 1e-6 * np.abs(V2).max()
+    assert np.abs(W - W2).max() < 1e-6 * np.abs(W2).max()
+
+
+def test_oracle_reconstructs_phantom(oracle_mod):
+    N, n = 32, 300
+    d = synth.make_dataset(n, N, seed=0)
+    p = oracle_mod.make_particles(n, rot=d["rot"], tilt=d["tilt"], psi=d["psi"])
+    o = oracle_mod.Oracle(N)
+    o.insert(d["images"], p, threads=1)
+    vol = o.finalize()
+    ph = synth.phantom_volume(d["phantom"], N)
+    assert np.corrcoef(vol.ravel(), ph.ravel())[0, 1] > 0.999
+
+
+def test_oracle_ctf_value_vs_numpy(oracle_mod):
+    N = 32
+    c = synth.ctf_2d(N, 1.5, 300.0, 20000.0, 19500.0, 30.0, 2.7, 0.07)
+    pp = oracle_mod.make_particles(1, kV=300.0, defocusU=20000.0, defocusV=19500.0, defocus_angle=30.0, Cs=2.7, Q0=0.07)
+    f = np.fft.fftfreq(N)
+    err = max(abs(oracle_mod.ctf_value(pp, f[j] / 1.5, f[i] / 1.5) - c[i, j]) for i in range(N) for j in range(N))
+    assert err < 1e-7
+
+
+def test_oracle_ctf_weights_rules(oracle_mod):
+    # RF.cpp:616-624: |ctf| < minCTF -> (sgn, |ctf|) else (1/ctf, 1); phaseFlipped -> |wCTF|
+    pp = oracle_mod.make_particles(1, kV=300.0, defocusU=15000.0, Cs=2.7, Q0=0.07)
+    o = oracle_mod.Oracle(32, use_ctf=True, sampling=1.5, min_ctf=0.2)
+    of = oracle_mod.Oracle(32, use_ctf=True, sampling=1.5, min_ctf=0.2, phase_flipped=True)
+    seen_small = seen_big = False
+    for i in range(0, 20):
+        for j in range(0, 20):
+            c = oracle_mod.ctf_value(pp, (j / 64) * (1.0 / 1.5), (i / 64) * (1.0 / 1.5))
+            wc, wm = o.ctf_weights(pp, i, j)
+            if abs(c) < 0.2:
+                assert abs(wm - abs(c)) < 1e-12 and wc == (1.0 if c >= 0 else -1.0)
+                seen_small = True
+            else:
+                assert wm == 1.0 and abs(wc - 1.0 / c) < 1e-12
+                seen_big = True
+            assert of.ctf_weights(pp, i, j)[0] == abs(wc)
+    assert seen_small and seen_big
+
+
+def test_oracle_integer_shift_is_circular(oracle_mod):
+    o = oracle_mod.Oracle(16)
+    img = np.random.default_rng(0).normal(size=(16, 16)).astype(np.float32)
+    out = o.apply_shift(img, 3, -2)
+    assert np.array_equal(out, np.roll(img.astype(np.float64), (-2, 3), axis=(0, 1)))
+    # fractional shift: cubic B-spline interpolation of a smooth blob that vanishes at the borders
+    # (xmippCore prefilters with mirror boundaries and indexes with wrap)
+    g = np.arange(16) - 8.0
+    blob = np.exp(-0.5 * (g[:, None] ** 2 + g[None, :] ** 2) / 2.0 ** 2).astype(np.float32)
+    out = o.apply_shift(blob, 0.5, -1.25)
+    want = np.exp(-0.5 * ((g[:, None] + 1.25) ** 2 + (g[None, :] - 0.5) ** 2) / 2.0 ** 2)
+    assert np.abs(out - want).max() < 2e-3
+    # interpolation property away from the borders (mirror prefilter + wrap indexing differ only there)
+    assert np.abs(o.apply_shift(blob, 1e-7, 0) - blob)[2:-2, 2:-2].max() < 1e-6
+
+
+def test_oracle_multithread_same_scheme(oracle_mod):
+    # two threads at box 32 never take conflicting rows; more threads can race across the fy = 0
+    # wrap exactly as the reference's row scheduler does ("reference thread race")
+    N, n = 32, 20
+    d = synth.make_dataset(n, N, seed=2)
+    p = oracle_mod.make_particles(n, rot=d["rot"], tilt=d["tilt"], psi=d["psi"])
+    o1 = oracle_mod.Oracle(N)
+    o1.insert(d["images"], p, threads=1)
+    o2 = oracle_mod.Oracle(N)
+    o2.insert(d["images"], p, threads=8)
+    W1 = o1.accumulators()[1]
+    W2 = o2.accumulators()[1]
+    assert np.linalg.norm(W1 - W2) / np.linalg.norm(W1) < 5e-2

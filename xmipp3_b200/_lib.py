@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_insert_batch", "rfb200_insert_batch_device", "rfb200_sync", "rfb200_reset",
     "rfb200_nccl_unique_id", "rfb200_nccl_init", "rfb200_reduce_nccl", "rfb200_accumulator_ptrs",
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
+    "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice",
 ]
 
@@ -103,6 +104,10 @@ def load(build=True):
     L.rfb200_export_accumulators.argtypes = [H, C.c_void_p, C.c_void_p]
     L.rfb200_finalize.argtypes = [H, C.c_void_p]
     L.rfb200_get_timings.argtypes = [H, C.POINTER(Timings)]
+    L.rfb200_timer_start.argtypes = [H]
+    L.rfb200_timer_stop.argtypes = [H, C.POINTER(C.c_double)]
+    L.rfb200_weight_sum.argtypes = [H, C.POINTER(C.c_double)]
+    L.rfb200_get_streams.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.rfb200_debug_slice_dims.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rfb200_debug_get_slice.argtypes = [H, C.c_int32, C.c_void_p]
     _lib = L
@@ -232,6 +237,24 @@ class Reconstructor:
         t = Timings()
         self._check(self._L.rfb200_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    def timer_start(self):
+        self._check(self._L.rfb200_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self._L.rfb200_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def weight_sum(self):
+        s = C.c_double()
+        self._check(self._L.rfb200_weight_sum(self._h, C.byref(s)))
+        return s.value
+
+    def streams(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._L.rfb200_get_streams(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_slice(self, idx):
         side, rp = C.c_int32(), C.c_int32()

@@ -138,6 +138,9 @@ struct rfb200_handle_s {
 #endif
     int nRanks = 1, rank = 0;
     int gatherGrid = 0;             // resident CTAs of the persistent gather: SMs x occupancy
+    cudaEvent_t swStart = nullptr, swStop = nullptr;
+    double* dSum = nullptr;         // 1024 partials + 1 result
+    double* hSum = nullptr;         // pinned
 };
 
 namespace {
@@ -387,6 +390,10 @@ void free_all(rfb200_handle h) {
     if (h->copy) cudaStreamSynchronize(h->copy);
     resolve_timings(h);
     for (auto e : h->evPool) cudaEventDestroy(e);
+    if (h->swStart) cudaEventDestroy(h->swStart);
+    if (h->swStop) cudaEventDestroy(h->swStop);
+    if (h->dSum) cudaFree(h->dSum);
+    if (h->hSum) cudaFreeHost(h->hSum);
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dRaw[0], h->dRaw[1],
@@ -469,6 +476,10 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMemcpy(h->dEdgeGroups, starts.data(), sizeof(int32_t) * starts.size(), cudaMemcpyHostToDevice));
     }
     RF_CUDA(h, cudaMalloc(&h->dTileCounter, sizeof(int)));
+    RF_CUDA(h, cudaMalloc(&h->dSum, sizeof(double) * 1025));
+    RF_CUDA(h, cudaMallocHost(&h->hSum, sizeof(double)));
+    RF_CUDA(h, cudaEventCreate(&h->swStart));
+    RF_CUDA(h, cudaEventCreate(&h->swStop));
     RF_CUDA(h, cudaMalloc(&h->dG, sizeof(float) * G.size()));
     RF_CUDA(h, cudaMemcpy(h->dG, G.data(), sizeof(float) * G.size(), cudaMemcpyHostToDevice));
 
@@ -770,6 +781,48 @@ int rfb200_get_timings(rfb200_handle h, rfb200_timings* t) {
     t->planes = h->nPlanes;
     t->gather_launches = h->nGatherLaunches;
     t->kernel_launches = h->nKernelLaunches;
+    return RFB200_OK;
+}
+
+int rfb200_timer_start(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    // make the compute stream wait for any copy still in flight so that the stopwatch starts "behind everything"
+    RF_CUDA(h, cudaStreamSynchronize(h->copy));
+    RF_CUDA(h, cudaEventRecord(h->swStart, h->compute));
+    return RFB200_OK;
+}
+
+int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms) {
+    if (!h || !elapsed_ms) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    RF_CUDA(h, cudaStreamSynchronize(h->copy));
+    RF_CUDA(h, cudaEventRecord(h->swStop, h->compute));
+    RF_CUDA(h, cudaEventSynchronize(h->swStop));
+    float ms = 0;
+    RF_CUDA(h, cudaEventElapsedTime(&ms, h->swStart, h->swStop));
+    *elapsed_ms = ms;
+    return RFB200_OK;
+}
+
+int rfb200_weight_sum(rfb200_handle h, double* sum) {
+    if (!h || !sum) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    k_weight_sum_partial<<<1024, 256, 0, h->compute>>>(h->dWb, h->nBlocked, h->dSum);
+    RF_CUDA(h, cudaGetLastError());
+    k_weight_sum_final<<<1, 256, 0, h->compute>>>(h->dSum, 1024, h->dSum + 1024);
+    RF_CUDA(h, cudaGetLastError());
+    h->nKernelLaunches += 2;
+    RF_CUDA(h, cudaMemcpyAsync(h->hSum, h->dSum + 1024, sizeof(double), cudaMemcpyDeviceToHost, h->compute));
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    *sum = *h->hSum;
+    return RFB200_OK;
+}
+
+int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_stream) {
+    if (!h) return RFB200_ERR_ARG;
+    if (compute_stream) *compute_stream = (void*)h->compute;
+    if (copy_stream) *copy_stream = (void*)h->copy;
     return RFB200_OK;
 }
 

@@ -498,6 +498,32 @@ __global__ void __launch_bounds__(256) k_export(const __grid_constant__ Geometry
     W[idx] = w;
 }
 
+// deterministic two-stage FP64 sum of the weight accumulator (fixed grid, fixed tree)
+__global__ void __launch_bounds__(256) k_weight_sum_partial(const float* __restrict__ Wb, int64_t n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += (double)Wb[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) k_weight_sum_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double acc = 0;
+    for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
 // ================================================================== K3b
 // out[kk][ii][jj] (N^3) = vol[k mod Z][i mod Z][j mod Z] * G[k^2+i^2+j^2], logical k = kk - N/2
 __global__ void __launch_bounds__(256) k_crop_correct(const float* __restrict__ vol, const float* __restrict__ G,
