@@ -81,6 +81,8 @@ def load(build=True):
     if _lib is not None:
         return _lib
     path = _build.LIB_CUDA
+    if os.environ.get("RFB200_LIB"):          # developer override: A/B-test an alternative build of the same sources
+        path, build = os.environ["RFB200_LIB"], False
     if build:
         path = _build.build_cuda()
     if not os.path.exists(path):

@@ -305,11 +305,14 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
         sp.P = g.P; sp.Xh = g.P / 2 + 1; sp.iLo = h->iLo; sp.iHi = h->iHi;
         sp.R = g.R; sp.Rp = g.Rp; sp.side = g.side;
         sp.useCtf = h->cfg.use_ctf; sp.phaseFlipped = h->cfg.phase_flipped;
-        sp.iTs = 1.0 / h->cfg.sampling;
+        const double aStep = (h->cfg.use_ctf ? 1.0 / h->cfg.sampling : 1.0) / (double)g.P;
+        sp.a2 = aStep * aStep;
+        sp.a = (float)aStep;
+        sp.minCtfF = (float)h->cfg.min_ctf;
         sp.minCtf = h->cfg.min_ctf;
         sp.invP2 = (float)(1.0 / ((double)g.P * (double)g.P));
-        dim3 grid(((g.R + 1) * (2 * g.R + 1) + 255) / 256, n);
-        k_make_slices<<<grid, 256, 0, h->compute>>>(h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dJmax, sp);
+        dim3 grid((g.R + 1 + 31) / 32, (2 * g.R + 1 + 8 * kSliceRowsPerThread - 1) / (8 * kSliceRowsPerThread), n);
+        k_make_slices<<<grid, dim3(32, 8), 0, h->compute>>>(h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dJmax, sp);
         RF_CUDA(h, cudaGetLastError());
     }
     h->nKernelLaunches += 2;

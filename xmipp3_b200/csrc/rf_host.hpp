@@ -272,6 +272,7 @@ inline Geometry make_geometry(int N, double padProj, double padVol, double maxRe
     g.r = (float)r;
     g.r2 = (float)(r * r);
     g.iDelta = (float)((kBlobTable - 1) / (r * r));
+    g.sMax = g.r2 * g.iDelta;
     g.reach = (float)(maxRes * g.Z + r);
     g.inplane_reach = (float)(R + rho);
     return g;

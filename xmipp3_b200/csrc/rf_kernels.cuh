@@ -68,7 +68,9 @@ struct SliceParams {
     int iLo, iHi;              // valid signed row range of the half-plane FFT
     int R, Rp, side;
     int useCtf, phaseFlipped;
-    double iTs;                // 1/sampling
+    double a2;                 // (1/(P*sampling))^2: integer |freq|^2 -> continuous u^2
+    float a;                   // 1/(P*sampling)
+    float minCtfF;
     double minCtf;
     float invP2;               // forward FFT normalisation 1/P^2 (RF.cpp:405-407)
 };
@@ -87,55 +89,89 @@ __device__ __forceinline__ double d_bessj0(double x) {
     return sqrt(0.636619772 / ax) * (cos(xx) * a1 - z * sin(xx) * a2);
 }
 
-// wCTF / wModulator of half-plane pixel (j, ip) — RF.cpp:600-625 with ctf.h:452-502, 1002-1029.
-// The phase argument is formed and range-reduced in double; sin/cos run in FP32 on the reduced
-// argument; the minCTF decision is taken in double.
-__device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
-    double X = ((double)j / sp.P) * sp.iTs;
-    double Y = ((double)ip / sp.P) * sp.iTs;
-    double u2 = X * X + Y * Y;
+// damping envelope of getValuePureAt (ctf.h:474-484), double precision; only evaluated when a CTF row
+// carries envelope parameters
+__device__ __noinline__ double d_ctf_envelope(const CtfConsts& c, double u2, double deltaf) {
+    double u = sqrt(u2), u4 = u2 * u2;
+    double Eespr = exp(-c.K3 * u4);
+    double EdeltaF = d_bessj0(c.K5 * u2);
+    double xr = u * c.DeltaR;
+    double EdeltaR = (fabs(xr) < 0.0001) ? 1.0 : sin(3.14159265358979323846 * xr) / (3.14159265358979323846 * xr);
+    double aux = c.K7 * u2 * u + deltaf * u;
+    double Ealpha = exp(-c.K6 * aux * aux);
+    double Ed = Eespr * EdeltaF * EdeltaR * Ealpha + c.envR0 + c.envR1 * u + c.envR2 * u2;
+    return Ed < 0 ? 0.0 : Ed;
+}
+
+// RF.cpp:609-624 applied to a CTF value: NaN handling, "invert or damp" by minCTF, phase flipping
+template <typename T>
+__device__ __forceinline__ void d_ctf_rules(T v, T minCtf, int phaseFlipped, int j, int ip, float& wCTF, float& wMod) {
+    T wm = 1, wc = v;
+    if (isnan(v)) {                                       // :609-615
+        if (ip == 0 && j == 0) wm = wc = 1;
+        else wm = wc = 0;
+    }
+    if (fabs(wc) < minCtf) {                              // :616-622
+        wm = fabs(wc);
+        wc = (wc >= 0) ? T(1) : T(-1);
+    } else
+        wc = T(1) / wc;
+    if (phaseFlipped) wc = fabs(wc);                      // :623-624
+    wCTF = (float)wc;
+    wMod = (float)wm;
+}
+
+// Full double-precision evaluation of getValuePureNoKAt (ctf.h:452-502, 1002-1029).  Only used for the rare
+// pixels whose |CTF| is within FP32 noise of the minCTF threshold, so that the invert-or-damp decision is the
+// one a double-precision program takes.
+__device__ __noinline__ void d_ctf_weights_exact(const CtfConsts& c, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
+    const int r2i = j * j + ip * ip;
+    const double u2 = (double)r2i * sp.a2;
     double deltaf = 0.0;
-    if (!(fabs(X) < 1e-6 && fabs(Y) < 1e-6)) {
-        // cos(2(atan2(Y,X) - az)) without the atan2
-        double inv = 1.0 / u2;
-        double c2 = (X * X - Y * Y) * inv, s2 = 2.0 * X * Y * inv;
+    if (!(fabs((double)j) * sp.a < 1e-6 && fabs((double)ip) * sp.a < 1e-6)) {
+        const double inv = 1.0 / (double)r2i;
+        const double c2 = (double)(j * j - ip * ip) * inv, s2 = (double)(2 * j * ip) * inv;
         deltaf = c.defocus_average + c.defocus_deviation * (c2 * c.cos2az + s2 * c.sin2az);
     }
-    double u4 = u2 * u2;
-    double arg = c.K1 * deltaf * u2 + c.K2 * u4;
+    double arg = u2 * fma(c.K1, deltaf, c.K2 * u2);
+    if (c.has_vpp) arg += -c.phase_shift * (1.0 - exp(-u2 / (2.0 * c.vpp_radius * c.vpp_radius)));
+    double sd, cd;
+    sincos(arg, &sd, &cd);
+    const double E = c.has_envelope ? d_ctf_envelope(c, u2, deltaf) : 1.0;
+    const double v = c.K * c.K * (c.Kcos * cd - c.Ksin * sd) * E;     // K * ( -K (Ksin sin - Kcos cos) E )
+    d_ctf_rules<double>(v, sp.minCtf, sp.phaseFlipped, j, ip, wCTF, wMod);
+}
+
+// wCTF / wModulator of half-plane pixel (j, ip) — RF.cpp:600-625.  Only the phase argument needs double
+// precision (it reaches hundreds of radians): it is formed from exact integer frequencies and range-reduced
+// in double; the astigmatism angle term, sin/cos and the minCTF rules run in FP32.
+// cos(2(atan2(Y,X) - az)) is expanded so that no atan2 is needed.
+__device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
+    const int r2i = j * j + ip * ip;                      // exact: |freq|^2 in units of (1/(P*Ts))^2
+    const double u2 = (double)r2i * sp.a2;
+    double deltaf = 0.0;
+    const float ax = fabsf((float)j) * sp.a, ay = fabsf((float)ip) * sp.a;
+    if (!(ax < 1e-6f && ay < 1e-6f)) {                    // precomputeValues(X,Y): deltaf = 0 at the origin
+        const float inv = 1.0f / (float)r2i;
+        const float c2 = (float)(j * j - ip * ip) * inv, s2 = (float)(2 * j * ip) * inv;
+        deltaf = c.defocus_average + c.defocus_deviation * (double)(c2 * (float)c.cos2az + s2 * (float)c.sin2az);
+    }
+    double arg = u2 * fma(c.K1, deltaf, c.K2 * u2);
     if (c.has_vpp) arg += -c.phase_shift * (1.0 - exp(-u2 / (2.0 * c.vpp_radius * c.vpp_radius)));
     const double inv2pi = 0.15915494309189535, twopi_hi = 6.283185307179586, twopi_lo = 2.4492935982947064e-16;
-    double kk = rint(arg * inv2pi);
+    const double kk = rint(arg * inv2pi);
     double red = fma(-kk, twopi_hi, arg);
     red = fma(-kk, twopi_lo, red);
     float sn, cs;
     sincosf((float)red, &sn, &cs);
-    double E = 1.0;
-    if (c.has_envelope) {
-        double u = sqrt(u2);
-        double Eespr = exp(-c.K3 * u4);
-        double EdeltaF = d_bessj0(c.K5 * u2);
-        double xr = u * c.DeltaR;
-        double EdeltaR = (fabs(xr) < 0.0001) ? 1.0 : sin(3.14159265358979323846 * xr) / (3.14159265358979323846 * xr);
-        double aux = c.K7 * u2 * u + deltaf * u;
-        double Ealpha = exp(-c.K6 * aux * aux);
-        E = Eespr * EdeltaF * EdeltaR * Ealpha + c.envR0 + c.envR1 * u + c.envR2 * u2;
-        if (E < 0) E = 0;
+    float E = 1.0f;
+    if (c.has_envelope) E = (float)d_ctf_envelope(c, u2, deltaf);
+    const float v = (float)(c.K * c.K) * ((float)c.Kcos * cs - (float)c.Ksin * sn) * E;
+    if (fabsf(fabsf(v) - sp.minCtfF) < 4e-6f) {
+        d_ctf_weights_exact(c, sp, j, ip, wCTF, wMod);
+        return;
     }
-    double v = c.K * (-c.K * (c.Ksin * (double)sn - c.Kcos * (double)cs) * E);   // getValuePureNoKAt = K*pure
-    double wm = 1.0, wc = v;
-    if (isnan(v)) {                                   // RF.cpp:609-615
-        if (ip == 0 && j == 0) wm = wc = 1.0;
-        else wm = wc = 0.0;
-    }
-    if (fabs(wc) < sp.minCtf) {                       // :616-622
-        wm = fabs(wc);
-        wc = (wc >= 0) ? 1.0 : -1.0;
-    } else
-        wc = 1.0 / wc;
-    if (sp.phaseFlipped) wc = fabs(wc);               // :623-624
-    wCTF = (float)wc;
-    wMod = (float)wm;
+    d_ctf_rules<float>(v, sp.minCtfF, sp.phaseFlipped, j, ip, wCTF, wMod);
 }
 
 // contribution of original half-plane pixel (j >= 0, ip): (re, im, m) = (wCTF*w*F, w), w = weight*wModulator
@@ -156,32 +192,39 @@ __device__ __forceinline__ float4 d_pixel_contrib(const float2* __restrict__ fft
     return out;
 }
 
-// grid (ceil((R+1)*(2R+1)/256), nImg): one thread per original half-plane pixel inside the bounding
-// square; it writes its own entry and the Hermitian mirror entry of the full-plane slice.
-__global__ void __launch_bounds__(256) k_make_slices(const float2* __restrict__ fft, float4* __restrict__ slices,
+// grid (ceil((R+1)/32), ceil((2R+1)/32), nImg), block (32, 8): threadIdx.x runs along j (coalesced reads of
+// the FFT rows and writes of the slice rows), every thread handles 4 rows.  A thread owns original half-plane
+// pixels (j >= 0, ip) inside the bounding square; it writes its own entry and the Hermitian mirror entry of
+// the full-plane slice.
+constexpr int kSliceRowsPerThread = 4;
+__global__ void __launch_bounds__(256, 4) k_make_slices(const float2* __restrict__ fft, float4* __restrict__ slices,
                                                      float4* __restrict__ col0, const ImgParams* __restrict__ ip,
                                                      const CtfConsts* __restrict__ ctfs, const int* __restrict__ jmax,
-                                                     SliceParams sp) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int W = sp.R + 1, H = 2 * sp.R + 1;
-    if (idx >= W * H) return;
-    int img = blockIdx.y;
-    int r = idx / W, j = idx - r * W;
-    int ipx = r - sp.R;
+                                                     const __grid_constant__ SliceParams sp) {
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    if (j > sp.R) return;
+    const int img = blockIdx.z;
     const float2* f = fft + (size_t)img * sp.P * sp.Xh;
     const CtfConsts* ctf = sp.useCtf ? ctfs + img : nullptr;
-    float weight = ip[img].weight;
+    const float weight = ip[img].weight;
     float4* S = slices + (size_t)img * sp.side * sp.side;
-    float4 c = d_pixel_contrib(f, jmax, sp, ctf, weight, j, ipx);
-    if (j > 0) {
-        S[(size_t)(ipx + sp.Rp) * sp.side + (j + sp.Rp)] = c;
-        S[(size_t)(-ipx + sp.Rp) * sp.side + (-j + sp.Rp)] = make_float4(c.x, -c.y, c.z, 0.f);
-    } else {
-        // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference
-        // inserts this column twice for x > 0 voxels
-        float4 m = d_pixel_contrib(f, jmax, sp, ctf, weight, 0, -ipx);
-        S[(size_t)(ipx + sp.Rp) * sp.side + sp.Rp] = make_float4(c.x + m.x, c.y - m.y, c.z + m.z, 0.f);
-        col0[(size_t)img * sp.side + (ipx + sp.Rp)] = c;
+    const int rowBase = blockIdx.y * (8 * kSliceRowsPerThread) + threadIdx.y;
+#pragma unroll 2
+    for (int q = 0; q < kSliceRowsPerThread; ++q) {
+        const int r = rowBase + 8 * q;
+        if (r > 2 * sp.R) break;
+        const int ipx = r - sp.R;
+        float4 c = d_pixel_contrib(f, jmax, sp, ctf, weight, j, ipx);
+        if (j > 0) {
+            S[(size_t)(ipx + sp.Rp) * sp.side + (j + sp.Rp)] = c;
+            S[(size_t)(-ipx + sp.Rp) * sp.side + (-j + sp.Rp)] = make_float4(c.x, -c.y, c.z, 0.f);
+        } else {
+            // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference
+            // inserts this column twice for x > 0 voxels
+            float4 m = d_pixel_contrib(f, jmax, sp, ctf, weight, 0, -ipx);
+            S[(size_t)(ipx + sp.Rp) * sp.side + sp.Rp] = make_float4(c.x + m.x, c.y - m.y, c.z + m.z, 0.f);
+            col0[(size_t)img * sp.side + (ipx + sp.Rp)] = c;
+        }
     }
 }
 
@@ -202,15 +245,18 @@ struct GatherArgs {
 };
 
 constexpr int kGatherThreads = kTileVox;   // 512: one thread per voxel of the tile
-constexpr size_t kGatherSmem = kBlobTable * sizeof(float) + kMaxPlanes * sizeof(Hit) + 64 * sizeof(int);
+constexpr size_t kGatherSmem = kMaxPlanes * sizeof(Hit) + 64 * sizeof(int);   // dynamic part (the blob table is static)
+#ifndef RF_GATHER_CTAS
+#define RF_GATHER_CTAS 2
+#endif
 
 template <int K>
-__global__ void __launch_bounds__(kGatherThreads, 2) k_gather(const __grid_constant__ GatherArgs a) {
+__global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const __grid_constant__ GatherArgs a) {
     const Geometry& c_geo = a.geo;
+    __shared__ float tbl[kBlobTable];          // static: its shared address is a compile-time constant
     extern __shared__ __align__(16) unsigned char smem[];
-    float* tbl = reinterpret_cast<float*>(smem);
-    Hit* hits = reinterpret_cast<Hit*>(smem + kBlobTable * sizeof(float));
-    int* sInt = reinterpret_cast<int*>(smem + kBlobTable * sizeof(float) + kMaxPlanes * sizeof(Hit));
+    Hit* hits = reinterpret_cast<Hit*>(smem);
+    int* sInt = reinterpret_cast<int*>(smem + kMaxPlanes * sizeof(Hit));
     // sInt[0..15] warp counts, sInt[32] tile, sInt[33] running hit count
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -218,6 +264,13 @@ __global__ void __launch_bounds__(kGatherThreads, 2) k_gather(const __grid_const
 
     const int Z = c_geo.Z, lo = c_geo.lo, hi = c_geo.hi;
     const float r2 = c_geo.r2, rho = c_geo.rho, s2 = c_geo.s2, iDelta = c_geo.iDelta, rr = c_geo.r;
+    const float kI = s2 * iDelta, sMax = c_geo.sMax;
+    // shared byte address of tbl[0] minus (bits(2^23) << 2), modulo 2^32 (see the lookup below)
+    // Routed through shared memory so that the compiler treats it as an opaque value: the lookup address
+    // then costs a single LEA (bits << 2) + tblAdj.
+    if (threadIdx.x == 0) sInt[40] = (int)((uint32_t)__cvta_generic_to_shared(tbl) - (0x4B000000u << 2));
+    __syncthreads();
+    const uint32_t tblAdj = (uint32_t)((volatile int*)sInt)[40];
     const int Rp = c_geo.Rp, side = c_geo.side;
     // voxel owned by this thread inside the tile: warp -> 4x4x2 brick, lane -> voxel in brick
     const int vx = ((warp & 1) << 2) | (lane & 3);
@@ -309,24 +362,28 @@ __global__ void __launch_bounds__(kGatherThreads, 2) k_gather(const __grid_const
                 const int iw = __float2int_ru(br - rho);
                 const int jAbs = H.ja0 + jw + Rp, iAbs = H.jb0 + iw + Rp;   // slice coordinates of the window origin
                 if ((unsigned)jAbs <= (unsigned)(side - K) && (unsigned)iAbs <= (unsigned)(side - K)) {
-                    float dx2[K], dy2[K];
+                    // squared distances pre-scaled by iDelta: S = d^2 * iDelta is directly the table coordinate
+                    float dxs[K], dys[K];
                     const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
+                    const float h2s = h2 * iDelta;
 #pragma unroll
                     for (int q = 0; q < K; ++q) {
                         float da = da0 - (float)q, db = db0 - (float)q;
-                        dx2[q] = s2 * da * da;
-                        dy2[q] = fmaf(s2 * db, db, h2);
+                        dxs[q] = kI * da * da;
+                        dys[q] = fmaf(kI * db, db, h2s);
                     }
-                    const float4* p = a.slices + (size_t)pl.img * a.sliceStride + (size_t)iAbs * side + jAbs;
+                    const float4* p = a.slices + ((size_t)pl.img * a.sliceStride + (size_t)(iAbs * side + jAbs));
 #pragma unroll
                     for (int ti = 0; ti < K; ++ti) {
 #pragma unroll
                         for (int tj = 0; tj < K; ++tj) {
-                            const float d2 = dy2[ti] + dx2[tj];
-                            if (d2 <= r2) {
-                                // (int)(d2*iDelta + 0.5) of RF.cpp:725 via the 2^23 trick (round to nearest)
-                                const int idx = __float_as_int(fmaf(d2, iDelta, 8388608.0f)) & 0x7fffff;
-                                const float w = tbl[idx];
+                            const float S = dys[ti] + dxs[tj];
+                            if (S <= sMax) {
+                                // (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in
+                                // the mantissa; (bits << 2) + tblAdj is then the shared-memory byte address of the entry
+                                const uint32_t addr = (__float_as_uint(S + 8388608.0f) << 2) + tblAdj;
+                                float w;
+                                asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(addr));
                                 const float4 px = __ldg(p + tj);
                                 accRe = fmaf(w, px.x, accRe);
                                 accIm = fmaf(w, px.y, accIm);

@@ -7,7 +7,7 @@ namespace rfb200 {
 
 constexpr int kTile = 8;                     // voxels per tile edge (tile = 8^3 = 512 voxels = one CTA)
 constexpr int kTileVox = kTile * kTile * kTile;
-constexpr int kMaxPlanes = 1024;             // (image, symmetry) planes per gather launch; fits __constant__
+constexpr int kMaxPlanes = 512;              // (image, symmetry) planes per gather launch; fits __constant__
 constexpr int kBlobTable = 10000;            // BLOB_TABLE_SIZE_SQRT (reconstruct_fourier.h:41-44)
 constexpr int kMaxWin = 8;                   // largest candidate window edge supported by the gather
 
@@ -81,6 +81,7 @@ struct Geometry {
     float r2;                      // blob radius^2 (voxel units)
     float r;                       // blob radius
     float iDelta;                  // (T-1)/r^2
+    float sMax;                    // r^2 * iDelta: largest scaled squared distance inside the blob
     float reach;                   // maxRes*Z + r: no lattice point farther than this is touched
     float inplane_reach;           // R + rho (pixel units)
 };
