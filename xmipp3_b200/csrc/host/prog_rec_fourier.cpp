@@ -1,0 +1,424 @@
+// prog_rec_fourier.cpp — see prog_rec_fourier.h
+#include "prog_rec_fourier.h"
+
+#include <dlfcn.h>
+#include <libgen.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <thread>
+
+#include "image_io.h"
+#include "symmetries.h"
+
+namespace rfhost {
+
+namespace {
+
+// ---- the CUDA library, bound at run time
+struct Api {
+    void* lib = nullptr;
+    int (*create)(const rfb200_config*, rfb200_handle*) = nullptr;
+    void (*destroy)(rfb200_handle) = nullptr;
+    const char* (*last_error)(rfb200_handle) = nullptr;
+    int (*get_info)(rfb200_handle, rfb200_info*) = nullptr;
+    int (*insert_batch)(rfb200_handle, const float*, const rfb200_particle*, int32_t) = nullptr;
+    int (*finalize)(rfb200_handle, float*) = nullptr;
+    int (*get_timings)(rfb200_handle, rfb200_timings*) = nullptr;
+};
+
+std::string selfDir() {
+    Dl_info info;
+    if (dladdr((void*)&selfDir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.rfind('/');
+        if (s != std::string::npos) return p.substr(0, s);
+    }
+    return ".";
+}
+
+Api loadApi() {
+    Api a;
+    const char* env = getenv("RFB200_LIB");
+    std::vector<std::string> names;
+    if (env && *env) names.push_back(env);
+    names.push_back(selfDir() + "/librecfourier_b200.so");
+    names.push_back("librecfourier_b200.so");
+    std::string tried;
+    for (auto& n : names) {
+        a.lib = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (a.lib) break;
+        tried += "\n  " + n + ": " + (dlerror() ? dlerror() : "?");
+    }
+    if (!a.lib) throw ProgramError("cannot load the CUDA library librecfourier_b200.so (there is no CPU fallback):" + tried);
+#define BIND(field, sym)                                                     \
+    a.field = (decltype(a.field))dlsym(a.lib, sym);                          \
+    if (!a.field) throw ProgramError(std::string("symbol missing in librecfourier_b200.so: ") + sym);
+    BIND(create, "rfb200_create")
+    BIND(destroy, "rfb200_destroy")
+    BIND(last_error, "rfb200_last_error")
+    BIND(get_info, "rfb200_get_info")
+    BIND(insert_batch, "rfb200_insert_batch")
+    BIND(finalize, "rfb200_finalize")
+    BIND(get_timings, "rfb200_get_timings")
+#undef BIND
+    return a;
+}
+
+std::string dirOf(const std::string& path) {
+    size_t s = path.rfind('/');
+    return s == std::string::npos ? std::string() : path.substr(0, s);
+}
+
+bool fileExists(const std::string& p) { return access(p.c_str(), R_OK) == 0; }
+
+// CTF columns of one row (data/ctf.cpp:365-419 and 1172-1212), with the reference's defaults
+void ctfFromRow(const MetaData& md, size_t i, rfb200_particle& p) {
+    p.kV = md.getValueOrDefault("ctfVoltage", i, 100);
+    p.defocusU = md.getValueOrDefault("ctfDefocusU", i, 0);
+    p.defocusV = md.getValueOrDefault("ctfDefocusV", i, p.defocusU);
+    p.defocus_angle = md.getValueOrDefault("ctfDefocusAngle", i, 0);
+    p.Cs = md.getValueOrDefault("ctfSphericalAberration", i, 0);
+    p.Ca = md.getValueOrDefault("ctfChromaticAberration", i, 0);
+    p.espr = md.getValueOrDefault("ctfEnergyLoss", i, 0);
+    p.ispr = md.getValueOrDefault("ctfLensStability", i, 0);
+    p.alpha = md.getValueOrDefault("ctfConvergenceCone", i, 0);
+    p.DeltaF = md.getValueOrDefault("ctfLongitudinalDisplacement", i, 0);
+    p.DeltaR = md.getValueOrDefault("ctfTransversalDisplacement", i, 0);
+    p.Q0 = md.getValueOrDefault("ctfQ0", i, 0);
+    p.K = md.getValueOrDefault("ctfK", i, 1);
+    p.envR0 = md.getValueOrDefault("ctfEnvR0", i, 0);
+    p.envR1 = md.getValueOrDefault("ctfEnvR1", i, 0);
+    p.envR2 = md.getValueOrDefault("ctfEnvR2", i, 0);
+    p.phase_shift = md.getValueOrDefault("ctfPhaseShift", i, 0);
+    p.vpp_radius = md.getValueOrDefault("ctfVPPRadius", i, 0);
+}
+
+struct Args {
+    std::vector<std::string> v;
+    size_t find(const std::string& name) const {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i] == name) return i;
+        return std::string::npos;
+    }
+    // values following `name` up to the next option; an option is a token starting with '-' that is not a number
+    std::vector<std::string> values(const std::string& name) const {
+        std::vector<std::string> out;
+        size_t i = find(name);
+        if (i == std::string::npos) return out;
+        for (size_t k = i + 1; k < v.size(); ++k) {
+            const std::string& t = v[k];
+            bool isOpt = t.size() > 1 && t[0] == '-' && !(isdigit((unsigned char)t[1]) || t[1] == '.');
+            if (isOpt) break;
+            out.push_back(t);
+        }
+        return out;
+    }
+};
+
+double toDouble(const std::string& s, const std::string& opt) {
+    char* end = nullptr;
+    double v = strtod(s.c_str(), &end);
+    if (end == s.c_str() || *end) throw ProgramError("option " + opt + ": '" + s + "' is not a number");
+    return v;
+}
+
+}  // namespace
+
+std::string ProgRecFourierB200::usage() {
+    return
+        "Generate 3D reconstructions from projections using direct Fourier interpolation with arbitrary geometry.\n"
+        "Kaiser-windows are used for interpolation in Fourier space.  B200-native implementation of\n"
+        "xmipp_reconstruct_fourier / xmipp_cuda_reconstruct_fourier (same options).\n"
+        "   -i <md_file>                      : Metadata file with input projections\n"
+        "  [-o <volume_file=\"rec_fourier.vol\">] : Filename for output volume\n"
+        "  [--iter <iterations=1>]            : Number of iterations for weight correction (0 or 1)\n"
+        "  [--sym <symfile=c1>]               : Enforce symmetry in projections\n"
+        "  [--padding <proj=2.0> <vol=2.0>]   : Padding used for projections and volume\n"
+        "  [--max_resolution <p=0.5>]         : Max resolution (Nyquist=0.5)\n"
+        "  [--weight]                         : Use weights stored in the image metadata\n"
+        "  [--thr <threads=1> <rows=1>]       : Number of host threads reading images (rows is accepted and ignored)\n"
+        "  [--blob <radius=1.9> <order=0> <alpha=15>] : Blob parameters\n"
+        "  [--useCTF]                         : Use CTF information if present\n"
+        "  [--sampling <Ts=1>]                : sampling rate of the input images in Angstroms/pixel\n"
+        "  [--phaseFlipped]                   : Give this flag if images have been already phase flipped\n"
+        "  [--minCTF <ctf=0.01>]              : Minimum value of the CTF that will be inverted\n"
+        "  [--device <dev=0>]                 : GPU device to use\n"
+        "  [--bufferSize <size=1024>]         : Number of projections handed to the GPU per call\n"
+        "  [--fftOnGPU]                       : accepted for compatibility (the FFT always runs on the GPU)\n"
+        "  [--fast]                           : nearest-pixel insertion (not implemented on this path yet)\n"
+        "  [--prepare_fsc <fscfile>]          : Filename root for FSC files (not implemented on this path yet)\n"
+        "  [-v <verbosity=1>]\n";
+}
+
+void ProgRecFourierB200::readParams(int argc, const char* const* argv) {
+    Args a;
+    for (int i = 1; i < argc; ++i) a.v.push_back(argv[i]);
+    static const char* known[] = {"-i", "-o", "--iter", "--sym", "--padding", "--prepare_fsc", "--max_resolution", "--weight",
+                                  "--thr", "--blob", "--useCTF", "--sampling", "--phaseFlipped", "--minCTF", "--device",
+                                  "--bufferSize", "--fftOnGPU", "--fast", "-v", "-h", "--help"};
+    for (auto& t : a.v) {
+        bool isOpt = t.size() > 1 && t[0] == '-' && !(isdigit((unsigned char)t[1]) || t[1] == '.');
+        if (!isOpt) continue;
+        bool ok = false;
+        for (auto k : known) ok = ok || t == k;
+        if (!ok) throw ProgramError("unknown option " + t + "\n" + usage());
+    }
+    if (a.find("-h") != std::string::npos || a.find("--help") != std::string::npos) throw ProgramError(usage());
+    auto one = [&](const std::string& opt, std::string& dst) {
+        auto v = a.values(opt);
+        if (a.find(opt) != std::string::npos) {
+            if (v.empty()) throw ProgramError("option " + opt + " needs a value");
+            dst = v[0];
+        }
+    };
+    auto num = [&](const std::string& opt, size_t idx, double& dst) {
+        auto v = a.values(opt);
+        if (v.size() > idx) dst = toDouble(v[idx], opt);
+    };
+    one("-i", fn_sel);
+    if (fn_sel.empty()) throw ProgramError("-i <md_file> is required\n" + usage());
+    one("-o", fn_out);
+    one("--sym", fn_sym);
+    one("--prepare_fsc", fn_fsc);
+    do_weights = a.find("--weight") != std::string::npos;
+    num("--padding", 0, padding_factor_proj);
+    num("--padding", 1, padding_factor_vol);
+    num("--blob", 0, blob_radius);
+    double d;
+    d = blob_order; num("--blob", 1, d); blob_order = (int)d;
+    num("--blob", 2, blob_alpha);
+    num("--max_resolution", 0, maxResolution);
+    d = numThreads; {
+        auto v = a.values("--thr");
+        if (!v.empty()) {
+            if (v[0] == "all") d = std::max(1u, std::thread::hardware_concurrency());
+            else d = toDouble(v[0], "--thr");
+        }
+    }
+    numThreads = std::max(1, (int)d);
+    d = thrWidth; num("--thr", 1, d); thrWidth = (int)d;
+    d = NiterWeight; num("--iter", 0, d); NiterWeight = (int)d;
+    useCTF = a.find("--useCTF") != std::string::npos;
+    phaseFlipped = a.find("--phaseFlipped") != std::string::npos;
+    num("--minCTF", 0, minCTF);
+    if (useCTF) num("--sampling", 0, Ts);
+    d = device; num("--device", 0, d); device = (int)d;
+    d = bufferSize; num("--bufferSize", 0, d); bufferSize = std::max(1, (int)d);
+    fast = a.find("--fast") != std::string::npos;
+    d = verbose; num("-v", 0, d); verbose = (int)d;
+}
+
+void ProgRecFourierB200::show() const {
+    if (verbose <= 0) return;
+    std::cout << " =====================================================================\n"
+              << " Direct 3D reconstruction method using Kaiser windows as interpolators\n"
+              << " =====================================================================\n"
+              << " Input selfile             : " << fn_sel << "\n"
+              << " padding_factor_proj       : " << padding_factor_proj << "\n"
+              << " padding_factor_vol        : " << padding_factor_vol << "\n"
+              << " Output volume             : " << fn_out << "\n";
+    if (!fn_sym.empty()) std::cout << " Symmetry file for projections : " << fn_sym << "\n";
+    if (!fn_fsc.empty()) std::cout << " File root for FSC files: " << fn_fsc << "\n";
+    std::cout << (do_weights ? " Use weights stored in the image headers or doc file\n" : " Do NOT use weights\n");
+    if (useCTF)
+        std::cout << "Using CTF information\nSampling rate: " << Ts << "\nPhase flipped: " << phaseFlipped << "\nMinimum CTF: " << minCTF << "\n";
+    std::cout << "\n Interpolation Function"
+              << "\n   blrad                 : " << blob_radius
+              << "\n   blord                 : " << blob_order
+              << "\n   blalpha               : " << blob_alpha
+              << "\n max_resolution          : " << maxResolution
+              << "\n GPU device              : " << device
+              << "\n -----------------------------------------------------------------" << std::endl;
+}
+
+std::string ProgRecFourierB200::imageOfRow(const MetaData& md, size_t i, const std::string& mdDir) {
+    std::string name;
+    if (!md.getValue("image", i, name)) throw ProgramError("metadata has no 'image' column");
+    size_t idx;
+    std::string path, fmt;
+    parseImageName(name, idx, path, fmt);
+    if (!path.empty() && path[0] != '/' && !fileExists(path) && !mdDir.empty()) {
+        // relative to the metadata file
+        std::string cand = mdDir + "/" + path;
+        if (fileExists(cand)) {
+            size_t at = name.find('@');
+            return (at == std::string::npos ? std::string() : name.substr(0, at + 1)) + mdDir + "/" + name.substr(at == std::string::npos ? 0 : at + 1);
+        }
+    }
+    return name;
+}
+
+void ProgRecFourierB200::particleFromRow(const MetaData& md, size_t i, bool hasCtf, const std::string& mdDir, rfb200_particle& p) {
+    memset(&p, 0, sizeof p);
+    p.rot = md.getValueOrDefault("angleRot", i, 0);
+    p.tilt = md.getValueOrDefault("angleTilt", i, 0);
+    p.psi = md.getValueOrDefault("anglePsi", i, 0);
+    p.shift_x = md.getValueOrDefault("shiftX", i, 0);
+    p.shift_y = md.getValueOrDefault("shiftY", i, 0);
+    p.weight = md.getValueOrDefault("weight", i, 1);
+    p.kV = 100;
+    p.K = 1;
+    if (!hasCtf) return;
+    if (md.containsLabel("ctfDefocusU")) {
+        ctfFromRow(md, i, p);
+    } else if (md.containsLabel("ctfModel")) {
+        // indirection through a .ctfparam metadata file (data/ctf.cpp:388-395)
+        std::string fn;
+        md.getValue("ctfModel", i, fn);
+        if (!fn.empty() && fn[0] != '/' && !fileExists(fn) && !mdDir.empty() && fileExists(mdDir + "/" + fn)) fn = mdDir + "/" + fn;
+        MetaData ctf;
+        ctf.read(fn);
+        if (ctf.size() == 0) throw ProgramError("empty CTF model file " + fn);
+        ctfFromRow(ctf, 0, p);
+    }
+}
+
+void ProgRecFourierB200::run() {
+    show();
+    if (fast) throw ProgramError("--fast is not implemented on the B200 path yet");
+    if (!fn_fsc.empty()) throw ProgramError("--prepare_fsc is not implemented on the B200 path yet");
+    if (NiterWeight < 0 || NiterWeight > 1) throw ProgramError("--iter must be 0 or 1 on the B200 path");
+
+    // ---- produceSideinfo (RF.cpp:184-287)
+    MetaData SF;
+    try {
+        SF.read(fn_sel);
+    } catch (const std::exception& e) {
+        throw ProgramError(e.what());
+    }
+    SF.removeDisabled();
+    if (SF.size() == 0) throw ProgramError("no (enabled) images in " + fn_sel);
+    std::string mdPath = fn_sel.substr(fn_sel.find('@') == std::string::npos ? 0 : fn_sel.find('@') + 1);
+    const std::string mdDir = dirOf(mdPath);
+    ImageInfo info;
+    try {
+        info = readImageInfo(imageOfRow(SF, 0, mdDir));
+    } catch (const std::exception& e) {
+        throw ProgramError(e.what());
+    }
+    if (info.nx != info.ny) throw ProgramError("This algorithm only works for squared images");     // RF.cpp:202-203
+    const int N = info.nx;
+    std::vector<Mat3> sym;
+    if (!fn_sym.empty()) {
+        try {
+            sym = symmetryMatrices(fn_sym);
+        } catch (const std::exception& e) {
+            throw ProgramError(e.what());
+        }
+    }
+    const bool hasCtf = useCTF && (SF.containsLabel("ctfModel") || SF.containsLabel("ctfDefocusU"));     // RF.cpp:335-336
+
+    Api api = loadApi();
+    rfb200_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.abi_version = RFB200_ABI_VERSION;
+    cfg.img_size = N;
+    cfg.pad_proj = padding_factor_proj;
+    cfg.pad_vol = padding_factor_vol;
+    cfg.max_resolution = maxResolution;
+    cfg.blob_radius = blob_radius;
+    cfg.blob_alpha = blob_alpha;
+    cfg.blob_order = blob_order;
+    cfg.n_sym = (int)sym.size();
+    cfg.sym_matrices = sym.empty() ? nullptr : sym[0].data();
+    cfg.use_ctf = hasCtf ? 1 : 0;
+    cfg.phase_flipped = phaseFlipped ? 1 : 0;
+    cfg.sampling = Ts;
+    cfg.min_ctf = minCTF;
+    cfg.use_weights = do_weights ? 1 : 0;
+    cfg.n_iter_weight = NiterWeight;
+    cfg.fast = 0;
+    cfg.device = device;
+    cfg.max_batch = bufferSize;
+    rfb200_handle h = nullptr;
+    int rc = api.create(&cfg, &h);
+    if (rc != RFB200_OK) throw ProgramError(std::string("GPU initialisation failed: ") + api.last_error(nullptr));
+
+    // ---- processImages (RF.cpp:835-1013): batches of bufferSize particles; numThreads loader threads fill
+    // batch k+1 while the GPU works on batch k (insert_batch returns once the batch has been uploaded)
+    const size_t n = SF.size();
+    const size_t B = (size_t)bufferSize;
+    std::vector<float> buf[2];
+    std::vector<rfb200_particle> meta[2];
+    for (int k = 0; k < 2; ++k) {
+        buf[k].resize(B * (size_t)N * N);
+        meta[k].resize(B);
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    std::string loadError;
+    auto loadBatch = [&](size_t first, size_t cnt, int slot) {
+        std::atomic<size_t> next(0);
+        std::mutex errM;
+        auto worker = [&] {
+            for (;;) {
+                size_t k = next.fetch_add(1);
+                if (k >= cnt) return;
+                try {
+                    particleFromRow(SF, first + k, hasCtf, mdDir, meta[slot][k]);
+                    readImage2D(imageOfRow(SF, first + k, mdDir), &buf[slot][k * (size_t)N * N], N, N);
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> g(errM);
+                    if (loadError.empty()) loadError = e.what();
+                    return;
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < numThreads; ++t) th.emplace_back(worker);
+        worker();
+        for (auto& x : th) x.join();
+    };
+    int slot = 0;
+    size_t done = 0;
+    try {
+        for (size_t first = 0; first < n; first += B, slot ^= 1) {
+            size_t cnt = std::min(B, n - first);
+            loadBatch(first, cnt, slot);
+            if (!loadError.empty()) throw ProgramError(loadError);
+            rc = api.insert_batch(h, buf[slot].data(), meta[slot].data(), (int32_t)cnt);
+            if (rc != RFB200_OK) throw ProgramError(std::string("insert_batch failed: ") + api.last_error(h));
+            done += cnt;
+            if (verbose > 0) std::cout << "\r " << done << " / " << n << " images inserted" << std::flush;
+        }
+        if (verbose > 0) std::cout << std::endl;
+        // ---- correctWeight + finishComputations (RF.cpp:1056-1180)
+        std::vector<float> vol((size_t)N * N * N);
+        rc = api.finalize(h, vol.data());
+        if (rc != RFB200_OK) throw ProgramError(std::string("finalize failed: ") + api.last_error(h));
+        writeVolume(fn_out, vol.data(), N, N, N);                                               // RF.cpp:1179
+        if (verbose > 0) {
+            rfb200_timings t;
+            double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (api.get_timings(h, &t) == RFB200_OK)
+                std::cout << " GPU time (ms): h2d " << t.h2d_ms << ", pad " << t.preprocess_ms << ", fft " << t.fft2d_ms << ", slices "
+                          << t.slice_ms << ", gather " << t.gather_ms << ", edge " << t.edge_ms << ", finalize " << t.finalize_ms << "\n";
+            std::cout << " " << n << " images in " << secs << " s (" << n / secs << " images/s including file I/O)" << std::endl;
+        }
+    } catch (...) {
+        api.destroy(h);
+        closeImageCache();
+        throw;
+    }
+    api.destroy(h);
+    closeImageCache();
+}
+
+int ProgRecFourierB200::tryRun() {
+    try {
+        run();
+    } catch (const std::exception& e) {
+        std::cerr << "XMIPP_ERROR: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace rfhost
