@@ -110,6 +110,7 @@ struct rfb200_handle_s {
     cudaEvent_t evH2D[2] = {nullptr, nullptr}, evRawFree[2] = {nullptr, nullptr};
     bool rawBusy[2] = {false, false};
     float* dPad = nullptr;
+    float* dCoef = nullptr;          // B-spline coefficients of the chunk (allocated on first fractional shift)
     float2* dFft = nullptr;
     float4* dSlices = nullptr;
     float4* dCol0 = nullptr;
@@ -238,7 +239,8 @@ int get_plan2d(rfb200_handle h, int batch, cufftHandle* out) {
 }
 
 // fill one chunk's parameter slot on the host (double precision) and upload it
-int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, ParamSlot** slotOut, int* nPlanesOut) {
+int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, ParamSlot** slotOut, int* nPlanesOut, bool* anySplineOut) {
+    bool anySpline = false;
     ParamSlot& s = h->slots[h->slotIdx];
     h->slotIdx ^= 1;
     if (s.used) RF_CUDA(h, cudaEventSynchronize(s.done));
@@ -251,11 +253,24 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         double w = h->cfg.use_weights ? p.weight : 1.0;     // RF.cpp:374-381
         q.weight = (float)w;
         q.skip = (w == 0.0) ? 1 : 0;                        // RF.cpp:483-484
+        // readApplyGeo(only_apply_shifts): out(x) = in(x - shift).  Integer shifts are an exact circular
+        // shift; if either component is fractional the image goes through cubic B-spline interpolation.
         double rx = std::nearbyint(p.shift_x), ry = std::nearbyint(p.shift_y);
-        if (std::fabs(p.shift_x - rx) > 1e-9 || std::fabs(p.shift_y - ry) > 1e-9)
-            return fail(h, RFB200_ERR_UNSUPPORTED, "fractional shiftX/shiftY need the cubic B-spline path, which is not implemented yet");
-        q.shift_x = (int)rx;
-        q.shift_y = (int)ry;
+        bool integer = std::fabs(p.shift_x - rx) < 1e-9 && std::fabs(p.shift_y - ry) < 1e-9;
+        if (integer) {
+            q.mx = (int)(-rx);
+            q.my = (int)(-ry);
+            q.ux = q.uy = 0.f;
+            q.spline = 0;
+        } else {
+            double fx = std::floor(-p.shift_x), fy = std::floor(-p.shift_y);
+            q.mx = (int)fx;
+            q.my = (int)fy;
+            q.ux = (float)(-p.shift_x - fx);
+            q.uy = (float)(-p.shift_y - fy);
+            q.spline = 1;
+            anySpline = true;
+        }
         s.img[i] = q;
         if (h->cfg.use_ctf)
             s.ctf[i] = host::make_ctf(p.kV, p.defocusU, p.defocusV, p.defocus_angle, p.Cs, p.Ca, p.espr, p.ispr, p.alpha, p.DeltaF,
@@ -274,6 +289,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         RF_CUDA(h, cudaMemcpyAsync(h->dPlaneImg, s.planeImg, sizeof(int) * np, cudaMemcpyHostToDevice, h->compute));
     }
     s.used = true;
+    *anySplineOut = anySpline;
     *slotOut = &s;
     *nPlanesOut = np;
     return RFB200_OK;
@@ -284,12 +300,21 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
     const Geometry& g = h->geo;
     ParamSlot* slot = nullptr;
     int nPlanes = 0;
-    int rc = upload_chunk_params(h, meta, n, &slot, &nPlanes);
+    bool anySpline = false;
+    int rc = upload_chunk_params(h, meta, n, &slot, &nPlanes, &anySpline);
     if (rc) return rc;
     {
         StageTimer t(h, Stage::PAD, h->compute);
+        if (anySpline) {
+            if (!h->dCoef) RF_CUDA(h, cudaMalloc(&h->dCoef, sizeof(float) * (size_t)h->chunkImages * g.N * g.N));
+            dim3 pg((g.N + 127) / 128, n);
+            k_bspline_prefilter<<<pg, 128, 0, h->compute>>>(dRaw, h->dCoef, h->dImg, g.N, 0);
+            k_bspline_prefilter<<<pg, 128, 0, h->compute>>>(dRaw, h->dCoef, h->dImg, g.N, 1);
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 2;
+        }
         dim3 grid((g.N * g.N + 255) / 256, n);
-        k_pad_images<<<grid, 256, 0, h->compute>>>(dRaw, h->dPad, h->dImg, g.N, g.P);
+        k_pad_images<<<grid, 256, 0, h->compute>>>(dRaw, h->dCoef, h->dPad, h->dImg, g.N, g.P);
         RF_CUDA(h, cudaGetLastError());
     }
     {
@@ -400,7 +425,7 @@ void free_all(rfb200_handle h) {
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dRaw[0], h->dRaw[1],
-                   h->dPad, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlaneImg, h->dNorm,
+                   h->dPad, h->dCoef, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
@@ -586,7 +611,7 @@ int rfb200_get_info(rfb200_handle h, rfb200_info* info) {
     if (!h || !info) return RFB200_ERR_ARG;
     const Geometry& g = h->geo;
     info->N = g.N; info->P = g.P; info->Z = g.Z; info->X = g.X;
-    info->tiles_x = g.tx; info->tiles_y = g.ty; info->tiles_z = g.tz; info->tile = kTile;
+    info->tiles_x = g.tx; info->tiles_y = g.ty; info->tiles_z = g.tz; info->tile = kTileX;
     info->n_blocked = h->nBlocked;
     info->chunk_images = h->chunkImages;
     info->n_tiles_active = h->nTiles;

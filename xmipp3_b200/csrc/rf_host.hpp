@@ -259,8 +259,9 @@ inline Geometry make_geometry(int N, double padProj, double padVol, double maxRe
     g.X = g.Z / 2 + 1;
     g.hi = g.Z / 2;
     g.lo = -(g.Z - 1 - g.Z / 2);
-    g.tx = (g.Z / 2 + 1 + kTile - 1) / kTile;
-    g.ty = g.tz = (g.Z + kTile - 1) / kTile;
+    g.tx = (g.Z / 2 + 1 + kTileX - 1) / kTileX;
+    g.ty = (g.Z + kTileY - 1) / kTileY;
+    g.tz = (g.Z + kTileZ - 1) / kTileZ;
     g.yHalf = (g.Z % 2 == 0) ? g.Z / 2 - 1 : g.Z / 2;
     double rho = r * g.P / (double)g.Z;
     g.rho = (float)rho;
@@ -278,18 +279,19 @@ inline Geometry make_geometry(int N, double padProj, double padVol, double maxRe
     return g;
 }
 
-// local voxel (vx,vy,vz) in [0,8)^3 -> slot inside a tile.  A warp owns a 4x4x2 brick so that its 32
-// voxels are compact in space (fewer wasted lanes per plane) and its 32 slots are contiguous in memory.
+// local voxel (vx,vy,vz) in [0,16)x[0,16)x[0,8) -> slot inside a tile: brick * 32 + lane.  A warp owns a 4x4x2
+// brick so that its 32 voxels are compact in space (fewer wasted lanes per plane) and its 32 slots are
+// contiguous in memory.
 inline int tile_slot(int vx, int vy, int vz) {
-    int warp = (vx >> 2) | ((vy >> 2) << 1) | ((vz >> 1) << 2);
+    int brick = (vx >> 2) | ((vy >> 2) << 2) | ((vz >> 1) << 4);
     int lane = (vx & 3) | ((vy & 3) << 2) | ((vz & 1) << 4);
-    return warp * 32 + lane;
+    return brick * 32 + lane;
 }
 // blocked index of centred lattice point (ux in [0,Z/2], uy,uz in [lo,hi])
 inline int64_t blocked_index(const Geometry& g, int ux, int uy, int uz) {
     int x = ux, y = uy - g.lo, z = uz - g.lo;
-    int64_t tile = ((int64_t)(z / kTile) * g.ty + (y / kTile)) * g.tx + (x / kTile);
-    return tile * kTileVox + tile_slot(x % kTile, y % kTile, z % kTile);
+    int64_t tile = ((int64_t)(z / kTileZ) * g.ty + (y / kTileY)) * g.tx + (x / kTileX);
+    return tile * kTileVox + tile_slot(x % kTileX, y % kTileY, z % kTileZ);
 }
 inline int centred(const Geometry& g, int stored) { return stored <= g.Z / 2 ? stored : stored - g.Z; }
 
@@ -311,9 +313,9 @@ inline std::vector<int32_t> build_tile_list(const Geometry& g) {
     for (int tz = 0; tz < g.tz; ++tz)
         for (int ty = 0; ty < g.ty; ++ty)
             for (int tx = 0; tx < g.tx; ++tx) {
-                int x0 = tx * kTile, x1 = std::min(x0 + kTile - 1, g.Z / 2);
-                int y0 = g.lo + ty * kTile, y1 = std::min(y0 + kTile - 1, g.hi);
-                int z0 = g.lo + tz * kTile, z1 = std::min(z0 + kTile - 1, g.hi);
+                int x0 = tx * kTileX, x1 = std::min(x0 + kTileX - 1, g.Z / 2);
+                int y0 = g.lo + ty * kTileY, y1 = std::min(y0 + kTileY - 1, g.hi);
+                int z0 = g.lo + tz * kTileZ, z1 = std::min(z0 + kTileZ - 1, g.hi);
                 auto axis = [](int a, int b) { return (a > 0) ? (double)a : (b < 0 ? (double)-b : 0.0); };
                 double dx = axis(x0, x1), dy = axis(y0, y1), dz = axis(z0, z1);
                 double d = std::sqrt(dx * dx + dy * dy + dz * dz);

@@ -27,14 +27,14 @@ __device__ __forceinline__ int d_wrap(int x, int n) {
     return r < 0 ? r + n : r;
 }
 __device__ __forceinline__ int d_tile_slot(int vx, int vy, int vz) {
-    int warp = (vx >> 2) | ((vy >> 2) << 1) | ((vz >> 1) << 2);
+    int brick = (vx >> 2) | ((vy >> 2) << 2) | ((vz >> 1) << 4);
     int lane = (vx & 3) | ((vy & 3) << 2) | ((vz & 1) << 4);
-    return warp * 32 + lane;
+    return brick * 32 + lane;
 }
 __device__ __forceinline__ int64_t d_blocked_index(const Geometry& geo, int ux, int uy, int uz) {
     int x = ux, y = uy - geo.lo, z = uz - geo.lo;
-    int64_t tile = ((int64_t)(z / kTile) * geo.ty + (y / kTile)) * geo.tx + (x / kTile);
-    return tile * kTileVox + d_tile_slot(x % kTile, y % kTile, z % kTile);
+    int64_t tile = ((int64_t)(z / kTileZ) * geo.ty + (y / kTileY)) * geo.tx + (x / kTileX);
+    return tile * kTileVox + d_tile_slot(x % kTileX, y % kTileY, z % kTileZ);
 }
 // natural lattice point owned by the tile gather? (host twin: host::main_owns)
 __device__ __forceinline__ bool d_main_owns(const Geometry& geo, int ux, int uy) {
@@ -45,18 +45,98 @@ __device__ __forceinline__ bool d_main_owns(const Geometry& geo, int ux, int uy)
 }
 
 // ================================================================== K1a
+// Cubic B-spline prefilter (Unser's recursive filter, pole sqrt(3)-2, mirror boundaries) for the images
+// whose shift is fractional: xmippCore's readApplyGeo interpolates with BSPLINE3.
+// One thread filters one line; `stride` selects rows (1) or columns (N).  Recursion state in double.
+__device__ __forceinline__ void d_bspline_line(float* c, int n, long stride) {
+    if (n == 1) return;
+    const double z1 = -0.26794919243112270647, lambda = 6.0;   // sqrt(3)-2, (1-z1)(1-1/z1)
+    const int horizon = 28;                                     // ceil(log(DBL_EPSILON)/log|z1|)
+    double sum;
+    if (horizon < n) {
+        double zn = z1;
+        sum = lambda * c[0];
+        for (int k = 1; k < horizon; ++k) { sum += zn * lambda * c[k * stride]; zn *= z1; }
+    } else {
+        double zn = z1, iz = 1.0 / z1, z2n = pow(z1, (double)(n - 1));
+        sum = lambda * c[0] + z2n * lambda * c[(n - 1) * stride];
+        z2n *= z2n * iz;
+        for (int k = 1; k <= n - 2; ++k) { sum += (zn + z2n) * lambda * c[k * stride]; zn *= z1; z2n *= iz; }
+        sum /= (1.0 - zn * zn);
+    }
+    // causal pass; the running value is kept in double, the line holds float
+    double prev = sum;
+    c[0] = (float)prev;
+    double last2 = prev;
+    for (int k = 1; k < n; ++k) {
+        double v = lambda * c[k * stride] + z1 * prev;
+        last2 = prev;
+        prev = v;
+        c[k * stride] = (float)v;
+    }
+    // anticausal pass
+    double nxt = (z1 / (z1 * z1 - 1.0)) * (z1 * last2 + prev);
+    c[(n - 1) * stride] = (float)nxt;
+    for (int k = n - 2; k >= 0; --k) {
+        nxt = z1 * (nxt - (double)c[k * stride]);
+        c[k * stride] = (float)nxt;
+    }
+}
+// grid (ceil(N/128), nImg): rows pass (axis 0) reads raw and writes coef, columns pass (axis 1) works in place
+__global__ void __launch_bounds__(128) k_bspline_prefilter(const float* __restrict__ raw, float* __restrict__ coef,
+                                                           const ImgParams* __restrict__ ip, int N, int axis) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int img = blockIdx.y;
+    if (t >= N || !ip[img].spline) return;
+    float* c = coef + (size_t)img * N * N;
+    if (axis == 0) {
+        const float* r = raw + (size_t)img * N * N + (size_t)t * N;
+        float* line = c + (size_t)t * N;
+        for (int k = 0; k < N; ++k) line[k] = r[k];
+        d_bspline_line(line, N, 1);
+    } else {
+        d_bspline_line(c + t, N, N);
+    }
+}
+
+__device__ __forceinline__ void d_bspline3_weights(float t, float w[4]) {
+    float t2 = t * t, t3 = t2 * t;
+    w[0] = (1.0f - 3.0f * t + 3.0f * t2 - t3) * (1.0f / 6.0f);
+    w[1] = (4.0f - 6.0f * t2 + 3.0f * t3) * (1.0f / 6.0f);
+    w[2] = (1.0f + 3.0f * t + 3.0f * t2 - 3.0f * t3) * (1.0f / 6.0f);
+    w[3] = t3 * (1.0f / 6.0f);
+}
+
 // grid (ceil(N*N/256), nImg).  The P x P buffer is zeroed once at create; the set of written
 // positions is the same for every image, so zeros never need rewriting.
-__global__ void __launch_bounds__(256) k_pad_images(const float* __restrict__ raw, float* __restrict__ pad,
-                                                    const ImgParams* __restrict__ ip, int N, int P) {
+__global__ void __launch_bounds__(256) k_pad_images(const float* __restrict__ raw, const float* __restrict__ coef,
+                                                    float* __restrict__ pad, const ImgParams* __restrict__ ip, int N, int P) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * N) return;
     int img = blockIdx.y;
     int i = idx / N, j = idx - i * N;
     ImgParams q = ip[img];
-    // content moves by +shift with wrap (readApplyGeo, only_apply_shifts; RF.cpp:313-314,362)
-    int si = d_wrap(i - q.shift_y, N), sj = d_wrap(j - q.shift_x, N);
-    float v = __ldg(raw + (size_t)img * N * N + (size_t)si * N + sj);
+    // content moves by +shift with wrap (readApplyGeo, only_apply_shifts; RF.cpp:313-314,362):
+    // out(x) = in(x - shift); x - shift = (j + mx) + ux
+    float v;
+    if (!q.spline) {
+        int si = d_wrap(i + q.my, N), sj = d_wrap(j + q.mx, N);
+        v = __ldg(raw + (size_t)img * N * N + (size_t)si * N + sj);
+    } else {
+        float wx[4], wy[4];
+        d_bspline3_weights(q.ux, wx);
+        d_bspline3_weights(q.uy, wy);
+        const float* c = coef + (size_t)img * N * N;
+        v = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float* row = c + (size_t)d_wrap(i + q.my - 1 + a, N) * N;
+            float r = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) r = fmaf(wx[b], __ldg(row + d_wrap(j + q.mx - 1 + b, N)), r);
+            v = fmaf(wy[a], r, v);
+        }
+    }
     // logical index l = i - N/2 lands on physical (l mod P): pad + CenterFFT fused (RF.cpp:390-402)
     int pi = d_wrap(i - N / 2, P), pj = d_wrap(j - N / 2, P);
     pad[(size_t)img * P * P + (size_t)pi * P + pj] = v;
@@ -244,11 +324,12 @@ struct GatherArgs {
     float* Wb;
 };
 
-constexpr int kGatherThreads = kTileVox;   // 512: one thread per voxel of the tile
+constexpr int kGatherThreads = 512;         // 16 warps; each warp takes bricks of the tile from a shared counter
 constexpr size_t kGatherSmem = kMaxPlanes * sizeof(Hit) + 64 * sizeof(int);   // dynamic part (the blob table is static)
 #ifndef RF_GATHER_CTAS
 #define RF_GATHER_CTAS 2
 #endif
+static_assert(kMaxPlanes <= kGatherThreads, "phase A maps one thread to one plane");
 
 template <int K>
 __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const __grid_constant__ GatherArgs a) {
@@ -257,7 +338,7 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
     extern __shared__ __align__(16) unsigned char smem[];
     Hit* hits = reinterpret_cast<Hit*>(smem);
     int* sInt = reinterpret_cast<int*>(smem + kMaxPlanes * sizeof(Hit));
-    // sInt[0..15] warp counts, sInt[32] tile, sInt[33] running hit count
+    // sInt[0..15] warp counts, sInt[32] tile, sInt[33] hit count, sInt[34] next brick, sInt[40] table address
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kBlobTable; i += kGatherThreads) tbl[i] = __ldg(a.blobTable + i);
@@ -265,48 +346,44 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
     const int Z = c_geo.Z, lo = c_geo.lo, hi = c_geo.hi;
     const float r2 = c_geo.r2, rho = c_geo.rho, s2 = c_geo.s2, iDelta = c_geo.iDelta, rr = c_geo.r;
     const float kI = s2 * iDelta, sMax = c_geo.sMax;
-    // shared byte address of tbl[0] minus (bits(2^23) << 2), modulo 2^32 (see the lookup below)
-    // Routed through shared memory so that the compiler treats it as an opaque value: the lookup address
-    // then costs a single LEA (bits << 2) + tblAdj.
+    // Shared byte address of tbl[0] minus (bits(2^23) << 2), modulo 2^32 (see the lookup below).  Routed through
+    // shared memory so that the compiler treats it as an opaque value: the lookup address is then one LEA.
     if (threadIdx.x == 0) sInt[40] = (int)((uint32_t)__cvta_generic_to_shared(tbl) - (0x4B000000u << 2));
     __syncthreads();
     const uint32_t tblAdj = (uint32_t)((volatile int*)sInt)[40];
     const int Rp = c_geo.Rp, side = c_geo.side;
-    // voxel owned by this thread inside the tile: warp -> 4x4x2 brick, lane -> voxel in brick
-    const int vx = ((warp & 1) << 2) | (lane & 3);
-    const int vy = (((warp >> 1) & 1) << 2) | ((lane >> 2) & 3);
-    const int vz = ((warp >> 2) << 1) | (lane >> 4);
-    const float vxf = (float)vx, vyf = (float)vy, vzf = (float)vz;
-    // tile-level culling constants
-    const float halfExt = 0.5f * (kTile - 1);
-    const float inplaneLim = c_geo.inplane_reach + halfExt * 1.7320508f * sqrtf(1.0f / s2) + 1.0f;
+    // lane -> voxel inside a 4x4x2 brick
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    // tile-level culling constants: half extents of the 16x16x8 lattice box around its centre
+    const float hx = 0.5f * (kTileX - 1), hy = 0.5f * (kTileY - 1), hz = 0.5f * (kTileZ - 1);
+    const float inplaneLim = c_geo.inplane_reach + sqrtf(hx * hx + hy * hy + hz * hz) * sqrtf(1.0f / s2) + 1.0f;
+    const float reach2 = c_geo.reach * c_geo.reach + 1.0f;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { sInt[32] = atomicAdd(a.tileCounter, 1); sInt[33] = 0; }
+        if (tid == 0) { sInt[32] = atomicAdd(a.tileCounter, 1); sInt[33] = 0; sInt[34] = 0; }
         __syncthreads();
         const int t = sInt[32];
         if (t >= a.nTiles) break;
         const int tileId = __ldg(a.tileList + t);
         const int ttx = tileId % c_geo.tx, tty = (tileId / c_geo.tx) % c_geo.ty, ttz = tileId / (c_geo.tx * c_geo.ty);
-        const int ox = ttx * kTile, oy = lo + tty * kTile, oz = lo + ttz * kTile;
+        const int ox = ttx * kTileX, oy = lo + tty * kTileY, oz = lo + ttz * kTileZ;
 
         // ---------------- phase A: which planes of the chunk come near this tile? (thread <-> plane)
-        const float cx = ox + halfExt, cy = oy + halfExt, cz = oz + halfExt;
-        for (int base = 0; base < a.nPlanes; base += kGatherThreads) {
-            const int k = base + tid;
+        {
+            const float cx = ox + hx, cy = oy + hy, cz = oz + hz;
+            const int k = tid;
             bool hit = false;
             Hit e;
             if (k < a.nPlanes) {
                 const float* s = a.planesSoA + k;
-                float nx = __ldg(s + 6 * kMaxPlanes), ny = __ldg(s + 7 * kMaxPlanes), nz = __ldg(s + 8 * kMaxPlanes);
-                float hc = cx * nx + cy * ny + cz * nz;
-                float supp = halfExt * (fabsf(nx) + fabsf(ny) + fabsf(nz));
+                const float nx = __ldg(s + 6 * kMaxPlanes), ny = __ldg(s + 7 * kMaxPlanes), nz = __ldg(s + 8 * kMaxPlanes);
+                const float hc = cx * nx + cy * ny + cz * nz;
+                const float supp = hx * fabsf(nx) + hy * fabsf(ny) + hz * fabsf(nz);
                 if (fabsf(hc) <= rr + supp + 1e-2f) {
                     float ac = cx * __ldg(s) + cy * __ldg(s + kMaxPlanes) + cz * __ldg(s + 2 * kMaxPlanes);
                     float bc = cx * __ldg(s + 3 * kMaxPlanes) + cy * __ldg(s + 4 * kMaxPlanes) + cz * __ldg(s + 5 * kMaxPlanes);
                     if (fabsf(ac) <= inplaneLim && fabsf(bc) <= inplaneLim) {
-                        hit = true;
                         const PlaneD pd = a.planesD[k];
                         double a0 = ox * pd.e1[0] + oy * pd.e1[1] + oz * pd.e1[2];
                         double b0 = ox * pd.e2[0] + oy * pd.e2[1] + oz * pd.e2[2];
@@ -318,14 +395,33 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
                         e.fa = (float)(a0 - ja);
                         e.fb = (float)(b0 - jb);
                         e.h0 = (float)h0;
+                        // brick mask: bricks whose 4x4x2 box comes within the blob radius of the plane
+                        const float bs = 1.5f * fabsf(nx) + 1.5f * fabsf(ny) + 0.5f * fabsf(nz) + rr + 1e-2f;
+                        const float hb0 = e.h0 + 1.5f * nx + 1.5f * ny + 0.5f * nz;   // centre of brick (0,0,0)
+                        uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+                        for (int bk = 0; bk < 4; ++bk)
+#pragma unroll
+                            for (int bj = 0; bj < 4; ++bj)
+#pragma unroll
+                                for (int bi = 0; bi < 4; ++bi) {
+                                    const float hb = hb0 + 4.0f * bi * nx + 4.0f * bj * ny + 2.0f * bk * nz;
+                                    const int b = bi | (bj << 2) | (bk << 4);
+                                    if (fabsf(hb) <= bs) {
+                                        if (b < 32) mlo |= 1u << b;
+                                        else mhi |= 1u << (b - 32);
+                                    }
+                                }
+                        e.maskLo = mlo;
+                        e.maskHi = mhi;
+                        hit = (mlo | mhi) != 0;
                     }
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (lane == 0) sInt[warp] = __popc(m);
             __syncthreads();
-            int off = sInt[33];
-            int total = 0;
+            int off = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < kGatherThreads / 32; ++w) {
                 int c = sInt[w];
@@ -333,72 +429,78 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
                 total += c;
             }
             if (hit) hits[off + __popc(m & ((1u << lane) - 1u))] = e;
-            __syncthreads();
-            if (tid == 0) sInt[33] += total;
+            if (tid == 0) sInt[33] = total;
         }
         __syncthreads();
         const int nHits = sInt[33];
         if (nHits == 0) continue;
 
-        // ---------------- phase B: every thread gathers for its own voxel
-        const int ux = ox + vx, uy = oy + vy, uz = oz + vz;
-        bool owned = (ux <= Z / 2) && (uy <= hi) && (uz <= hi) && d_main_owns(c_geo, ux, uy);
-        {
-            float d2o = (float)ux * ux + (float)uy * uy + (float)uz * uz;
-            owned = owned && (d2o <= c_geo.reach * c_geo.reach + 1.0f);
-        }
-        float accRe = 0.f, accIm = 0.f, accW = 0.f;
-        for (int eI = 0; eI < nHits; ++eI) {
-            const Hit H = hits[eI];
-            const PlaneF& pl = c_planes[H.k];
-            const float h = fmaf(vzf, pl.n[2], fmaf(vyf, pl.n[1], fmaf(vxf, pl.n[0], H.h0)));
-            const float h2 = h * h;
-            const bool in = owned && (h2 <= r2);
-            if (!__any_sync(0xffffffffu, in)) continue;
-            if (in) {
-                const float ar = fmaf(vzf, pl.e1[2], fmaf(vyf, pl.e1[1], fmaf(vxf, pl.e1[0], H.fa)));
-                const float br = fmaf(vzf, pl.e2[2], fmaf(vyf, pl.e2[1], fmaf(vxf, pl.e2[0], H.fb)));
-                const int jw = __float2int_ru(ar - rho);
-                const int iw = __float2int_ru(br - rho);
-                const int jAbs = H.ja0 + jw + Rp, iAbs = H.jb0 + iw + Rp;   // slice coordinates of the window origin
-                if ((unsigned)jAbs <= (unsigned)(side - K) && (unsigned)iAbs <= (unsigned)(side - K)) {
-                    // squared distances pre-scaled by iDelta: S = d^2 * iDelta is directly the table coordinate
-                    float dxs[K], dys[K];
-                    const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
-                    const float h2s = h2 * iDelta;
+        // ---------------- phase B: warps take bricks from a shared counter; every lane gathers for its own voxel
+        for (;;) {
+            int brick = 0;
+            if (lane == 0) brick = atomicAdd(&sInt[34], 1);
+            brick = __shfl_sync(0xffffffffu, brick, 0);
+            if (brick >= kBricks) break;
+            const int vx = ((brick & 3) << 2) | lx, vy = (((brick >> 2) & 3) << 2) | ly, vz = ((brick >> 4) << 1) | lz;
+            const int ux = ox + vx, uy = oy + vy, uz = oz + vz;
+            bool owned = (ux <= Z / 2) && (uy <= hi) && (uz <= hi) && d_main_owns(c_geo, ux, uy);
+            owned = owned && ((float)ux * ux + (float)uy * uy + (float)uz * uz <= reach2);
+            if (!__any_sync(0xffffffffu, owned)) continue;
+            const float vxf = (float)vx, vyf = (float)vy, vzf = (float)vz;
+            const uint32_t bitLo = brick < 32 ? (1u << brick) : 0u, bitHi = brick < 32 ? 0u : (1u << (brick - 32));
+            float accRe = 0.f, accIm = 0.f, accW = 0.f;
+            for (int eI = 0; eI < nHits; ++eI) {
+                const uint2 mk = *reinterpret_cast<const uint2*>(&hits[eI].maskLo);
+                if (((mk.x & bitLo) | (mk.y & bitHi)) == 0) continue;
+                const Hit H = hits[eI];
+                const PlaneF& pl = c_planes[H.k];
+                const float h = fmaf(vzf, pl.n[2], fmaf(vyf, pl.n[1], fmaf(vxf, pl.n[0], H.h0)));
+                const float h2 = h * h;
+                const bool in = owned && (h2 <= r2);
+                if (!__any_sync(0xffffffffu, in)) continue;
+                if (in) {
+                    const float ar = fmaf(vzf, pl.e1[2], fmaf(vyf, pl.e1[1], fmaf(vxf, pl.e1[0], H.fa)));
+                    const float br = fmaf(vzf, pl.e2[2], fmaf(vyf, pl.e2[1], fmaf(vxf, pl.e2[0], H.fb)));
+                    const int jw = __float2int_ru(ar - rho);
+                    const int iw = __float2int_ru(br - rho);
+                    const int jAbs = H.ja0 + jw + Rp, iAbs = H.jb0 + iw + Rp;   // slice coordinates of the window origin
+                    if ((unsigned)jAbs <= (unsigned)(side - K) && (unsigned)iAbs <= (unsigned)(side - K)) {
+                        // squared distances pre-scaled by iDelta: S = d^2 * iDelta is directly the table coordinate
+                        float dxs[K], dys[K];
+                        const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
+                        const float h2s = h2 * iDelta;
 #pragma unroll
-                    for (int q = 0; q < K; ++q) {
-                        float da = da0 - (float)q, db = db0 - (float)q;
-                        dxs[q] = kI * da * da;
-                        dys[q] = fmaf(kI * db, db, h2s);
-                    }
-                    const float4* p = a.slices + ((size_t)pl.img * a.sliceStride + (size_t)(iAbs * side + jAbs));
-#pragma unroll
-                    for (int ti = 0; ti < K; ++ti) {
-#pragma unroll
-                        for (int tj = 0; tj < K; ++tj) {
-                            const float S = dys[ti] + dxs[tj];
-                            if (S <= sMax) {
-                                // (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in
-                                // the mantissa; (bits << 2) + tblAdj is then the shared-memory byte address of the entry
-                                const uint32_t addr = (__float_as_uint(S + 8388608.0f) << 2) + tblAdj;
-                                float w;
-                                asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(addr));
-                                const float4 px = __ldg(p + tj);
-                                accRe = fmaf(w, px.x, accRe);
-                                accIm = fmaf(w, px.y, accIm);
-                                accW = fmaf(w, px.z, accW);
-                            }
+                        for (int q = 0; q < K; ++q) {
+                            float da = da0 - (float)q, db = db0 - (float)q;
+                            dxs[q] = kI * da * da;
+                            dys[q] = fmaf(kI * db, db, h2s);
                         }
-                        p += side;
+                        const float4* p = a.slices + ((size_t)pl.img * a.sliceStride + (size_t)(iAbs * side + jAbs));
+#pragma unroll
+                        for (int ti = 0; ti < K; ++ti) {
+#pragma unroll
+                            for (int tj = 0; tj < K; ++tj) {
+                                const float S = dys[ti] + dxs[tj];
+                                if (S <= sMax) {
+                                    // (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in
+                                    // the mantissa; (bits << 2) + tblAdj is then the shared-memory byte address of the entry
+                                    const uint32_t addr = (__float_as_uint(S + 8388608.0f) << 2) + tblAdj;
+                                    float w;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(addr));
+                                    const float4 px = __ldg(p + tj);
+                                    accRe = fmaf(w, px.x, accRe);
+                                    accIm = fmaf(w, px.y, accIm);
+                                    accW = fmaf(w, px.z, accW);
+                                }
+                            }
+                            p += side;
+                        }
                     }
                 }
             }
-        }
-        // ---------------- phase C: one coalesced read-modify-write of the tile (blocked layout)
-        if (owned) {
-            const size_t o = (size_t)tileId * kTileVox + tid;
-            if (accW != 0.f || accRe != 0.f || accIm != 0.f) {
+            // one coalesced read-modify-write of the brick (blocked layout: 32 consecutive slots)
+            if (owned && (accW != 0.f || accRe != 0.f || accIm != 0.f)) {
+                const size_t o = (size_t)tileId * kTileVox + (size_t)brick * 32 + lane;
                 float2 v = a.Vb[o];
                 v.x += accRe;
                 v.y += accIm;

@@ -5,8 +5,11 @@
 
 namespace rfb200 {
 
-constexpr int kTile = 8;                     // voxels per tile edge (tile = 8^3 = 512 voxels = one CTA)
-constexpr int kTileVox = kTile * kTile * kTile;
+// A tile is the unit of work of one CTA: 16 x 16 x 8 voxels = 64 bricks of 4 x 4 x 2 voxels.  A warp owns one
+// brick at a time (lane <-> voxel), so a brick is compact in space and its 32 accumulators are contiguous.
+constexpr int kTileX = 16, kTileY = 16, kTileZ = 8;
+constexpr int kTileVox = kTileX * kTileY * kTileZ;   // 2048
+constexpr int kBricks = kTileVox / 32;               // 64: one bit each in Hit::mask
 constexpr int kMaxPlanes = 512;              // (image, symmetry) planes per gather launch; fits __constant__
 constexpr int kBlobTable = 10000;            // BLOB_TABLE_SIZE_SQRT (reconstruct_fourier.h:41-44)
 constexpr int kMaxWin = 8;                   // largest candidate window edge supported by the gather
@@ -42,21 +45,21 @@ struct CtfConsts {
 
 struct ImgParams {         // per image of a chunk
     float weight;          // 1 or the metadata weight (RF.cpp:374-381)
-    int32_t shift_x;       // integer part of the shift (exact circular shift)
-    int32_t shift_y;
-    float frac_x;          // fractional part (cubic B-spline path), 0 for integer shifts
-    float frac_y;
+    int32_t mx, my;        // floor(-shiftX), floor(-shiftY): source pixel of destination j is j + mx (+ fraction)
+    float ux, uy;          // fractional parts of -shift in [0,1); both 0 on the exact (integer) path
+    int32_t spline;        // 1: cubic B-spline interpolation (a shift is fractional), 0: exact circular shift
     int32_t skip;          // weight == 0 -> image not inserted (RF.cpp:483-484)
-    int32_t pad0, pad1;
+    int32_t pad0;
 };
 
 // A CTA-level hit: plane `k` intersects the tile.  Tile-origin projection split into
 // integer pixel + fraction so that the per-voxel FP32 arithmetic only sees small numbers.
-struct Hit {
+struct Hit {                // 32 B
     int32_t k;             // plane index in the chunk
     int32_t ja0, jb0;      // rint(alpha0), rint(beta0) of the tile origin
     float fa, fb;          // alpha0 - ja0, beta0 - jb0   in [-0.5, 0.5]
     float h0;              // height of the tile origin
+    uint32_t maskLo, maskHi;   // bricks of the tile whose voxels can lie within the blob radius of the plane
 };
 
 // Edge work item: a lattice point that the main gather does not own (orig-only planes
