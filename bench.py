@@ -339,6 +339,10 @@ def main():
         r.reset()
         r.insert_host_ptr(host[0][0].data_ptr(), host[0][1])
         r.weight_sum()
+        if world > 1:
+            r.reduce(0)          # warm-up of the communicator (connection set-up happens on the first collective)
+        if rank == 0:
+            r.finalize()         # creates the 3-D FFT plan and the finalisation buffers
         r.reset()
         barrier()
         t0 = time.perf_counter()
@@ -363,8 +367,10 @@ def main():
         extra = {"e2e_insert_s": t_ins - t0, "e2e_reduce_s": t_red - t_ins, "e2e_finalize_s": t1 - t_red}
         if rank == 0 and vol is not None:
             extra["volume_finite"] = bool(np.isfinite(vol).all())
-        launches_e2e = int(r.timings()["kernel_launches"])
-        extra["gpu_launches_e2e"] = launches_e2e
+        tm2 = r.timings()
+        extra["gpu_launches_e2e"] = int(tm2["kernel_launches"])
+        extra["e2e_h2d_ms_per_step"] = tm2["h2d_ms"] / K
+        extra["e2e_h2d_GBps"] = (B * box * box * 4 / 1e9) / (tm2["h2d_ms"] / K * 1e-3) if tm2["h2d_ms"] > 0 else None
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu_baseline = None
