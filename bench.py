@@ -346,10 +346,16 @@ def main():
         r.reset()
         barrier()
         t0 = time.perf_counter()
+        t_call_ins = t_call_sum = 0.0
         for i in range(K):
             hbuf, p = host[i & 1]
+            ta = time.perf_counter()
             r.insert_host_ptr(hbuf.data_ptr(), p)
+            tb = time.perf_counter()
             r.weight_sum()                       # 8-byte D2H result per step
+            tc = time.perf_counter()
+            t_call_ins += tb - ta
+            t_call_sum += tc - tb
         t_ins = time.perf_counter()
         if world > 1:
             r.reduce(0)
@@ -364,11 +370,13 @@ def main():
                "h2d_bytes_per_step": int(B * box * box * 4 + B * 24 * 8),
                "d2h_bytes_per_step": int(8 + (box ** 3 * 4) // K),
                "includes": "H2D from pinned host memory, per-step 8-byte read-back, final reduce (N>1), normalise + 3-D IFFT + D2H of the volume"}
-        extra = {"e2e_insert_s": t_ins - t0, "e2e_reduce_s": t_red - t_ins, "e2e_finalize_s": t1 - t_red}
+        extra = {"e2e_insert_call_ms_per_step": 1e3 * t_call_ins / K, "e2e_result_call_ms_per_step": 1e3 * t_call_sum / K,
+                 "e2e_insert_s": t_ins - t0, "e2e_reduce_s": t_red - t_ins, "e2e_finalize_s": t1 - t_red}
         if rank == 0 and vol is not None:
             extra["volume_finite"] = bool(np.isfinite(vol).all())
         tm2 = r.timings()
         extra["gpu_launches_e2e"] = int(tm2["kernel_launches"])
+        extra["e2e_stage_ms_per_step"] = {k: tm2[k] / K for k in ("h2d_ms", "preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}
         extra["e2e_h2d_ms_per_step"] = tm2["h2d_ms"] / K
         extra["e2e_h2d_GBps"] = (B * box * box * 4 / 1e9) / (tm2["h2d_ms"] / K * 1e-3) if tm2["h2d_ms"] > 0 else None
 

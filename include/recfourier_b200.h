@@ -75,7 +75,7 @@ typedef struct {
     double sampling;          /* --sampling <Ts=1>                                           */
     double min_ctf;           /* --minCTF <0.01>                                             */
     int32_t use_weights;      /* --weight                                                    */
-    int32_t n_iter_weight;    /* --iter <1>: 0 or 1                                          */
+    int32_t n_iter_weight;    /* --iter <1>: 0 = no weight correction, >= 1 passes           */
     int32_t fast;             /* --fast (nearest-pixel insertion + final blob convolution)   */
     int32_t device;           /* CUDA device ordinal                                         */
     int32_t max_batch;        /* largest n passed to rfb200_insert_batch (0 = default 1024)  */
@@ -143,6 +143,11 @@ int rfb200_export_accumulators(rfb200_handle h, float* V, float* W);
  * FFT, crop and gridding correction.  out: N*N*N float32 in HOST memory, [z][y][x].
  * The accumulators are left untouched, so more batches may follow. */
 int rfb200_finalize(rfb200_handle h, float* out);
+
+/* Half-set support for --prepare_fsc (RF.cpp:991-1053): push saves the current accumulators aside and zeroes
+ * them (so the next particles form an independent half set); merge adds the saved half back. */
+int rfb200_halfset_push(rfb200_handle h);
+int rfb200_halfset_merge(rfb200_handle h);
 
 int rfb200_get_timings(rfb200_handle h, rfb200_timings* t);
 

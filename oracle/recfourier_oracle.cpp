@@ -311,6 +311,7 @@ struct Oracle {
     std::vector<double> W;  // FourierWeights
     Fft fftP, fftZ;
     long n_inserted = 0;
+    std::vector<orf_particle> history;   // every particle handed to insert(), for the --iter > 1 re-insertion passes
 
     explicit Oracle(const orf_config& c)
         : cfg(c), N(c.img_size), P(int(c.img_size * c.pad_proj)), Z(int(c.img_size * c.pad_vol)),
@@ -523,6 +524,54 @@ struct Oracle {
         }
     }
 
+    // Re-insertion pass of the weight refinement (reprocessFlag, RF.cpp:770-775): same geometry as the
+    // insertion, no image data, wModulator = 1; every pair adds w * slot[target] to the new weights.
+    void reprocess_all(const std::vector<double>& slot, std::vector<double>& Wn) const {
+        const int Xh = P / 2 + 1;
+        const double r = cfg.blob_radius, r2 = r * r;
+        const int xsize_1 = X - 1;
+        size_t conserveRows = (size_t)std::ceil((double)P * cfg.max_resolution * 2.0);
+        conserveRows = (size_t)std::ceil((double)conserveRows / 2.0);
+        for (const orf_particle& p : history) {
+            double weight = cfg.use_weights ? p.weight : 1.0;
+            if (weight == 0.0) continue;
+            M3 Ainv = transpose(euler_matrix(p.rot, p.tilt, p.psi));
+            for (size_t isym = 0; isym < R.size(); ++isym) {
+                M3 A_SL = matmul(R[isym], Ainv);
+                for (int i = 0; i < P; ++i) {
+                    if ((size_t)i >= conserveRows && (size_t)i < (size_t)P - conserveRows) continue;
+                    double fy = idx2digfreq(i, P);
+                    for (int j = 0; j < Xh; ++j) {
+                        double fx = idx2digfreq(j, P);
+                        if (fx * fx + fy * fy > maxRes2) continue;
+                        double px = (A_SL.m[0] * fx + A_SL.m[1] * fy) * Z, py = (A_SL.m[3] * fx + A_SL.m[4] * fy) * Z,
+                               pz = (A_SL.m[6] * fx + A_SL.m[7] * fy) * Z;
+                        int x0 = (int)std::ceil(px - r), x1 = (int)std::floor(px + r);
+                        int y0 = (int)std::ceil(py - r), y1 = (int)std::floor(py + r);
+                        int z0 = (int)std::ceil(pz - r), z1 = (int)std::floor(pz + r);
+                        for (int iz = z0; iz <= z1; ++iz) {
+                            double dz = iz - pz, z2 = dz * dz;
+                            int wz = wrap(iz, Z), wzn = wrap(-wz, Z);
+                            for (int iy = y0; iy <= y1; ++iy) {
+                                double dy = iy - py, y2z2 = dy * dy + z2;
+                                if (y2z2 > r2) continue;
+                                int wy = wrap(iy, Z), wyn = wrap(-wy, Z);
+                                for (int ix = x0; ix <= x1; ++ix) {
+                                    double dx = ix - px, d2 = dx * dx + y2z2;
+                                    if (d2 > r2) continue;
+                                    double w = blobTableSqrt[(int)(d2 * iDeltaSqrt + 0.5)] * weight;
+                                    int wx = wrap(ix, Z);
+                                    size_t idx = (wx > xsize_1) ? ((size_t)wzn * Z + wyn) * X + wrap(-wx, Z) : ((size_t)wz * Z + wy) * X + wx;
+                                    Wn[idx] += w * slot[idx];                      // RF.cpp:773-774
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
     // processImages — RF.cpp:835-1013 with the thread scheme of :137-151, :344, :829:
     // T persistent workers + the coordinating caller meet at a barrier before and after
     // every operation.  PRELOAD: each worker loads + FFTs one image.  PROCESS: every
@@ -549,6 +598,7 @@ struct Oracle {
     struct Loaded { std::vector<cd> F; M3 Ainv; double weight = 0; orf_particle p; bool read = false; };
 
     void insert(const float* imgs, const orf_particle* meta, int n, int T) {
+        history.insert(history.end(), meta, meta + n);
         if (T < 1) T = 1;
         const int minSep = std::max((int)std::ceil(cfg.blob_radius), 1) + 1;   // :296-303 with thrWidth=1
         // conserveRows — :927-928
@@ -705,6 +755,15 @@ struct Oracle {
         } else {
             // :1069-1099 with NiterWeight==1: slot = 1/W where |W|>1e-3, else it keeps Re(V)
             for (size_t k = 0; k < n; ++k) w[k] = (std::fabs(w[k]) > 1e-3) ? 1.0 / w[k] : v[k].real();
+            for (int it = 1; it < cfg.n_iter_weight; ++it) {        // :1080-1092
+                std::vector<double> Wn(n, 0.0);
+                reprocess_all(w, Wn);
+                std::swap(Wn, W);
+                force_weight_symmetry();
+                std::swap(Wn, W);
+                for (size_t k = 0; k < n; ++k)
+                    if (std::fabs(Wn[k]) > 1e-3) w[k] /= Wn[k];
+            }
         }
         enforce_hermitian(v);                                          // :1122
         double corr2D_3D = std::pow(cfg.pad_proj, 2.) / (N * std::pow(cfg.pad_vol, 3.));   // :457-458

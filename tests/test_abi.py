@@ -89,7 +89,7 @@ def test_argument_validation_needs_no_gpu():
         _lib.Reconstructor(32, blob=(1.9, 1, 15.0))
     assert e.value.code == _lib.ERR_ARG
     with pytest.raises(_lib.RecFourierError) as e:
-        _lib.Reconstructor(32, n_iter_weight=3)
+        _lib.Reconstructor(32, fast=True)
     assert e.value.code == _lib.ERR_UNSUPPORTED
 
 

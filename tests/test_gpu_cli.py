@@ -69,11 +69,34 @@ def test_cli_end_to_end_mrcs_symmetry(tmp_path, oracle_mod):
     assert np.nanmin(synth.fsc(vol, ref)[1:]) >= 0.999
 
 
+def test_cli_prepare_fsc_and_iter(tmp_path, oracle_mod):
+    """--prepare_fsc writes the two half-set maps (images [0, (n-1)/2] and the rest, RF.cpp:846, 991-1053) and
+    the full map; --iter 2 runs the weight refinement (RF.cpp:1080-1092)."""
+    N, n = 32, 51
+    d, md = _dataset(tmp_path, N, n, True, False, ".stk", seed=5)
+    out = str(tmp_path / "full.vol")
+    root = str(tmp_path / "fsc")
+    prog = ProgRecFourier(useCTF=True, Ts=d["sampling"], fn_fsc=root, NiterWeight=2, minCTF=0.2, bufferSize=16)
+    prog.setIO(md, out)
+    prog.run()
+    cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], **d["ctf"])
+    p = oracle_mod.make_particles(n, **cols)
+    split = (n - 1) // 2 + 1
+    kw = dict(use_ctf=True, sampling=d["sampling"], min_ctf=0.2, n_iter_weight=2)
+    for name, sl in ((root + "_1_recons.vol", slice(0, split)), (root + "_2_recons.vol", slice(split, n)), (out, slice(0, n))):
+        o = oracle_mod.Oracle(N, **kw)
+        o.insert(d["images"][sl], p[sl], threads=1)
+        ref = o.finalize()
+        vol = io.read_volume(name)
+        assert synth.rel_l2(vol, ref) <= 1e-4, name
+        assert np.nanmin(synth.fsc(vol, ref)[1:]) >= 0.999, name
+
+
 def test_cli_errors(tmp_path):
     N, n = 16, 4
     d, md = _dataset(tmp_path, N, n, False, False, ".stk")
-    prog = ProgRecFourier(NiterWeight=3)
+    prog = ProgRecFourier(maxResolution=0.9)
     prog.setIO(md, str(tmp_path / "x.vol"))
     with pytest.raises(RuntimeError) as e:
         prog.run()
-    assert "--iter" in str(e.value)
+    assert "max_resolution" in str(e.value)

@@ -68,6 +68,9 @@ CASES = [
     dict(N=32, n=50, n_iter_weight=0),              # --iter 0: no weight correction
     dict(N=32, n=60, ctf=True, phase_flipped=True),
     dict(N=32, n=60, ctf=True, min_ctf=0.2),
+    dict(N=32, n=40, ctf=True, min_ctf=0.3, n_iter_weight=2),    # --iter 2: weight refinement pass
+    dict(N=32, n=40, ctf=True, min_ctf=0.3, n_iter_weight=3),
+    dict(N=24, n=30, n_iter_weight=2, sym="c3"),
 ]
 
 

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_insert_batch", "rfb200_insert_batch_device", "rfb200_sync", "rfb200_reset",
     "rfb200_nccl_unique_id", "rfb200_nccl_init", "rfb200_reduce_nccl", "rfb200_accumulator_ptrs",
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
-    "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
+    "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice",
 ]
 
@@ -106,6 +106,8 @@ def load(build=True):
     L.rfb200_export_accumulators.argtypes = [H, C.c_void_p, C.c_void_p]
     L.rfb200_finalize.argtypes = [H, C.c_void_p]
     L.rfb200_get_timings.argtypes = [H, C.POINTER(Timings)]
+    L.rfb200_halfset_push.argtypes = [H]
+    L.rfb200_halfset_merge.argtypes = [H]
     L.rfb200_timer_start.argtypes = [H]
     L.rfb200_timer_stop.argtypes = [H, C.POINTER(C.c_double)]
     L.rfb200_weight_sum.argtypes = [H, C.POINTER(C.c_double)]
@@ -239,6 +241,12 @@ class Reconstructor:
         t = Timings()
         self._check(self._L.rfb200_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    def halfset_push(self):
+        self._check(self._L.rfb200_halfset_push(self._h))
+
+    def halfset_merge(self):
+        self._check(self._L.rfb200_halfset_merge(self._h))
 
     def timer_start(self):
         self._check(self._L.rfb200_timer_start(self._h))

@@ -31,6 +31,8 @@ struct Api {
     int (*get_info)(rfb200_handle, rfb200_info*) = nullptr;
     int (*insert_batch)(rfb200_handle, const float*, const rfb200_particle*, int32_t) = nullptr;
     int (*finalize)(rfb200_handle, float*) = nullptr;
+    int (*halfset_push)(rfb200_handle) = nullptr;
+    int (*halfset_merge)(rfb200_handle) = nullptr;
     int (*get_timings)(rfb200_handle, rfb200_timings*) = nullptr;
 };
 
@@ -67,6 +69,8 @@ Api loadApi() {
     BIND(get_info, "rfb200_get_info")
     BIND(insert_batch, "rfb200_insert_batch")
     BIND(finalize, "rfb200_finalize")
+    BIND(halfset_push, "rfb200_halfset_push")
+    BIND(halfset_merge, "rfb200_halfset_merge")
     BIND(get_timings, "rfb200_get_timings")
 #undef BIND
     return a;
@@ -139,7 +143,7 @@ std::string ProgRecFourierB200::usage() {
         "xmipp_reconstruct_fourier / xmipp_cuda_reconstruct_fourier (same options).\n"
         "   -i <md_file>                      : Metadata file with input projections\n"
         "  [-o <volume_file=\"rec_fourier.vol\">] : Filename for output volume\n"
-        "  [--iter <iterations=1>]            : Number of iterations for weight correction (0 or 1)\n"
+        "  [--iter <iterations=1>]            : Number of iterations for weight correction\n"
         "  [--sym <symfile=c1>]               : Enforce symmetry in projections\n"
         "  [--padding <proj=2.0> <vol=2.0>]   : Padding used for projections and volume\n"
         "  [--max_resolution <p=0.5>]         : Max resolution (Nyquist=0.5)\n"
@@ -154,7 +158,7 @@ std::string ProgRecFourierB200::usage() {
         "  [--bufferSize <size=1024>]         : Number of projections handed to the GPU per call\n"
         "  [--fftOnGPU]                       : accepted for compatibility (the FFT always runs on the GPU)\n"
         "  [--fast]                           : nearest-pixel insertion (not implemented on this path yet)\n"
-        "  [--prepare_fsc <fscfile>]          : Filename root for FSC files (not implemented on this path yet)\n"
+        "  [--prepare_fsc <fscfile>]          : Filename root for FSC files (<root>_1_recons.vol, <root>_2_recons.vol)\n"
         "  [-v <verbosity=1>]\n";
 }
 
@@ -284,8 +288,7 @@ void ProgRecFourierB200::particleFromRow(const MetaData& md, size_t i, bool hasC
 void ProgRecFourierB200::run() {
     show();
     if (fast) throw ProgramError("--fast is not implemented on the B200 path yet");
-    if (!fn_fsc.empty()) throw ProgramError("--prepare_fsc is not implemented on the B200 path yet");
-    if (NiterWeight < 0 || NiterWeight > 1) throw ProgramError("--iter must be 0 or 1 on the B200 path");
+    if (NiterWeight < 0) throw ProgramError("--iter must be >= 0");
 
     // ---- produceSideinfo (RF.cpp:184-287)
     MetaData SF;
@@ -379,21 +382,39 @@ void ProgRecFourierB200::run() {
     int slot = 0;
     size_t done = 0;
     try {
-        for (size_t first = 0; first < n; first += B, slot ^= 1) {
-            size_t cnt = std::min(B, n - first);
-            loadBatch(first, cnt, slot);
-            if (!loadError.empty()) throw ProgramError(loadError);
-            rc = api.insert_batch(h, buf[slot].data(), meta[slot].data(), (int32_t)cnt);
-            if (rc != RFB200_OK) throw ProgramError(std::string("insert_batch failed: ") + api.last_error(h));
-            done += cnt;
-            if (verbose > 0) std::cout << "\r " << done << " / " << n << " images inserted" << std::flush;
+        // --prepare_fsc (RF.cpp:846, 991-1053): images [0, FSCIndex] and (FSCIndex, n) are reconstructed as two
+        // independent half sets "<root>_1_recons.vol" / "<root>_2_recons.vol" before the full map is formed
+        const bool saveFSC = !fn_fsc.empty();
+        const size_t FSCIndex = (n - 1) / 2;
+        std::vector<float> vol((size_t)N * N * N);
+        auto insertRange = [&](size_t begin, size_t end) {
+            for (size_t first = begin; first < end; first += B, slot ^= 1) {
+                size_t cnt = std::min(B, end - first);
+                loadBatch(first, cnt, slot);
+                if (!loadError.empty()) throw ProgramError(loadError);
+                rc = api.insert_batch(h, buf[slot].data(), meta[slot].data(), (int32_t)cnt);
+                if (rc != RFB200_OK) throw ProgramError(std::string("insert_batch failed: ") + api.last_error(h));
+                done += cnt;
+                if (verbose > 0) std::cout << "\r " << done << " / " << n << " images inserted" << std::flush;
+            }
+        };
+        auto finish = [&](const std::string& name) {
+            rc = api.finalize(h, vol.data());                                                   // RF.cpp:1056-1180
+            if (rc != RFB200_OK) throw ProgramError(std::string("finalize failed: ") + api.last_error(h));
+            writeVolume(name, vol.data(), N, N, N);                                             // RF.cpp:1179
+        };
+        if (saveFSC) {
+            insertRange(0, FSCIndex + 1);
+            finish(fn_fsc + "_1_recons.vol");
+            if (api.halfset_push(h) != RFB200_OK) throw ProgramError(std::string("halfset_push failed: ") + api.last_error(h));
+            insertRange(FSCIndex + 1, n);
+            finish(fn_fsc + "_2_recons.vol");
+            if (api.halfset_merge(h) != RFB200_OK) throw ProgramError(std::string("halfset_merge failed: ") + api.last_error(h));
+        } else {
+            insertRange(0, n);
         }
         if (verbose > 0) std::cout << std::endl;
-        // ---- correctWeight + finishComputations (RF.cpp:1056-1180)
-        std::vector<float> vol((size_t)N * N * N);
-        rc = api.finalize(h, vol.data());
-        if (rc != RFB200_OK) throw ProgramError(std::string("finalize failed: ") + api.last_error(h));
-        writeVolume(fn_out, vol.data(), N, N, N);                                               // RF.cpp:1179
+        finish(fn_out);
         if (verbose > 0) {
             rfb200_timings t;
             double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -104,6 +104,10 @@ struct rfb200_handle_s {
     // accumulators (blocked layout)
     float2* dVb = nullptr;
     float* dWb = nullptr;
+    float* dWb2 = nullptr;          // only with use_ctf && n_iter_weight > 1
+    float2* dVsaved = nullptr;      // half-set snapshot (--prepare_fsc)
+    float* dWsaved = nullptr;
+    float* dW2saved = nullptr;
     int64_t nBlocked = 0;
     // per-chunk buffers
     float* dRaw[2] = {nullptr, nullptr};
@@ -206,8 +210,13 @@ void resolve_timings(rfb200_handle h) {
 
 template <int K>
 int launch_gather_k(rfb200_handle h, const GatherArgs& a, int grid) {
-    RF_CUDA(h, cudaFuncSetAttribute(k_gather<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
-    k_gather<K><<<grid, kGatherThreads, kGatherSmem, h->compute>>>(a);
+    if (a.Wb2) {
+        RF_CUDA(h, cudaFuncSetAttribute(k_gather<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
+        k_gather<K, true><<<grid, kGatherThreads, kGatherSmem, h->compute>>>(a);
+    } else {
+        RF_CUDA(h, cudaFuncSetAttribute(k_gather<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
+        k_gather<K, false><<<grid, kGatherThreads, kGatherSmem, h->compute>>>(a);
+    }
     RF_CUDA(h, cudaGetLastError());
     return RFB200_OK;
 }
@@ -367,7 +376,7 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
             a.blobTable = h->dBlobTable;
             a.planesD = h->dPlanesD + p0; a.planesSoA = h->dPlanesSoA; a.nPlanes = np;
             a.slices = h->dSlices; a.sliceStride = (size_t)g.side * g.side;
-            a.Vb = h->dVb; a.Wb = h->dWb;
+            a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
             rc = launch_gather(h, a, std::min(h->gatherGrid, h->nTiles));
             if (rc) return rc;
         }
@@ -379,7 +388,7 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
             e.planesD = h->dPlanesD + p0; e.planeImg = h->dPlaneImg + p0; e.nPlanes = np;
             e.blobTable = h->dBlobTable; e.slices = h->dSlices; e.col0 = h->dCol0;
             e.sliceStride = (size_t)g.side * g.side;
-            e.Vb = h->dVb; e.Wb = h->dWb;
+            e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
             e.iDeltaD = h->tables.iDeltaSqrt;
             k_edge<<<(h->nEdgeGroups + 127) / 128, 128, 0, h->compute>>>(e);
             RF_CUDA(h, cudaGetLastError());
@@ -405,7 +414,6 @@ int validate(const rfb200_config* c, std::string& why) {
     if (c->blob_order != 0 && c->blob_order != 2) { why = "blob order must be 0 or 2 (kaiser_Fourier_value, blobs.cpp:146)"; return RFB200_ERR_ARG; }
     if (c->n_sym < 0 || (c->n_sym > 0 && !c->sym_matrices)) { why = "symmetry matrices missing"; return RFB200_ERR_ARG; }
     if (c->n_iter_weight < 0) { why = "n_iter_weight must be >= 0"; return RFB200_ERR_ARG; }
-    if (c->n_iter_weight > 1) { why = "--iter > 1 (weight refinement passes) is not implemented on this path yet"; return RFB200_ERR_UNSUPPORTED; }
     if (c->fast) { why = "--fast is not implemented on this path yet"; return RFB200_ERR_UNSUPPORTED; }
     if (c->use_ctf && !(c->sampling > 0.0)) { why = "sampling must be positive with use_ctf"; return RFB200_ERR_ARG; }
     return RFB200_OK;
@@ -424,7 +432,7 @@ void free_all(rfb200_handle h) {
     if (h->hSum) cudaFreeHost(h->hSum);
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
-    void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dRaw[0], h->dRaw[1],
+    void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
                    h->dPad, h->dCoef, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut};
     for (void* p : dev) if (p) cudaFree(p);
@@ -517,6 +525,10 @@ int do_create(rfb200_handle h) {
     RF_CUDA(h, cudaMalloc(&h->dWb, sizeof(float) * h->nBlocked));
     RF_CUDA(h, cudaMemset(h->dVb, 0, sizeof(float2) * h->nBlocked));
     RF_CUDA(h, cudaMemset(h->dWb, 0, sizeof(float) * h->nBlocked));
+    if (c.use_ctf && c.n_iter_weight > 1) {
+        RF_CUDA(h, cudaMalloc(&h->dWb2, sizeof(float) * h->nBlocked));
+        RF_CUDA(h, cudaMemset(h->dWb2, 0, sizeof(float) * h->nBlocked));
+    }
 
     // ---- per-chunk buffers
     const size_t CH = h->chunkImages;
@@ -552,8 +564,8 @@ int do_create(rfb200_handle h) {
     switch (g.K) {
 #define OCC_CASE(KK)                                                                                              \
     case KK:                                                                                                      \
-        RF_CUDA(h, cudaFuncSetAttribute(k_gather<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem)); \
-        RF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather<KK>, kGatherThreads, kGatherSmem));  \
+        RF_CUDA(h, cudaFuncSetAttribute(k_gather<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem)); \
+        RF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather<KK, false>, kGatherThreads, kGatherSmem));  \
         break;
         OCC_CASE(1) OCC_CASE(2) OCC_CASE(3) OCC_CASE(4) OCC_CASE(5) OCC_CASE(6) OCC_CASE(7) OCC_CASE(8)
 #undef OCC_CASE
@@ -672,6 +684,7 @@ int rfb200_reset(rfb200_handle h) {
     if (rc) return rc;
     RF_CUDA(h, cudaMemsetAsync(h->dVb, 0, sizeof(float2) * h->nBlocked, h->compute));
     RF_CUDA(h, cudaMemsetAsync(h->dWb, 0, sizeof(float) * h->nBlocked, h->compute));
+    if (h->dWb2) RF_CUDA(h, cudaMemsetAsync(h->dWb2, 0, sizeof(float) * h->nBlocked, h->compute));
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
     for (double& m : h->ms) m = 0;
     h->nImages = h->nPlanes = h->nGatherLaunches = h->nKernelLaunches = 0;
@@ -722,6 +735,7 @@ int rfb200_reduce_nccl(rfb200_handle h, int32_t root) {
         StageTimer t(h, Stage::REDUCE, h->compute);
         ncclResult_t r1 = g_nccl.Reduce(h->dVb, h->dVb, (size_t)h->nBlocked * 2, ncclFloat, ncclSum, root, h->comm, h->compute);
         ncclResult_t r2 = g_nccl.Reduce(h->dWb, h->dWb, (size_t)h->nBlocked, ncclFloat, ncclSum, root, h->comm, h->compute);
+        if (h->dWb2 && r2 == ncclSuccess) r2 = g_nccl.Reduce(h->dWb2, h->dWb2, (size_t)h->nBlocked, ncclFloat, ncclSum, root, h->comm, h->compute);
         if (r1 != ncclSuccess || r2 != ncclSuccess) return fail(h, RFB200_ERR_NCCL, "ncclReduce failed");
     }
     return RFB200_OK;
@@ -777,7 +791,7 @@ int rfb200_finalize(rfb200_handle h, float* out) {
         StageTimer t(h, Stage::FINALIZE, h->compute);
         NormArgs a{};
         a.geo = g;
-        a.Vb = h->dVb; a.Wb = h->dWb; a.out = h->dNorm;
+        a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2 ? h->dWb2 : h->dWb; a.out = h->dNorm;
         a.corr = (float)(std::pow(c.pad_proj, 2.0) / (c.img_size * std::pow(c.pad_vol, 3.0)));   // RF.cpp:457-458
         a.nIterWeight = c.n_iter_weight;
         k_normalize<<<(unsigned)((nHalf + 255) / 256), 256, 0, h->compute>>>(a);
@@ -809,6 +823,38 @@ int rfb200_get_timings(rfb200_handle h, rfb200_timings* t) {
     t->planes = h->nPlanes;
     t->gather_launches = h->nGatherLaunches;
     t->kernel_launches = h->nKernelLaunches;
+    return RFB200_OK;
+}
+
+int rfb200_halfset_push(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!h->dVsaved) {
+        RF_CUDA(h, cudaMalloc(&h->dVsaved, sizeof(float2) * h->nBlocked));
+        RF_CUDA(h, cudaMalloc(&h->dWsaved, sizeof(float) * h->nBlocked));
+        if (h->dWb2) RF_CUDA(h, cudaMalloc(&h->dW2saved, sizeof(float) * h->nBlocked));
+    }
+    RF_CUDA(h, cudaMemcpyAsync(h->dVsaved, h->dVb, sizeof(float2) * h->nBlocked, cudaMemcpyDeviceToDevice, h->compute));
+    RF_CUDA(h, cudaMemcpyAsync(h->dWsaved, h->dWb, sizeof(float) * h->nBlocked, cudaMemcpyDeviceToDevice, h->compute));
+    RF_CUDA(h, cudaMemsetAsync(h->dVb, 0, sizeof(float2) * h->nBlocked, h->compute));
+    RF_CUDA(h, cudaMemsetAsync(h->dWb, 0, sizeof(float) * h->nBlocked, h->compute));
+    if (h->dWb2) {
+        RF_CUDA(h, cudaMemcpyAsync(h->dW2saved, h->dWb2, sizeof(float) * h->nBlocked, cudaMemcpyDeviceToDevice, h->compute));
+        RF_CUDA(h, cudaMemsetAsync(h->dWb2, 0, sizeof(float) * h->nBlocked, h->compute));
+    }
+    return RFB200_OK;
+}
+
+int rfb200_halfset_merge(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    if (!h->dVsaved) return fail(h, RFB200_ERR_STATE, "rfb200_halfset_push has not been called");
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int64_t n = h->nBlocked;
+    k_axpy<<<2048, 256, 0, h->compute>>>(reinterpret_cast<float*>(h->dVb), reinterpret_cast<const float*>(h->dVsaved), 2 * n);
+    k_axpy<<<2048, 256, 0, h->compute>>>(h->dWb, h->dWsaved, n);
+    if (h->dWb2) k_axpy<<<2048, 256, 0, h->compute>>>(h->dWb2, h->dW2saved, n);
+    RF_CUDA(h, cudaGetLastError());
+    h->nKernelLaunches += h->dWb2 ? 3 : 2;
     return RFB200_OK;
 }
 

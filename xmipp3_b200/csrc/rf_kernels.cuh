@@ -269,6 +269,7 @@ __device__ __forceinline__ float4 d_pixel_contrib(const float2* __restrict__ fft
     out.x = F.x * s;
     out.y = F.y * s;
     out.z = w;
+    out.w = weight;      // weight without the CTF modulator: what a --iter > 1 re-insertion pass adds (RF.cpp:770-775)
     return out;
 }
 
@@ -297,12 +298,12 @@ __global__ void __launch_bounds__(256, 4) k_make_slices(const float2* __restrict
         float4 c = d_pixel_contrib(f, jmax, sp, ctf, weight, j, ipx);
         if (j > 0) {
             S[(size_t)(ipx + sp.Rp) * sp.side + (j + sp.Rp)] = c;
-            S[(size_t)(-ipx + sp.Rp) * sp.side + (-j + sp.Rp)] = make_float4(c.x, -c.y, c.z, 0.f);
+            S[(size_t)(-ipx + sp.Rp) * sp.side + (-j + sp.Rp)] = make_float4(c.x, -c.y, c.z, c.w);
         } else {
             // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference
             // inserts this column twice for x > 0 voxels
             float4 m = d_pixel_contrib(f, jmax, sp, ctf, weight, 0, -ipx);
-            S[(size_t)(ipx + sp.Rp) * sp.side + sp.Rp] = make_float4(c.x + m.x, c.y - m.y, c.z + m.z, 0.f);
+            S[(size_t)(ipx + sp.Rp) * sp.side + sp.Rp] = make_float4(c.x + m.x, c.y - m.y, c.z + m.z, c.w + m.w);
             col0[(size_t)img * sp.side + (ipx + sp.Rp)] = c;
         }
     }
@@ -322,23 +323,27 @@ struct GatherArgs {
     size_t sliceStride;          // side*side
     float2* Vb;
     float* Wb;
+    float* Wb2;                  // un-modulated weight sum, only for --iter > 1 with CTF (else nullptr)
 };
 
-constexpr int kGatherThreads = 512;         // 16 warps; each warp takes bricks of the tile from a shared counter
+#ifndef RF_GATHER_THREADS
+#define RF_GATHER_THREADS 512
+#endif
+constexpr int kGatherThreads = RF_GATHER_THREADS;   // warps take bricks of the tile from a shared counter
 constexpr size_t kGatherSmem = kMaxPlanes * sizeof(Hit) + 64 * sizeof(int);   // dynamic part (the blob table is static)
 #ifndef RF_GATHER_CTAS
 #define RF_GATHER_CTAS 2
 #endif
 static_assert(kMaxPlanes <= kGatherThreads, "phase A maps one thread to one plane");
 
-template <int K>
+template <int K, bool kTwoW>
 __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const __grid_constant__ GatherArgs a) {
     const Geometry& c_geo = a.geo;
     __shared__ float tbl[kBlobTable];          // static: its shared address is a compile-time constant
     extern __shared__ __align__(16) unsigned char smem[];
     Hit* hits = reinterpret_cast<Hit*>(smem);
     int* sInt = reinterpret_cast<int*>(smem + kMaxPlanes * sizeof(Hit));
-    // sInt[0..15] warp counts, sInt[32] tile, sInt[33] hit count, sInt[34] next brick, sInt[40] table address
+    // sInt[0..31] warp counts, sInt[32] tile, sInt[33] hit count, sInt[34] next brick, sInt[40] table address
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kBlobTable; i += kGatherThreads) tbl[i] = __ldg(a.blobTable + i);
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
             if (!__any_sync(0xffffffffu, owned)) continue;
             const float vxf = (float)vx, vyf = (float)vy, vzf = (float)vz;
             const uint32_t bitLo = brick < 32 ? (1u << brick) : 0u, bitHi = brick < 32 ? 0u : (1u << (brick - 32));
-            float accRe = 0.f, accIm = 0.f, accW = 0.f;
+            float accRe = 0.f, accIm = 0.f, accW = 0.f, accW2 = 0.f;
             for (int eI = 0; eI < nHits; ++eI) {
                 const uint2 mk = *reinterpret_cast<const uint2*>(&hits[eI].maskLo);
                 if (((mk.x & bitLo) | (mk.y & bitHi)) == 0) continue;
@@ -491,6 +496,7 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
                                     accRe = fmaf(w, px.x, accRe);
                                     accIm = fmaf(w, px.y, accIm);
                                     accW = fmaf(w, px.z, accW);
+                                    if (kTwoW) accW2 = fmaf(w, px.w, accW2);
                                 }
                             }
                             p += side;
@@ -506,6 +512,7 @@ __global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const
                 v.y += accIm;
                 a.Vb[o] = v;
                 a.Wb[o] += accW;
+                if (kTwoW) a.Wb2[o] += accW2;
             }
         }
     }
@@ -526,6 +533,7 @@ struct EdgeArgs {
     size_t sliceStride;
     float2* Vb;
     float* Wb;
+    float* Wb2;                  // may be nullptr
     double iDeltaD;
 };
 
@@ -539,7 +547,7 @@ __global__ void __launch_bounds__(128) k_edge(const __grid_constant__ EdgeArgs a
     const double r2 = (double)c_geo.r * (double)c_geo.r, rho = c_geo.rho, s2 = c_geo.s2;
     const double lim = c_geo.inplane_reach;
     const int Rp = c_geo.Rp, side = c_geo.side, K = c_geo.K;
-    double accRe = 0, accIm = 0, accW = 0;
+    double accRe = 0, accIm = 0, accW = 0, accW2 = 0;
     const int i0 = a.groupStart[grp], i1 = a.groupStart[grp + 1];
     const int64_t store = a.items[i0].store;
     for (int it = i0; it < i1; ++it) {
@@ -574,16 +582,18 @@ __global__ void __launch_bounds__(128) k_edge(const __grid_constant__ EdgeArgs a
                     accRe += (double)w * px.x;
                     accIm += (double)w * px.y;
                     accW += (double)w * px.z;
+                    accW2 += (double)w * px.w;
                 }
             }
         }
     }
-    if (accW != 0 || accRe != 0 || accIm != 0) {
+    if (accW != 0 || accRe != 0 || accIm != 0 || accW2 != 0) {
         float2 v = a.Vb[store];
         v.x += (float)accRe;
         v.y += (float)accIm;
         a.Vb[store] = v;
         a.Wb[store] += (float)accW;
+        if (a.Wb2) a.Wb2[store] += (float)accW2;
     }
 }
 
@@ -592,6 +602,7 @@ struct NormArgs {
     Geometry geo;
     const float2* Vb;
     const float* Wb;
+    const float* Wb2;   // un-modulated weights for --iter > 1 (== Wb when no CTF modulators exist)
     float2* out;        // natural layout [z][y][x], Z*Z*X, input of the C2R transform
     float corr;         // corr2D_3D (RF.cpp:457-458)
     int nIterWeight;
@@ -610,6 +621,16 @@ __device__ __forceinline__ float2 d_norm_value(const NormArgs& a, int z, int y, 
     }
     if (a.nIterWeight == 0) return make_float2(v.x * a.corr, v.y * a.corr);
     float winv = (fabsf(w) > 1e-3f) ? 1.0f / w : v.x;          // RF.cpp:1076-1077 (incl. its quirk)
+    if (a.nIterWeight > 1) {
+        // weight refinement passes, RF.cpp:1080-1092: a re-insertion adds w*slot[target] for every pair, i.e.
+        // slot * (un-modulated weight sum of the voxel); where that exceeds 1e-3 the slot is divided by it
+        float w2 = a.Wb2[b];
+        if (x == 0 && uy <= c_geo.yHalf) w2 *= 0.5f;
+        for (int it = 1; it < a.nIterWeight; ++it) {
+            float wn = winv * w2;
+            if (fabsf(wn) > 1e-3f) winv /= wn;
+        }
+    }
     if (1.0f / winv > 1e-3f) {                                 // RF.cpp:472-473
         float s = a.corr * winv;
         return make_float2(v.x * s, v.y * s);
@@ -655,6 +676,11 @@ __global__ void __launch_bounds__(256) k_export(const __grid_constant__ Geometry
     if (x == 0 && uy <= c_geo.yHalf) { v.x *= 0.5f; v.y *= 0.5f; w *= 0.5f; }
     V[idx] = v;
     W[idx] = w;
+}
+
+// y += x (merging a saved half-set into the current accumulators)
+__global__ void __launch_bounds__(256) k_axpy(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
 }
 
 // deterministic two-stage FP64 sum of the weight accumulator (fixed grid, fixed tree)

@@ -18,6 +18,7 @@ class ProgRecFourier:
         self.fn_sel = None
         self.fn_out = "rec_fourier.vol"
         self.fn_sym = "c1"
+        self.fn_fsc = ""
         self.do_weights = False
         self.padding_factor_proj = 2.0
         self.padding_factor_vol = 2.0
@@ -46,6 +47,8 @@ class ProgRecFourier:
              "--max_resolution", repr(float(self.maxResolution)), "--thr", str(int(self.numThreads)),
              "--iter", str(int(self.NiterWeight)), "--minCTF", repr(float(self.minCTF)),
              "--device", str(int(self.device)), "--bufferSize", str(int(self.bufferSize))]
+        if self.fn_fsc:
+            a += ["--prepare_fsc", self.fn_fsc]
         if self.do_weights:
             a.append("--weight")
         if self.useCTF:
