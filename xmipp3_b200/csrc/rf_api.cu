@@ -122,6 +122,7 @@ struct rfb200_handle_s {
     CtfConsts* dCtf = nullptr;
     PlaneD* dPlanesD = nullptr;
     float* dPlanesSoA = nullptr;
+    PlaneF* dPlanesFStage = nullptr;   // device staging of the __constant__ plane table
     int* dPlaneImg = nullptr;
     ParamSlot slots[2];
     int slotIdx = 0;
@@ -144,6 +145,7 @@ struct rfb200_handle_s {
     int nRanks = 1, rank = 0;
     int gatherGrid = 0;             // resident CTAs of the persistent gather: SMs x occupancy
     cudaEvent_t swStart = nullptr, swStop = nullptr;
+    bool swStarted = false;
     double* dSum = nullptr;         // 1024 partials + 1 result
     double* hSum = nullptr;         // pinned
 };
@@ -199,13 +201,32 @@ struct StageTimer {   // records an event pair around a stage on a stream
     }
 };
 void resolve_timings(rfb200_handle h) {
+    static const bool trace = getenv("RFB200_TRACE") != nullptr;     // developer aid: stage timeline on stderr
+    static const char* names[] = {"h2d", "pad", "fft2d", "slice", "gather", "edge", "finalize", "reduce"};
     for (auto& p : h->pending) {
         float t = 0;
         if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) h->ms[p.stage] += t;
+        if (trace && h->swStarted) {
+            float t0 = 0, t1 = 0;
+            if (cudaEventElapsedTime(&t0, h->swStart, p.a) == cudaSuccess && cudaEventElapsedTime(&t1, h->swStart, p.b) == cudaSuccess)
+                fprintf(stderr, "[rfb200 trace] %-8s %9.3f -> %9.3f ms\n", names[p.stage], t0, t1);
+            else
+                cudaGetLastError();   // events recorded before the stopwatch started
+        }
         h->evPool.push_back(p.a);
         h->evPool.push_back(p.b);
     }
     h->pending.clear();
+}
+
+// copy `bytes` (rounded up to 16) from pinned host memory to device memory with a kernel on the compute stream
+int fetch_params(rfb200_handle h, void* dst, const void* srcPinned, size_t bytes) {
+    size_t n16 = (bytes + 15) / 16;
+    if (!n16) return RFB200_OK;
+    int blocks = (int)std::min<size_t>(64, (n16 + 255) / 256);
+    k_fetch_params<<<blocks, 256, 0, h->compute>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(srcPinned), n16);
+    RF_CUDA(h, cudaGetLastError());
+    return RFB200_OK;
 }
 
 template <int K>
@@ -291,12 +312,13 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
             ++np;
         }
     }
-    RF_CUDA(h, cudaMemcpyAsync(h->dImg, s.img, sizeof(ImgParams) * n, cudaMemcpyHostToDevice, h->compute));
-    if (h->cfg.use_ctf) RF_CUDA(h, cudaMemcpyAsync(h->dCtf, s.ctf, sizeof(CtfConsts) * n, cudaMemcpyHostToDevice, h->compute));
-    if (np) {
-        RF_CUDA(h, cudaMemcpyAsync(h->dPlanesD, s.planesD, sizeof(PlaneD) * np, cudaMemcpyHostToDevice, h->compute));
-        RF_CUDA(h, cudaMemcpyAsync(h->dPlaneImg, s.planeImg, sizeof(int) * np, cudaMemcpyHostToDevice, h->compute));
+    int rcf = fetch_params(h, h->dImg, s.img, sizeof(ImgParams) * n);
+    if (!rcf && h->cfg.use_ctf) rcf = fetch_params(h, h->dCtf, s.ctf, sizeof(CtfConsts) * n);
+    if (!rcf && np) {
+        rcf = fetch_params(h, h->dPlanesD, s.planesD, sizeof(PlaneD) * np);
+        if (!rcf) rcf = fetch_params(h, h->dPlaneImg, s.planeImg, sizeof(int) * np);
     }
+    if (rcf) return rcf;
     s.used = true;
     *anySplineOut = anySpline;
     *slotOut = &s;
@@ -365,8 +387,10 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
                 soaChunk[(6 + c) * kMaxPlanes + k] = f.n[c];
             }
         }
-        RF_CUDA(h, cudaMemcpyAsync(h->dPlanesSoA, soaChunk, sizeof(float) * 9 * kMaxPlanes, cudaMemcpyHostToDevice, h->compute));
-        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planes, slot->planesF + p0, sizeof(PlaneF) * np, 0, cudaMemcpyHostToDevice, h->compute));
+        rc = fetch_params(h, h->dPlanesSoA, soaChunk, sizeof(float) * 9 * kMaxPlanes);
+        if (!rc) rc = fetch_params(h, h->dPlanesFStage, slot->planesF + p0, sizeof(PlaneF) * np);
+        if (rc) return rc;
+        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planes, h->dPlanesFStage, sizeof(PlaneF) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
         RF_CUDA(h, cudaMemsetAsync(h->dTileCounter, 0, sizeof(int), h->compute));
         {
             StageTimer t(h, Stage::GATHER, h->compute);
@@ -433,7 +457,7 @@ void free_all(rfb200_handle h) {
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
-                   h->dPad, h->dCoef, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlaneImg, h->dNorm,
+                   h->dPad, h->dCoef, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlanesFStage, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
@@ -546,16 +570,17 @@ int do_create(rfb200_handle h) {
     RF_CUDA(h, cudaMalloc(&h->dCtf, sizeof(CtfConsts) * CH));
     const size_t maxPlanes = CH * h->nSymTot;
     const size_t nSub = (maxPlanes + kMaxPlanes - 1) / kMaxPlanes;
-    RF_CUDA(h, cudaMalloc(&h->dPlanesD, sizeof(PlaneD) * maxPlanes));
-    RF_CUDA(h, cudaMalloc(&h->dPlaneImg, sizeof(int) * maxPlanes));
+    RF_CUDA(h, cudaMalloc(&h->dPlanesD, sizeof(PlaneD) * maxPlanes + 16));
+    RF_CUDA(h, cudaMalloc(&h->dPlaneImg, sizeof(int) * maxPlanes + 16));
     RF_CUDA(h, cudaMalloc(&h->dPlanesSoA, sizeof(float) * 9 * kMaxPlanes));
+    RF_CUDA(h, cudaMalloc(&h->dPlanesFStage, sizeof(PlaneF) * kMaxPlanes));
     for (auto& s : h->slots) {
         RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
         RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));
-        RF_CUDA(h, cudaMallocHost(&s.planesD, sizeof(PlaneD) * maxPlanes));
+        RF_CUDA(h, cudaMallocHost(&s.planesD, sizeof(PlaneD) * maxPlanes + 16));
         RF_CUDA(h, cudaMallocHost(&s.planesF, sizeof(PlaneF) * maxPlanes));
         RF_CUDA(h, cudaMallocHost(&s.planesSoA, sizeof(float) * 9 * kMaxPlanes * nSub));
-        RF_CUDA(h, cudaMallocHost(&s.planeImg, sizeof(int) * maxPlanes));
+        RF_CUDA(h, cudaMallocHost(&s.planeImg, sizeof(int) * maxPlanes + 16));
         RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
     // persistent grid: as many CTAs as fit
@@ -864,6 +889,7 @@ int rfb200_timer_start(rfb200_handle h) {
     // make the compute stream wait for any copy still in flight so that the stopwatch starts "behind everything"
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
     RF_CUDA(h, cudaEventRecord(h->swStart, h->compute));
+    h->swStarted = true;
     return RFB200_OK;
 }
 

@@ -678,6 +678,13 @@ __global__ void __launch_bounds__(256) k_export(const __grid_constant__ Geometry
     W[idx] = w;
 }
 
+// Parameter upload by the SMs: reads the chunk's (small) parameter blocks straight from pinned, mapped host
+// memory.  A DMA copy would queue behind the 268 MB particle transfers of the copy stream in the single
+// host-to-device engine and stall the compute stream for milliseconds (seen in the stage timeline).
+__global__ void __launch_bounds__(256) k_fetch_params(uint4* __restrict__ dst, const uint4* __restrict__ srcHost, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = srcHost[i];
+}
+
 // y += x (merging a saved half-set into the current accumulators)
 __global__ void __launch_bounds__(256) k_axpy(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
