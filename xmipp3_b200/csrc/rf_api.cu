@@ -19,6 +19,7 @@
 #include "../../include/recfourier_b200.h"
 #include "rf_host.hpp"
 #include "rf_kernels.cuh"
+#include "rf_sticks.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -45,6 +46,11 @@ struct ParamSlot {      // pinned host staging for one chunk's parameters
     PlaneF* planesF = nullptr;
     float* planesSoA = nullptr;
     int* planeImg = nullptr;
+    // stick gather: class-sorted, (a,b,d)-permuted copies, one region per launch sub-range
+    PlaneD* planesDp = nullptr;
+    PlaneS* planesS = nullptr;
+    float* soaP = nullptr;
+    int* imgPlane0 = nullptr;
     cudaEvent_t done = nullptr;
     bool used = false;
 };
@@ -144,6 +150,24 @@ struct rfb200_handle_s {
 #endif
     int nRanks = 1, rank = 0;
     int gatherGrid = 0;             // resident CTAs of the persistent gather: SMs x occupancy
+    // ---- stick gather (default path; RFB200_GATHER=tiles selects the first-generation tile gather)
+    bool sticks = true;
+    float2* dSlices2 = nullptr;     // per image two float2 planes (A, and B = A shifted by one pixel)
+    float2* dCol02 = nullptr;
+    float* dDamped = nullptr;       // per image (2R+1) x (R+1) weights of the CTF-damped (flagged) pixels (use_ctf only)
+    float* dDamped2 = nullptr;      // their un-modulated weights (use_ctf && n_iter_weight > 1)
+    unsigned long long* dD = nullptr;   // blocked volume of 2^32 fixed-point damped-pixel weights (use_ctf only)
+    unsigned long long* dD2 = nullptr;  // same for the un-modulated weights
+    bool dampedDirty = false;
+    int32_t* dRimTab = nullptr;
+    StickUnit* dUnits[3] = {nullptr, nullptr, nullptr};
+    int nUnits[3] = {0, 0, 0};
+    int* dStickCounters = nullptr;  // 3 ints
+    PlaneD* dPlanesDp = nullptr;
+    float* dPlanesSoAp = nullptr;
+    PlaneS* dPlanesSStage = nullptr;
+    int* dImgPlane0 = nullptr;
+    int stickGrid = 0;
     cudaEvent_t swStart = nullptr, swStop = nullptr;
     bool swStarted = false;
     double* dSum = nullptr;         // 1024 partials + 1 result
@@ -255,6 +279,37 @@ int launch_gather(rfb200_handle h, const GatherArgs& a, int grid) {
     return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
 }
 
+template <int K>
+int launch_sticks_k(rfb200_handle h, const StickArgs& a, int grid) {
+    RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
+    k_gather_sticks<K><<<grid, kStickThreads, kStickSmem, h->compute>>>(a);
+    RF_CUDA(h, cudaGetLastError());
+    return RFB200_OK;
+}
+int launch_sticks(rfb200_handle h, const StickArgs& a, int grid) {
+    switch (h->geo.K) {
+        case 1: return launch_sticks_k<1>(h, a, grid);
+        case 2: return launch_sticks_k<2>(h, a, grid);
+        case 3: return launch_sticks_k<3>(h, a, grid);
+        case 4: return launch_sticks_k<4>(h, a, grid);
+        case 5: return launch_sticks_k<5>(h, a, grid);
+        case 6: return launch_sticks_k<6>(h, a, grid);
+        case 7: return launch_sticks_k<7>(h, a, grid);
+        case 8: return launch_sticks_k<8>(h, a, grid);
+    }
+    return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
+}
+
+// W += weights of the CTF-damped pixels; must run before W is read, reduced or copied
+int flush_deficit(rfb200_handle h) {
+    if (!h->dampedDirty || !h->dD) return RFB200_OK;
+    k_fold_damped<<<2048, 256, 0, h->compute>>>(h->dWb, h->dD, h->nBlocked);
+    if (h->dD2) k_fold_damped<<<2048, 256, 0, h->compute>>>(h->dWb2, h->dD2, h->nBlocked);
+    RF_CUDA(h, cudaGetLastError());
+    h->nKernelLaunches += h->dD2 ? 2 : 1;
+    h->dampedDirty = false;
+    return RFB200_OK;
+}
 
 int get_plan2d(rfb200_handle h, int batch, cufftHandle* out) {
     auto it = h->plans2d.find(batch);
@@ -302,6 +357,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
             anySpline = true;
         }
         s.img[i] = q;
+        if (s.imgPlane0) s.imgPlane0[i] = q.skip ? -1 : np;
         if (h->cfg.use_ctf)
             s.ctf[i] = host::make_ctf(p.kV, p.defocusU, p.defocusV, p.defocus_angle, p.Cs, p.Ca, p.espr, p.ispr, p.alpha, p.DeltaF,
                                       p.DeltaR, p.Q0, p.K, p.envR0, p.envR1, p.envR2, p.phase_shift, p.vpp_radius);
@@ -318,11 +374,125 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         rcf = fetch_params(h, h->dPlanesD, s.planesD, sizeof(PlaneD) * np);
         if (!rcf) rcf = fetch_params(h, h->dPlaneImg, s.planeImg, sizeof(int) * np);
     }
+    if (!rcf && h->sticks) {
+        // per launch sub-range: stable sort of the planes by class (axis dominating the normal), components
+        // permuted to the (a,b,d) order of the class
+        for (int p0 = 0; p0 < np; p0 += kMaxPlanes) {
+            const int cnt = std::min(kMaxPlanes, np - p0);
+            int start[4] = {0, 0, 0, 0};
+            for (int k = 0; k < cnt; ++k) start[host::plane_class(s.planesD[p0 + k]) + 1]++;
+            for (int c = 0; c < 3; ++c) start[c + 1] += start[c];
+            int fill[3] = {start[0], start[1], start[2]};
+            float* soa = s.soaP + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
+            for (int k = 0; k < cnt; ++k) {
+                const int cls = host::plane_class(s.planesD[p0 + k]);
+                const int pos = fill[cls]++;
+                const int img = s.planeImg[p0 + k];
+                host::permute_plane(s.planesD[p0 + k], cls, img, s.img[img].weight, s.planesDp[p0 + pos], s.planesS[p0 + pos]);
+                const PlaneS& f = s.planesS[p0 + pos];
+                const float comp[9] = {f.e1a, f.e1b, f.e1d, f.e2a, f.e2b, f.e2d, f.na, f.nb, f.nd};
+                for (int c = 0; c < 9; ++c) soa[c * kMaxPlanes + pos] = comp[c];
+            }
+        }
+        if (np) rcf = fetch_params(h, h->dPlanesDp, s.planesDp, sizeof(PlaneD) * np);
+        if (!rcf) rcf = fetch_params(h, h->dImgPlane0, s.imgPlane0, sizeof(int) * n);
+    }
     if (rcf) return rcf;
     s.used = true;
     *anySplineOut = anySpline;
     *slotOut = &s;
     *nPlanesOut = np;
+    return RFB200_OK;
+}
+
+SliceParams make_slice_params(rfb200_handle h) {
+    const Geometry& g = h->geo;
+    SliceParams sp{};
+    sp.P = g.P; sp.Xh = g.P / 2 + 1; sp.iLo = h->iLo; sp.iHi = h->iHi;
+    sp.R = g.R; sp.Rp = g.Rp; sp.side = g.side;
+    sp.useCtf = h->cfg.use_ctf; sp.phaseFlipped = h->cfg.phase_flipped;
+    const double aStep = (h->cfg.use_ctf ? 1.0 / h->cfg.sampling : 1.0) / (double)g.P;
+    sp.a2 = aStep * aStep;
+    sp.a = (float)aStep;
+    sp.minCtfF = (float)h->cfg.min_ctf;
+    sp.minCtf = h->cfg.min_ctf;
+    sp.invP2 = (float)(1.0 / ((double)g.P * (double)g.P));
+    return sp;
+}
+
+// K1b' -> K2' (one launch per plane class) -> K2e' -> K2r for the n images whose half-plane FFTs sit in dFft
+int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
+    const Geometry& g = h->geo;
+    int rc = RFB200_OK;
+    {
+        StageTimer t(h, Stage::SLICE, h->compute);
+        Slice2Args a{};
+        a.sp = make_slice_params(h);
+        a.pitch = g.pitch; a.planeStride = g.planeStride;
+        a.fft = h->dFft; a.slices = h->dSlices2; a.col0 = h->dCol02; a.damped = h->dDamped; a.damped2 = h->dDamped2;
+        a.ip = h->dImg; a.ctfs = h->dCtf; a.jmax = h->dJmax;
+        dim3 grid((g.R + 1 + 31) / 32, (2 * g.R + 1 + 8 * kSliceRowsPerThread - 1) / (8 * kSliceRowsPerThread), n);
+        k_make_slices2<<<grid, dim3(32, 8), 0, h->compute>>>(a);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+    }
+    for (int p0 = 0; p0 < nPlanes; p0 += kMaxPlanes) {
+        const int np = std::min(kMaxPlanes, nPlanes - p0);
+        const float* soaChunk = slot->soaP + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
+        rc = fetch_params(h, h->dPlanesSoAp, soaChunk, sizeof(float) * 9 * kMaxPlanes);
+        if (!rc) rc = fetch_params(h, h->dPlanesSStage, slot->planesS + p0, sizeof(PlaneS) * np);
+        if (rc) return rc;
+        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planesS, h->dPlanesSStage, sizeof(PlaneS) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
+        RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, 3 * sizeof(int), h->compute));
+        int start[4] = {0, 0, 0, 0};
+        for (int k = 0; k < np; ++k) start[host::plane_class(slot->planesD[p0 + k]) + 1]++;
+        for (int c = 0; c < 3; ++c) start[c + 1] += start[c];
+        {
+            StageTimer t(h, Stage::GATHER, h->compute);
+            // the three classes touch the same voxels: launches are serialised on the stream, each owns its sticks
+            for (int cls = 0; cls < 3; ++cls) {
+                if (start[cls + 1] == start[cls] || h->nUnits[cls] == 0) continue;
+                StickArgs a{};
+                a.geo = g;
+                a.units = h->dUnits[cls]; a.nUnits = h->nUnits[cls]; a.counter = h->dStickCounters + cls;
+                a.cls = cls; a.kBegin = start[cls]; a.kEnd = start[cls + 1];
+                a.blobTable = h->dBlobTable;
+                a.planesDp = h->dPlanesDp + p0; a.planesSoA = h->dPlanesSoAp;
+                a.slices = h->dSlices2; a.rimTab = h->dRimTab + g.Rp;
+                a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
+                rc = launch_sticks(h, a, std::min(h->stickGrid, (h->nUnits[cls] + kStickWarps - 1) / kStickWarps));
+                if (rc) return rc;
+                h->nKernelLaunches += 1;
+            }
+        }
+        if (h->nEdge) {
+            StageTimer t(h, Stage::EDGE, h->compute);
+            Edge2Args e{};
+            e.geo = g;
+            e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
+            e.planesD = h->dPlanesD + p0; e.planeImg = h->dPlaneImg + p0; e.img = h->dImg; e.nPlanes = np;
+            e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
+            e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
+            e.iDeltaD = h->tables.iDeltaSqrt;
+            k_edge2<<<(h->nEdgeGroups + 127) / 128, 128, 0, h->compute>>>(e);
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 1;
+        }
+        h->nGatherLaunches += 1;
+    }
+    if (h->dDamped && nPlanes) {
+        StageTimer t(h, Stage::EDGE, h->compute);
+        DampedArgs d{};
+        d.geo = g;
+        d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
+        d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
+        d.D = h->dD; d.D2 = h->dD2;
+        const int total = (g.R + 1) * (2 * g.R + 1);
+        k_damped_scatter<<<dim3((total + 255) / 256, n), 256, 0, h->compute>>>(d);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+        h->dampedDirty = true;
+    }
     return RFB200_OK;
 }
 
@@ -354,6 +524,15 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
         rc = get_plan2d(h, n, &plan);
         if (rc) return rc;
         RF_CUFFT(h, cufftExecR2C(plan, h->dPad, reinterpret_cast<cufftComplex*>(h->dFft)));
+    }
+    if (h->sticks) {
+        rc = insert_planes_sticks(h, slot, n, nPlanes);
+        if (rc) return rc;
+        RF_CUDA(h, cudaEventRecord(slot->done, h->compute));
+        h->nImages += n;
+        h->nPlanes += nPlanes;
+        h->lastChunkImages = n;
+        return RFB200_OK;
     }
     {
         StageTimer t(h, Stage::SLICE, h->compute);
@@ -458,10 +637,11 @@ void free_all(rfb200_handle h) {
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
                    h->dPad, h->dCoef, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlanesFStage, h->dPlaneImg, h->dNorm,
-                   h->dVol, h->dOut};
+                   h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
+                   h->dStickCounters, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
-        void* hp[] = {s.img, s.ctf, s.planesD, s.planesF, s.planesSoA, s.planeImg};
+        void* hp[] = {s.img, s.ctf, s.planesD, s.planesF, s.planesSoA, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0};
         for (void* p : hp) if (p) cudaFreeHost(p);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -500,6 +680,11 @@ int do_create(rfb200_handle h) {
     h->geo = host::make_geometry(c.img_size, c.pad_proj, c.pad_vol, c.max_resolution, c.blob_radius, R);
     Geometry& g = h->geo;
     if (g.K > kMaxWin) return fail(h, RFB200_ERR_ARG, "blob radius too large for the interpolation window (max 8 pixels)");
+    {
+        const char* e = getenv("RFB200_GATHER");      // developer switch: "tiles" = first-generation tile gather
+        h->sticks = !(e && std::string(e) == "tiles");
+    }
+    std::vector<int32_t> rimTab = host::build_rim_table(g, h->jmax, h->iLo, h->iHi);
     std::vector<int32_t> tiles = host::build_tile_list(g);
     std::vector<EdgeItem> edge = host::build_edge_items(g);
     h->nTiles = (int)tiles.size();
@@ -562,10 +747,38 @@ int do_create(rfb200_handle h) {
     RF_CUDA(h, cudaMalloc(&h->dPad, sizeof(float) * nPad));
     RF_CUDA(h, cudaMemset(h->dPad, 0, sizeof(float) * nPad));
     RF_CUDA(h, cudaMalloc(&h->dFft, sizeof(float2) * nFft));
-    RF_CUDA(h, cudaMalloc(&h->dSlices, sizeof(float4) * nSl));
-    RF_CUDA(h, cudaMemset(h->dSlices, 0, sizeof(float4) * nSl));
-    RF_CUDA(h, cudaMalloc(&h->dCol0, sizeof(float4) * nC0));
-    RF_CUDA(h, cudaMemset(h->dCol0, 0, sizeof(float4) * nC0));
+    if (!h->sticks) {
+        RF_CUDA(h, cudaMalloc(&h->dSlices, sizeof(float4) * nSl));
+        RF_CUDA(h, cudaMemset(h->dSlices, 0, sizeof(float4) * nSl));
+        RF_CUDA(h, cudaMalloc(&h->dCol0, sizeof(float4) * nC0));
+        RF_CUDA(h, cudaMemset(h->dCol0, 0, sizeof(float4) * nC0));
+    } else {
+        const size_t nSl2 = CH * 2 * (size_t)g.planeStride;
+        RF_CUDA(h, cudaMalloc(&h->dSlices2, sizeof(float2) * nSl2 + 64));
+        RF_CUDA(h, cudaMemset(h->dSlices2, 0, sizeof(float2) * nSl2 + 64));
+        RF_CUDA(h, cudaMalloc(&h->dCol02, sizeof(float2) * nC0));
+        RF_CUDA(h, cudaMemset(h->dCol02, 0, sizeof(float2) * nC0));
+        RF_CUDA(h, cudaMalloc(&h->dRimTab, sizeof(int32_t) * rimTab.size()));
+        RF_CUDA(h, cudaMemcpy(h->dRimTab, rimTab.data(), sizeof(int32_t) * rimTab.size(), cudaMemcpyHostToDevice));
+        if (c.use_ctf) {
+            RF_CUDA(h, cudaMalloc(&h->dDamped, sizeof(float) * CH * (size_t)(2 * g.R + 1) * (g.R + 1)));
+            RF_CUDA(h, cudaMalloc(&h->dD, sizeof(unsigned long long) * h->nBlocked));
+            RF_CUDA(h, cudaMemset(h->dD, 0, sizeof(unsigned long long) * h->nBlocked));
+            if (c.n_iter_weight > 1) {
+                RF_CUDA(h, cudaMalloc(&h->dDamped2, sizeof(float) * CH * (size_t)(2 * g.R + 1) * (g.R + 1)));
+                RF_CUDA(h, cudaMalloc(&h->dD2, sizeof(unsigned long long) * h->nBlocked));
+                RF_CUDA(h, cudaMemset(h->dD2, 0, sizeof(unsigned long long) * h->nBlocked));
+            }
+        }
+        for (int cls = 0; cls < 3; ++cls) {
+            std::vector<StickUnit> units = host::build_stick_units(g, cls);
+            h->nUnits[cls] = (int)units.size();
+            if (units.empty()) continue;
+            RF_CUDA(h, cudaMalloc(&h->dUnits[cls], sizeof(StickUnit) * units.size()));
+            RF_CUDA(h, cudaMemcpy(h->dUnits[cls], units.data(), sizeof(StickUnit) * units.size(), cudaMemcpyHostToDevice));
+        }
+        RF_CUDA(h, cudaMalloc(&h->dStickCounters, 3 * sizeof(int)));
+    }
     RF_CUDA(h, cudaMalloc(&h->dImg, sizeof(ImgParams) * CH));
     RF_CUDA(h, cudaMalloc(&h->dCtf, sizeof(CtfConsts) * CH));
     const size_t maxPlanes = CH * h->nSymTot;
@@ -574,6 +787,12 @@ int do_create(rfb200_handle h) {
     RF_CUDA(h, cudaMalloc(&h->dPlaneImg, sizeof(int) * maxPlanes + 16));
     RF_CUDA(h, cudaMalloc(&h->dPlanesSoA, sizeof(float) * 9 * kMaxPlanes));
     RF_CUDA(h, cudaMalloc(&h->dPlanesFStage, sizeof(PlaneF) * kMaxPlanes));
+    if (h->sticks) {
+        RF_CUDA(h, cudaMalloc(&h->dPlanesDp, sizeof(PlaneD) * maxPlanes + 16));
+        RF_CUDA(h, cudaMalloc(&h->dPlanesSoAp, sizeof(float) * 9 * kMaxPlanes));
+        RF_CUDA(h, cudaMalloc(&h->dPlanesSStage, sizeof(PlaneS) * kMaxPlanes));
+        RF_CUDA(h, cudaMalloc(&h->dImgPlane0, sizeof(int) * CH + 16));
+    }
     for (auto& s : h->slots) {
         RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
         RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));
@@ -581,6 +800,12 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMallocHost(&s.planesF, sizeof(PlaneF) * maxPlanes));
         RF_CUDA(h, cudaMallocHost(&s.planesSoA, sizeof(float) * 9 * kMaxPlanes * nSub));
         RF_CUDA(h, cudaMallocHost(&s.planeImg, sizeof(int) * maxPlanes + 16));
+        if (h->sticks) {
+            RF_CUDA(h, cudaMallocHost(&s.planesDp, sizeof(PlaneD) * maxPlanes + 16));
+            RF_CUDA(h, cudaMallocHost(&s.planesS, sizeof(PlaneS) * maxPlanes + 16));
+            RF_CUDA(h, cudaMallocHost(&s.soaP, sizeof(float) * 9 * kMaxPlanes * nSub));
+            RF_CUDA(h, cudaMallocHost(&s.imgPlane0, sizeof(int) * CH + 16));
+        }
         RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
     // persistent grid: as many CTAs as fit
@@ -599,6 +824,7 @@ int do_create(rfb200_handle h) {
     if (rcK) return fail(h, rcK, "unsupported interpolation window");
     if (occ < 1) occ = 1;
     h->gatherGrid = prop.multiProcessorCount * occ;
+    h->stickGrid = prop.multiProcessorCount;
     RF_CUDA(h, cudaDeviceSynchronize());
     return RFB200_OK;
 }
@@ -710,6 +936,9 @@ int rfb200_reset(rfb200_handle h) {
     RF_CUDA(h, cudaMemsetAsync(h->dVb, 0, sizeof(float2) * h->nBlocked, h->compute));
     RF_CUDA(h, cudaMemsetAsync(h->dWb, 0, sizeof(float) * h->nBlocked, h->compute));
     if (h->dWb2) RF_CUDA(h, cudaMemsetAsync(h->dWb2, 0, sizeof(float) * h->nBlocked, h->compute));
+    if (h->dD) RF_CUDA(h, cudaMemsetAsync(h->dD, 0, sizeof(unsigned long long) * h->nBlocked, h->compute));
+    if (h->dD2) RF_CUDA(h, cudaMemsetAsync(h->dD2, 0, sizeof(unsigned long long) * h->nBlocked, h->compute));
+    h->dampedDirty = false;
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
     for (double& m : h->ms) m = 0;
     h->nImages = h->nPlanes = h->nGatherLaunches = h->nKernelLaunches = 0;
@@ -756,6 +985,7 @@ int rfb200_reduce_nccl(rfb200_handle h, int32_t root) {
     if (!h) return RFB200_ERR_ARG;
     if (!h->comm) return fail(h, RFB200_ERR_STATE, "rfb200_nccl_init has not been called");
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
     {
         StageTimer t(h, Stage::REDUCE, h->compute);
         ncclResult_t r1 = g_nccl.Reduce(h->dVb, h->dVb, (size_t)h->nBlocked * 2, ncclFloat, ncclSum, root, h->comm, h->compute);
@@ -772,6 +1002,7 @@ int rfb200_reduce_nccl(rfb200_handle h, int32_t root) {
 
 int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_blocked) {
     if (!h) return RFB200_ERR_ARG;
+    if (int rcf = flush_deficit(h)) return rcf;
     if (d_V) *d_V = h->dVb;
     if (d_W) *d_W = h->dWb;
     if (n_blocked) *n_blocked = h->nBlocked;
@@ -783,6 +1014,7 @@ int rfb200_export_accumulators(rfb200_handle h, float* V, float* W) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     const Geometry& g = h->geo;
     size_t total = (size_t)g.Z * g.Z * g.X;
+    if (int rcf = flush_deficit(h)) return rcf;
     float2* dV = nullptr;
     float* dW = nullptr;
     RF_CUDA(h, cudaMalloc(&dV, sizeof(float2) * total));
@@ -812,6 +1044,7 @@ int rfb200_finalize(rfb200_handle h, float* out) {
     if (!h->dNorm) RF_CUDA(h, cudaMalloc(&h->dNorm, sizeof(float2) * nHalf));
     if (!h->dVol) RF_CUDA(h, cudaMalloc(&h->dVol, sizeof(float) * nVol));
     if (!h->dOut) RF_CUDA(h, cudaMalloc(&h->dOut, sizeof(float) * nOut));
+    if (int rcf = flush_deficit(h)) return rcf;
     {
         StageTimer t(h, Stage::FINALIZE, h->compute);
         NormArgs a{};
@@ -854,6 +1087,7 @@ int rfb200_get_timings(rfb200_handle h, rfb200_timings* t) {
 int rfb200_halfset_push(rfb200_handle h) {
     if (!h) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
     if (!h->dVsaved) {
         RF_CUDA(h, cudaMalloc(&h->dVsaved, sizeof(float2) * h->nBlocked));
         RF_CUDA(h, cudaMalloc(&h->dWsaved, sizeof(float) * h->nBlocked));
@@ -874,6 +1108,7 @@ int rfb200_halfset_merge(rfb200_handle h) {
     if (!h) return RFB200_ERR_ARG;
     if (!h->dVsaved) return fail(h, RFB200_ERR_STATE, "rfb200_halfset_push has not been called");
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
     const int64_t n = h->nBlocked;
     k_axpy<<<2048, 256, 0, h->compute>>>(reinterpret_cast<float*>(h->dVb), reinterpret_cast<const float*>(h->dVsaved), 2 * n);
     k_axpy<<<2048, 256, 0, h->compute>>>(h->dWb, h->dWsaved, n);
@@ -908,6 +1143,7 @@ int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms) {
 int rfb200_weight_sum(rfb200_handle h, double* sum) {
     if (!h || !sum) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
     k_weight_sum_partial<<<1024, 256, 0, h->compute>>>(h->dWb, h->nBlocked, h->dSum);
     RF_CUDA(h, cudaGetLastError());
     k_weight_sum_final<<<1, 256, 0, h->compute>>>(h->dSum, 1024, h->dSum + 1024);
@@ -938,7 +1174,25 @@ int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     size_t n = (size_t)h->geo.side * h->geo.side;
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
-    RF_CUDA(h, cudaMemcpy(out4, h->dSlices + (size_t)idx * n, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    if (!h->sticks) {
+        RF_CUDA(h, cudaMemcpy(out4, h->dSlices + (size_t)idx * n, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+        return RFB200_OK;
+    }
+    // format v2: plane A holds (re, im); the third channel is rebuilt from the validity table (multiplicity of the
+    // pixel: 1 inside the resolution disc, 2 on column 0, 0 outside)
+    const Geometry& g = h->geo;
+    std::vector<float2> A((size_t)g.planeStride);
+    RF_CUDA(h, cudaMemcpy(A.data(), h->dSlices2 + (size_t)idx * 2 * g.planeStride, sizeof(float2) * A.size(), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> rim = host::build_rim_table(h->geo, h->jmax, h->iLo, h->iHi);
+    for (int i = 0; i < g.side; ++i)
+        for (int j = 0; j < g.side; ++j) {
+            const float2 v = A[(size_t)i * g.pitch + j];
+            const int rt = rim[i], jc = j - g.Rp;
+            const int jPos = (rt & 0x3fff) - 1, jNeg = ((rt >> 14) & 0x3fff) - 1;
+            float m = jc > 0 ? (jc <= jPos ? 1.f : 0.f) : (jc < 0 ? (-jc <= jNeg ? 1.f : 0.f) : (float)(rt >> 28));
+            float* o = out4 + ((size_t)i * g.side + j) * 4;
+            o[0] = v.x; o[1] = v.y; o[2] = m; o[3] = 0.f;
+        }
     return RFB200_OK;
 }
 

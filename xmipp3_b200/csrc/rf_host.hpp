@@ -276,7 +276,91 @@ inline Geometry make_geometry(int N, double padProj, double padVol, double maxRe
     g.sMax = g.r2 * g.iDelta;
     g.reach = (float)(maxRes * g.Z + r);
     g.inplane_reach = (float)(R + rho);
+    g.pitch = (g.side + 2 + 1) & ~1;
+    g.planeStride = g.side * g.pitch;
+    g.xOwnMax = (g.Z % 2 == 0) ? g.Z / 2 - 1 : g.Z / 2;
+    g.rimIn2 = -1.f;   // set by build_rim_table
     return g;
+}
+
+// Validity / multiplicity of the FULL-plane slice pixels, one packed entry per centred row i in [-Rp, Rp]:
+//   (jPos+1) | (jNeg+1) << 14 | m0 << 28,  jPos = jmax of original row i (columns j > 0), jNeg = jmax of original
+//   row -i (columns j < 0 are Hermitian mirrors), m0 = multiplicity of column 0 (original (0,i) + mirror of (0,-i)).
+// Also sets g.rimIn2: inside that pixel radius (minus the window reach) every pixel is valid, so the gather can
+// count weights without looking at the table.
+inline std::vector<int32_t> build_rim_table(Geometry& g, const std::vector<int>& jmax, int iLo, int iHi) {
+    auto jm = [&](int i) { return (i >= iLo && i <= iHi) ? jmax[i - iLo] : -1; };
+    std::vector<int32_t> t(g.side);
+    double minInvalid2 = 1e300;
+    for (int i = -g.Rp; i <= g.Rp; ++i) {
+        int jp = jm(i), jn = jm(-i);
+        int m0 = (jp >= 0 ? 1 : 0) + (jn >= 0 ? 1 : 0);
+        t[i + g.Rp] = (jp + 1) | ((jn + 1) << 14) | (m0 << 28);
+        // first invalid pixel of the row on either side (column 0 is handled by the column-0 test of the gather,
+        // but a row where it is not doubly valid must take the slow path too)
+        double i2 = (double)i * i;
+        minInvalid2 = std::min(minInvalid2, i2 + (double)(jp + 1) * (jp + 1));
+        minInvalid2 = std::min(minInvalid2, i2 + (double)(jn + 1) * (jn + 1));
+        if (m0 != 2) minInvalid2 = std::min(minInvalid2, i2);
+    }
+    double rfree = std::sqrt(minInvalid2) - 1e-3 - std::sqrt(2.0) * g.K;
+    g.rimIn2 = rfree > 0 ? (float)(rfree * rfree) : -1.f;
+    return t;
+}
+
+// Sticks of class cls (0: d = x, 1: d = y, 2: d = z) whose lattice box comes within `reach` of the origin and holds
+// at least one voxel owned by the main gather; origins in stored-offset coordinates permuted to (a,b,d); sorted by
+// distance so that concurrently running warps work on neighbouring sticks (slice rings stay in L1/L2) and the
+// heavy central sticks start first.
+inline std::vector<StickUnit> build_stick_units(const Geometry& g, int cls) {
+    struct T { float d; StickUnit u; };
+    std::vector<T> v;
+    const int ext[3] = {g.tx * kTileX, g.ty * kTileY, g.tz * kTileZ};       // allocated extents x, y-lo, z-lo
+    const int ax[3][3] = {{1, 2, 0}, {0, 2, 1}, {0, 1, 2}};                 // (a,b,d) -> natural axis
+    const int A = ax[cls][0], B = ax[cls][1], D = ax[cls][2];
+    const int off[3] = {0, g.lo, g.lo};
+    const int maxc[3] = {g.xOwnMax, g.hi, g.hi};                            // largest owned centred coordinate
+    auto axis = [](int a, int b) { return (a > 0) ? (double)a : (b < 0 ? (double)-b : 0.0); };
+    for (int t0 = 0; t0 < ext[D]; t0 += kStickL)
+        for (int b0 = 0; b0 < ext[B]; b0 += kStickB)
+            for (int a0 = 0; a0 < ext[A]; a0 += kStickA) {
+                int lo3[3], hi3[3];
+                lo3[A] = a0 + off[A]; hi3[A] = std::min(a0 + kStickA - 1 + off[A], maxc[A]);
+                lo3[B] = b0 + off[B]; hi3[B] = std::min(b0 + kStickB - 1 + off[B], maxc[B]);
+                lo3[D] = t0 + off[D]; hi3[D] = std::min(t0 + kStickL - 1 + off[D], maxc[D]);
+                if (hi3[0] < lo3[0] || hi3[1] < lo3[1] || hi3[2] < lo3[2]) continue;
+                double dx = axis(lo3[0], hi3[0]), dy = axis(lo3[1], hi3[1]), dz = axis(lo3[2], hi3[2]);
+                double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+                if (d > g.reach + 1e-3) continue;
+                v.push_back({(float)d, StickUnit{a0, b0, t0, 0}});
+            }
+    std::stable_sort(v.begin(), v.end(), [](const T& a, const T& b) { return a.d < b.d; });
+    std::vector<StickUnit> out(v.size());
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].u;
+    return out;
+}
+
+// class of a plane = axis dominating its normal (ties -> lowest axis)
+inline int plane_class(const PlaneD& pd) {
+    double ax = std::fabs(pd.n[0]), ay = std::fabs(pd.n[1]), az = std::fabs(pd.n[2]);
+    if (ax >= ay && ax >= az) return 0;
+    if (ay >= az) return 1;
+    return 2;
+}
+// permute the components of a plane to the (a,b,d) order of its class
+inline void permute_plane(const PlaneD& pd, int cls, int img, float weight, PlaneD& pdp, PlaneS& ps) {
+    const int ax[3][3] = {{1, 2, 0}, {0, 2, 1}, {0, 1, 2}};
+    for (int c = 0; c < 3; ++c) {
+        pdp.e1[c] = pd.e1[ax[cls][c]];
+        pdp.e2[c] = pd.e2[ax[cls][c]];
+        pdp.n[c] = pd.n[ax[cls][c]];
+    }
+    ps.e1a = (float)pdp.e1[0]; ps.e1b = (float)pdp.e1[1]; ps.e1d = (float)pdp.e1[2];
+    ps.e2a = (float)pdp.e2[0]; ps.e2b = (float)pdp.e2[1]; ps.e2d = (float)pdp.e2[2];
+    ps.na = (float)pdp.n[0]; ps.nb = (float)pdp.n[1]; ps.nd = (float)pdp.n[2];
+    ps.img = img;
+    ps.weight = weight;
+    ps.invNd = (float)(1.0 / pdp.n[2]);
 }
 
 // local voxel (vx,vy,vz) in [0,16)x[0,16)x[0,8) -> slot inside a tile: brick * 32 + lane.  A warp owns a 4x4x2

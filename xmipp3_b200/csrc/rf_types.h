@@ -70,6 +70,28 @@ struct EdgeItem {
     int64_t store;         // blocked index of the stored voxel it adds into
 };
 
+// ---- stick gather (rf_sticks.cuh) ------------------------------------------------------------------------
+// A stick is the unit of work of one warp: 8 x 4 columns (lane <-> column) running kStickL voxels along the
+// axis d that dominates the normal of the planes it processes.  Class 0: d = x, (a,b) = (y,z); class 1:
+// d = y, (a,b) = (x,z); class 2: d = z, (a,b) = (x,y).
+constexpr int kStickA = 8, kStickB = 4;
+#ifndef RF_STICK_L
+#define RF_STICK_L 32
+#endif
+constexpr int kStickL = RF_STICK_L;
+struct PlaneS {            // 48 B, __constant__: plane of one (image, symmetry) with components permuted to (a,b,d)
+    float e1a, e1b, e1d;
+    float e2a, e2b, e2d;
+    float na, nb, nd;
+    int32_t img;           // image index inside the chunk
+    float weight;          // image weight (RF.cpp:374-381)
+    float invNd;           // 1 / nd
+};
+struct StickUnit {         // 16 B: stick origin in stored-offset coordinates (x, y - lo, z - lo), permuted to (a,b,d)
+    int32_t a0, b0, t0;
+    int32_t pad;
+};
+
 struct Geometry {
     int32_t N, P, Z, X;            // image, padded image, padded volume, Z/2+1
     int32_t lo, hi;                // centred range of y,z: [lo, hi]
@@ -87,6 +109,12 @@ struct Geometry {
     float sMax;                    // r^2 * iDelta: largest scaled squared distance inside the blob
     float reach;                   // maxRes*Z + r: no lattice point farther than this is touched
     float inplane_reach;           // R + rho (pixel units)
+    // slice format v2 (stick gather): two float2 planes per image, B[i][j] = A[i][j+1] (16-byte aligned pairs)
+    int32_t pitch;                 // row pitch of a slice plane in float2 units (even)
+    int32_t planeStride;           // side * pitch (float2 units); an image holds 2 planes
+    int32_t xOwnMax;               // largest ux owned by the main gather (originals and mirrors both land there)
+    float rimIn2;                  // (pixel radius)^2 inside which every candidate of a window is a valid pixel
+                                   // with multiplicity 1 unless the window touches column j = 0
 };
 
 }  // namespace rfb200
