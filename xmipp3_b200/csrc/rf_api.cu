@@ -279,12 +279,20 @@ int launch_gather(rfb200_handle h, const GatherArgs& a, int grid) {
     return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
 }
 
-template <int K>
-int launch_sticks_k(rfb200_handle h, const StickArgs& a, int grid) {
-    RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
-    k_gather_sticks<K><<<grid, kStickThreads, kStickSmem, h->compute>>>(a);
+template <int K, int CLS>
+int launch_sticks_kc(rfb200_handle h, const StickArgs& a, int grid) {
+    RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
+    k_gather_sticks<K, CLS><<<grid, kStickThreads, kStickSmem, h->compute>>>(a);
     RF_CUDA(h, cudaGetLastError());
     return RFB200_OK;
+}
+template <int K>
+int launch_sticks_k(rfb200_handle h, const StickArgs& a, int grid) {
+    switch (a.cls) {
+        case 0: return launch_sticks_kc<K, 0>(h, a, grid);
+        case 1: return launch_sticks_kc<K, 1>(h, a, grid);
+        default: return launch_sticks_kc<K, 2>(h, a, grid);
+    }
 }
 int launch_sticks(rfb200_handle h, const StickArgs& a, int grid) {
     switch (h->geo.K) {
@@ -474,7 +482,7 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
             e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
             e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
             e.iDeltaD = h->tables.iDeltaSqrt;
-            k_edge2<<<(h->nEdgeGroups + 127) / 128, 128, 0, h->compute>>>(e);
+            k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->compute>>>(e);      // one warp per target voxel
             RF_CUDA(h, cudaGetLastError());
             h->nKernelLaunches += 1;
         }
@@ -488,7 +496,7 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
         d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
         d.D = h->dD; d.D2 = h->dD2;
         const int total = (g.R + 1) * (2 * g.R + 1);
-        k_damped_scatter<<<dim3((total + 255) / 256, n), 256, 0, h->compute>>>(d);
+        k_damped_scatter<<<dim3((total + 256 * kDampedPerThread - 1) / (256 * kDampedPerThread), n), 256, 0, h->compute>>>(d);
         RF_CUDA(h, cudaGetLastError());
         h->nKernelLaunches += 1;
         h->dampedDirty = true;

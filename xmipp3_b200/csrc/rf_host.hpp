@@ -303,7 +303,8 @@ inline std::vector<int32_t> build_rim_table(Geometry& g, const std::vector<int>&
         minInvalid2 = std::min(minInvalid2, i2 + (double)(jn + 1) * (jn + 1));
         if (m0 != 2) minInvalid2 = std::min(minInvalid2, i2);
     }
-    double rfree = std::sqrt(minInvalid2) - 1e-3 - std::sqrt(2.0) * g.K;
+    // only ACCEPTED candidates count, and those lie within the blob radius rho (pixel units) of the projected voxel
+    double rfree = std::sqrt(minInvalid2) - 1e-2 - (double)g.rho;
     g.rimIn2 = rfree > 0 ? (float)(rfree * rfree) : -1.f;
     return t;
 }

@@ -3,11 +3,12 @@
 //   K1b' k_make_slices2     half-plane FFT -> two float2 full-plane slices (B is A shifted by one pixel, so every
 //                           candidate-window row is a run of 16-byte aligned pixel PAIRS in one of them) + the
 //                           true weights of the CTF-damped pixels (RF.cpp:600-625 hoisted)
-//   K2'  k_gather_sticks    voxel-centric gather, "column walk": a warp owns a stick of 8 x 4 columns that run
-//                           along the axis dominating the plane normal; lane <-> column; at every step the lane's
-//                           voxel is inside the blob slab of the plane, so (nearly) all lanes do useful work.
-//                           Accumulators of the stick live in shared memory ([depth][lane]: conflict-free for any
-//                           per-lane depth), ownership is exclusive -> no atomics, bit-reproducible.
+//   K2'  k_gather_sticks    voxel-centric gather, "column walk": a warp owns a stick of 4 x 4 columns that run
+//                           along the axis dominating the plane normal; two lanes per column (even / odd depth);
+//                           at every step the lane's voxel is inside the blob slab of the plane, so (nearly) all
+//                           lanes do useful work, and the 32 voxels of a step are compact (few image rows per
+//                           load instruction).  Accumulators of the stick live in shared memory ([depth][column]:
+//                           conflict-free for any per-column depth), ownership is exclusive -> bit-reproducible.
 //                           Replaces the scatter loop RF.cpp:586-792.
 //   K2e' k_edge2            lattice points the stick gather does not own (as k_edge, new slice format)
 //   K2r  k_damped_scatter   W of the (rare) pixels whose CTF is below --minCTF: their weight is |CTF| instead of 1
@@ -24,12 +25,12 @@ namespace rfb200 {
 __constant__ PlaneS c_planesS[kMaxPlanes];   // class-sorted planes of one launch, components permuted to (a,b,d)
 
 #ifndef RF_STICK_WARPS
-#define RF_STICK_WARPS 15
+#define RF_STICK_WARPS 16
 #endif
 constexpr int kStickWarps = RF_STICK_WARPS;
 constexpr int kStickThreads = kStickWarps * 32;
-constexpr size_t kStickSmem = (size_t)kStickWarps * kStickL * 32 * (sizeof(float2) + sizeof(float));
-static_assert(kStickL <= 32 && kStickL % 4 == 0, "touched-row mask is 32 bits; bricks are 4 deep along x and y");
+constexpr size_t kStickSmem = (size_t)kStickWarps * kStickL * kStickCols * (sizeof(float2) + sizeof(float));
+static_assert(kStickL <= 64 && kStickL % 4 == 0, "touched-row mask is 64 bits; bricks are 4 deep along x and y");
 constexpr double kFixedScale = 4294967296.0;   // 2^32 fixed point
 
 // rimTab entry of centred slice row i: (jPos+1) | (jNeg+1) << 14 | m0 << 28 with
@@ -78,7 +79,7 @@ struct Slice2Args {
 };
 
 // same thread mapping as k_make_slices: grid (ceil((R+1)/32), ceil((2R+1)/32), nImg), block (32, 8)
-__global__ void __launch_bounds__(256, 4) k_make_slices2(const __grid_constant__ Slice2Args a) {
+__global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__ Slice2Args a) {
     const SliceParams& sp = a.sp;
     const int j = blockIdx.x * 32 + threadIdx.x;
     if (j > sp.R) return;
@@ -138,23 +139,76 @@ struct StickArgs {
     float* Wb2;                  // un-modulated weight sum for --iter > 1 with CTF (else nullptr)
 };
 
-// 16-byte read-only load of a pixel pair under a predicate (no branch: all loads of a window issue back to back)
-__device__ __forceinline__ float4 d_ldg_pair_pred(const float2* p, bool pred) {
-    float4 v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "l"(p), "r"((int)pred));
-    return v;
+// One candidate, fully predicated (no branches, so that the 16 candidates of a window interleave):
+//   if (S <= sMax) { w = table[round(S)]; accRe += w*re; accIm += w*im; if (re is not flagged) accW += w*mult; }
+// (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in the mantissa; (bits << 2) +
+// tblAdj is then the shared-memory byte address of the table entry.  The LSB of `re` flags a CTF-damped pixel whose
+// weight comes from k_damped_scatter instead.
+__device__ __forceinline__ void d_candidate(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
+                                            const float mult, float& accRe, float& accIm, float& accW) {
+    asm("{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .f32 w, t;\n\t"
+        ".reg .b32 a, f;\n\t"
+        "setp.le.f32 p, %3, %4;\n\t"
+        "add.rn.f32 t, %3, 0f4B000000;\n\t"
+        "mov.b32 a, t;\n\t"
+        "shl.b32 a, a, 2;\n\t"
+        "add.u32 a, a, %5;\n\t"
+        "@p ld.shared.f32 w, [a];\n\t"
+        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
+        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
+        "mov.b32 f, %6;\n\t"
+        "and.b32 f, f, 1;\n\t"
+        "setp.eq.and.u32 q, f, 0, p;\n\t"
+        "@q fma.rn.f32 %2, w, %8, %2;\n\t"
+        "}"
+        : "+f"(accRe), "+f"(accIm), "+f"(accW)
+        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im), "f"(mult));
+}
+__device__ __forceinline__ void d_candidate1(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
+                                             float& accRe, float& accIm, float& accW) {
+    asm("{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .f32 w, t;\n\t"
+        ".reg .b32 a, f;\n\t"
+        "setp.le.f32 p, %3, %4;\n\t"
+        "add.rn.f32 t, %3, 0f4B000000;\n\t"
+        "mov.b32 a, t;\n\t"
+        "shl.b32 a, a, 2;\n\t"
+        "add.u32 a, a, %5;\n\t"
+        "@p ld.shared.f32 w, [a];\n\t"
+        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
+        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
+        "mov.b32 f, %6;\n\t"
+        "and.b32 f, f, 1;\n\t"
+        "setp.eq.and.u32 q, f, 0, p;\n\t"
+        "@q add.rn.f32 %2, %2, w;\n\t"
+        "}"
+        : "+f"(accRe), "+f"(accIm), "+f"(accW)
+        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im));
 }
 
 // One step of one column: evaluate the K x K candidate window of the lane's voxel.  p points at the window origin
 // (16-byte aligned pixel pair).  kSlow additionally weighs every candidate with its multiplicity (0 outside the
-// resolution disc, 2 on column j = 0), looked up per window row.
+// resolution disc, 2 on column j = 0), looked up per window row.  Two accumulator sets (even / odd candidates)
+// halve the length of the dependent FMA chains.
 template <int K, bool kSlow>
 __device__ __forceinline__ void d_stick_window(const float2* __restrict__ p, const int pitch, const float (&dxs)[K], const float (&dys)[K],
                                                const float sMax, const uint32_t tblAdj, const int jc, const int ic,
                                                const int* __restrict__ rimTab, float& accRe, float& accIm, float& accW) {
     constexpr int NP = (K + 1) / 2;
+#ifdef RF_STICK_UNCOND_LOADS
+    float4 px[K][NP];
+#pragma unroll
+    for (int ti = 0; ti < K; ++ti) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) px[ti][q] = __ldg(reinterpret_cast<const float4*>(p + ti * pitch + 2 * q));
+    }
+#else
+    // A pixel pair is fetched only if one of its two candidates is accepted: fewer lanes per load instruction means
+    // fewer cache lines (L1 wavefronts) per instruction, and the kernel is bound by the L1 data pipe.  The registers
+    // are zeroed first: a conditionally defined register would stay live across the whole step loop.
     float4 px[K][NP];
 #pragma unroll
     for (int ti = 0; ti < K; ++ti) {
@@ -163,9 +217,12 @@ __device__ __forceinline__ void d_stick_window(const float2* __restrict__ p, con
             const int t0 = 2 * q, t1 = 2 * q + 1;
             bool in = dys[ti] + dxs[t0] <= sMax;
             if (t1 < K) in = in || (dys[ti] + dxs[t1] <= sMax);
-            px[ti][q] = d_ldg_pair_pred(p + (size_t)ti * pitch + t0, in);
+            px[ti][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) px[ti][q] = __ldg(reinterpret_cast<const float4*>(p + ti * pitch + t0));
         }
     }
+#endif
+    float re1 = 0.f, im1 = 0.f, w1 = 0.f;
 #pragma unroll
     for (int ti = 0; ti < K; ++ti) {
         int rt = 0;
@@ -177,38 +234,137 @@ __device__ __forceinline__ void d_stick_window(const float2* __restrict__ p, con
                 const int tj = 2 * q + e;
                 if (tj < K) {
                     const float S = dys[ti] + dxs[tj];
-                    if (S <= sMax) {
-                        // (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in the
-                        // mantissa; (bits << 2) + tblAdj is then the shared-memory byte address of the table entry
-                        const uint32_t addr = (__float_as_uint(S + 8388608.0f) << 2) + tblAdj;
-                        float w;
-                        asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(addr));
-                        const float re = e ? px[ti][q].z : px[ti][q].x;
-                        accRe = fmaf(w, re, accRe);
-                        accIm = fmaf(w, e ? px[ti][q].w : px[ti][q].y, accIm);
-                        if (!(__float_as_uint(re) & 1u)) {       // CTF-damped pixels get their weight from k_damped_scatter
-                            if (kSlow) accW = fmaf(w, d_rim_mult(rt, jc + tj), accW);
-                            else accW += w;
-                        }
+                    const float re = e ? px[ti][q].z : px[ti][q].x, im = e ? px[ti][q].w : px[ti][q].y;
+                    if (e) {
+                        if (kSlow) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), re1, im1, w1);
+                        else d_candidate1(S, sMax, tblAdj, re, im, re1, im1, w1);
+                    } else {
+                        if (kSlow) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), accRe, accIm, accW);
+                        else d_candidate1(S, sMax, tblAdj, re, im, accRe, accIm, accW);
                     }
                 }
             }
         }
     }
+    accRe += re1;
+    accIm += im1;
+    accW += w1;
 }
 
+// fire-and-forget adds to the accumulators: one writer per address per launch (exclusive stick ownership) and
+// launches are ordered on the stream, so the result is still bit-reproducible; no load latency in the write-out
+__device__ __forceinline__ void d_red_add2(float2* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void d_red_add(float* addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+// A task = one plane crossing one stick.  Per-lane state of the column walk; `k` indexes c_planesS.
+struct StickTask {
+    int k;
+    int ja0, jb0;          // integer pixel of the stick origin's projection
+    float arL, brL, hL;    // lane's column at tau = 0: fractional in-plane position and height above the plane
+    int tauLo, tauHi;      // the lane's first depth (column start + parity) and the column's last depth inside the slab
+};
+
+// geometry constants of the kernel that the step functions need
+struct StickConsts {
+    int Rp, side, pitch, planeStride;
+    float rho, iDelta, sMax, kI, rimIn2, rhoCol0;
+    uint32_t tblAdj;
+};
+
+// window origin of the lane's voxel at depth tau: returns in-bounds flag, sets special (needs the multiplicity path)
 template <int K>
-__global__ void __launch_bounds__(kStickThreads, 1) k_gather_sticks(const __grid_constant__ StickArgs a) {
+__device__ __forceinline__ bool d_window_origin(const StickConsts& c, const StickTask& t, const PlaneS& pl, int tau, int& jw, int& iw,
+                                                float& ar, float& br, float& h, bool& special) {
+    const float ft = (float)tau;
+    ar = fmaf(ft, pl.e1d, t.arL);
+    br = fmaf(ft, pl.e2d, t.brL);
+    h = fmaf(ft, pl.nd, t.hL);
+    jw = __float2int_ru(ar - c.rho);
+    iw = __float2int_ru(br - c.rho);
+    const int jAbs = t.ja0 + jw + c.Rp, iAbs = t.jb0 + iw + c.Rp;
+    // Fast path needs every ACCEPTED candidate (in-plane distance <= rho) to be a valid pixel of multiplicity 1:
+    // inside the all-valid disc and away from column 0.
+    const float Aabs = (float)t.ja0 + ar, Babs = (float)t.jb0 + br;
+    special = (Aabs * Aabs + Babs * Babs > c.rimIn2) || (fabsf(Aabs) <= c.rhoCol0);
+    return (unsigned)jAbs <= (unsigned)(c.side - K) && (unsigned)iAbs <= (unsigned)(c.side - K);
+}
+template <int K>
+__device__ __forceinline__ const float2* d_window_ptr(const StickConsts& c, const float2* sl, const StickTask& t, int jw, int iw) {
+    const int jAbs = t.ja0 + jw + c.Rp, iAbs = t.jb0 + iw + c.Rp;
+    // odd window origin: read plane B (B[j] = A[j+1]) at jAbs-1 so that pairs stay 16-byte aligned
+    const int odd = jAbs & 1;
+    return sl + (iAbs * c.pitch + jAbs - odd + (odd ? c.planeStride : 0));
+}
+
+// Walk the columns of one task, two depths per column and iteration.  kChecked = false: every step of every
+// active lane is known to be in bounds and to need no multiplicity handling (both ends of each column were
+// tested; the conditions are convex along it).
+template <int K, bool kChecked>
+__device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const StickTask& t, const int nIter, const float2* __restrict__ slices,
+                                               const int imgStride, const int* __restrict__ rimTab, float2* accV, float* accW, const int col) {
+    const PlaneS& pl = c_planesS[t.k];
+    const float2* sl = slices + (size_t)pl.img * imgStride;
+    const float weight = pl.weight;
+    uint64_t touched = 0;
+    for (int s = 0; s < nIter; ++s) {
+        const int tau = t.tauLo + 2 * s;
+        int jw, iw;
+        float ar, br, h;
+        bool special = false;
+        bool ok = d_window_origin<K>(c, t, pl, tau, jw, iw, ar, br, h, special);
+        ok = (kChecked ? ok : true) && tau <= t.tauHi;
+        bool anySlow = false;
+        if (kChecked) anySlow = __any_sync(0xffffffffu, ok && special);
+        if (ok) {
+            float dxs[K], dys[K];
+            const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
+            const float h2s = h * h * c.iDelta;
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                const float da = da0 - (float)q, db = db0 - (float)q;
+                dxs[q] = c.kI * da * da;
+                dys[q] = fmaf(c.kI * db, db, h2s);
+            }
+            const float2* p = d_window_ptr<K>(c, sl, t, jw, iw);
+            float accRe = 0.f, accIm = 0.f, accWt = 0.f;
+            if (kChecked && anySlow)
+                d_stick_window<K, true>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+            else
+                d_stick_window<K, false>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+            const int o = tau * kStickCols + col;
+            float2 v = accV[o];
+            v.x += accRe;
+            v.y += accIm;
+            accV[o] = v;
+            accW[o] = fmaf(weight, accWt, accW[o]);
+            touched |= 1ull << tau;
+        }
+    }
+    return touched;
+}
+
+#ifdef RF_STICK_MAXREG
+#define RF_STICK_BOUNDS __maxnreg__(RF_STICK_MAXREG)
+#else
+#define RF_STICK_BOUNDS __launch_bounds__(kStickThreads, 1)
+#endif
+template <int K, int CLS>
+__global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArgs a) {
     const Geometry& geo = a.geo;
     __shared__ float tbl[kBlobTable];          // static: its shared address is a compile-time constant
     __shared__ int sAdj;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* accV = reinterpret_cast<float2*>(smem) + (size_t)warp * kStickL * 32;
-    float* accW = reinterpret_cast<float*>(smem + sizeof(float2) * kStickWarps * kStickL * 32) + (size_t)warp * kStickL * 32;
+    constexpr int kAccN = kStickL * kStickCols;
+    float2* accV = reinterpret_cast<float2*>(smem) + (size_t)warp * kAccN;
+    float* accW = reinterpret_cast<float*>(smem + sizeof(float2) * kStickWarps * kAccN) + (size_t)warp * kAccN;
 
     for (int i = tid; i < kBlobTable; i += kStickThreads) tbl[i] = __ldg(a.blobTable + i);
-    for (int i = lane; i < kStickL * 32; i += 32) {
+    for (int i = lane; i < kAccN; i += 32) {
         accV[i] = make_float2(0.f, 0.f);
         accW[i] = 0.f;
     }
@@ -216,21 +372,25 @@ __global__ void __launch_bounds__(kStickThreads, 1) k_gather_sticks(const __grid
     // the compiler treats it as an opaque value: the lookup address is then one LEA.
     if (tid == 0) sAdj = (int)((uint32_t)__cvta_generic_to_shared(tbl) - (0x4B000000u << 2));
     __syncthreads();
-    const uint32_t tblAdj = (uint32_t)(*(volatile int*)&sAdj);
 
-    const int cls = a.cls;
-    const int lo = geo.lo, hi = geo.hi, Rp = geo.Rp, side = geo.side, pitch = geo.pitch;
-    const float rho = geo.rho, iDelta = geo.iDelta, sMax = geo.sMax, kI = geo.s2 * geo.iDelta;
-    const float reach2 = geo.reach * geo.reach + 1.0f, rimIn2 = geo.rimIn2;
+    constexpr int cls = CLS;
+    StickConsts c;
+    c.Rp = geo.Rp; c.side = geo.side; c.pitch = geo.pitch; c.planeStride = geo.planeStride;
+    c.rho = geo.rho; c.iDelta = geo.iDelta; c.sMax = geo.sMax; c.kI = geo.s2 * geo.iDelta;
+    c.rimIn2 = geo.rimIn2; c.rhoCol0 = geo.rho + 1e-2f;
+    c.tblAdj = (uint32_t)(*(volatile int*)&sAdj);
+    const int lo = geo.lo, hi = geo.hi;
+    const float reach2 = geo.reach * geo.reach + 1.0f;
     const float rSlab = geo.r + 1e-3f;
-    const int la = lane & (kStickA - 1), lb = lane >> 3;
+    const int col = lane & (kStickCols - 1), par = lane >> 4;       // two lanes per column: even / odd depth
+    const int la = col & (kStickA - 1), lb = col / kStickA;
     const float laf = (float)la, lbf = (float)lb;
     const int offA = (cls == 0) ? lo : 0, offB = lo, offD = (cls == 0) ? 0 : lo;
     // culling: half extents of the stick's lattice box around its centre, in (a,b,d) order
     const float hA = 0.5f * (kStickA - 1), hB = 0.5f * (kStickB - 1), hD = 0.5f * (kStickL - 1);
     const float inLim = geo.inplane_reach + sqrtf(hA * hA + hB * hB + hD * hD) * sqrtf(1.0f / geo.s2) + 1.0f;
     const float inLim2 = inLim * inLim;
-    const size_t imgStride = 2 * (size_t)geo.planeStride;
+    const int imgStride = 2 * geo.planeStride;
 
     for (;;) {
         int u = 0;
@@ -265,7 +425,7 @@ __global__ void __launch_bounds__(kStickThreads, 1) k_gather_sticks(const __grid
         }
         int tauMin = max(tMin - T0c, 0), tauMax = min(tMax - T0c, kStickL - 1);
         if (!colOk) tauMax = -1;
-        uint32_t touched = 0;
+        uint64_t touched = 0;
 
         // ---- planes of this class: lane <-> plane culling, then the warp walks the hits in plane order
         const float cA = (float)A0c + hA, cB = (float)B0c + hB, cD = (float)T0c + hD;
@@ -287,100 +447,82 @@ __global__ void __launch_bounds__(kStickThreads, 1) k_gather_sticks(const __grid
             while (m) {
                 const int k = kb + __ffs(m) - 1;
                 m &= m - 1;
+                // ---- set up task k
                 const PlaneS& pl = c_planesS[k];
-                // segment of the column inside the slab |h| <= r:  h(tau) = hL + tau * nd
                 const PlaneD pd = a.planesDp[k];
                 const double a0 = A0c * pd.e1[0] + B0c * pd.e1[1] + T0c * pd.e1[2];
                 const double b0 = A0c * pd.e2[0] + B0c * pd.e2[1] + T0c * pd.e2[2];
                 const double h0 = A0c * pd.n[0] + B0c * pd.n[1] + T0c * pd.n[2];
                 const double ja = rint(a0), jb = rint(b0);
-                const int ja0 = (int)ja, jb0 = (int)jb;
-                // per-voxel FP32 arithmetic only sees offsets < 32 from the (double precision) stick origin
-                const float arL = fmaf(lbf, pl.e1b, fmaf(laf, pl.e1a, (float)(a0 - ja)));
-                const float brL = fmaf(lbf, pl.e2b, fmaf(laf, pl.e2a, (float)(b0 - jb)));
-                const float hL = fmaf(lbf, pl.nb, fmaf(laf, pl.na, (float)h0));
-                const float c0 = -hL * pl.invNd, hw = rSlab * fabsf(pl.invNd);
-                const int tauLo = max(__float2int_ru(c0 - hw), tauMin);
-                const int tauHi = min(__float2int_rd(c0 + hw), tauMax);
-                const int nSteps = __reduce_max_sync(0xffffffffu, max(tauHi - tauLo + 1, 0));
-                if (nSteps == 0) continue;
-                const float2* sl = a.slices + (size_t)pl.img * imgStride;
-                const float e1d = pl.e1d, e2d = pl.e2d, nd = pl.nd, weight = pl.weight;
-                const float jaf = (float)ja0, jbf = (float)jb0;
-                for (int s = 0; s < nSteps; ++s) {
-                    const int tau = tauLo + s;
-                    const float ft = (float)tau;
-                    const float ar = fmaf(ft, e1d, arL), br = fmaf(ft, e2d, brL), h = fmaf(ft, nd, hL);
-                    const int jw = __float2int_ru(ar - rho), iw = __float2int_ru(br - rho);
-                    const int jc = ja0 + jw, ic = jb0 + iw;                 // centred pixel of the window origin
-                    const int jAbs = jc + Rp, iAbs = ic + Rp;
-                    const bool ok = tau <= tauHi && (unsigned)jAbs <= (unsigned)(side - K) && (unsigned)iAbs <= (unsigned)(side - K);
-                    // fast path needs: every candidate a valid pixel of multiplicity 1
-                    const float Aabs = jaf + ar, Babs = jbf + br;
-                    const bool special = (Aabs * Aabs + Babs * Babs > rimIn2) || ((unsigned)(-jc) <= (unsigned)(K - 1));
-                    const bool anySlow = __any_sync(0xffffffffu, ok && special);
-                    if (ok) {
-                        float dxs[K], dys[K];
-                        const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
-                        const float h2s = h * h * iDelta;
+                StickTask t;
+                t.k = k;
+                t.ja0 = (int)ja;
+                t.jb0 = (int)jb;
+                // per-voxel FP32 arithmetic only sees offsets < kStickL from the (double precision) stick origin
+                t.arL = fmaf(lbf, pl.e1b, fmaf(laf, pl.e1a, (float)(a0 - ja)));
+                t.brL = fmaf(lbf, pl.e2b, fmaf(laf, pl.e2a, (float)(b0 - jb)));
+                t.hL = fmaf(lbf, pl.nb, fmaf(laf, pl.na, (float)h0));
+                // segment of the column inside the slab |h| <= r:  h(tau) = hL + tau * nd
+                const float c0 = -t.hL * pl.invNd, hw = rSlab * fabsf(pl.invNd);
+                const int colLo = max(__float2int_ru(c0 - hw), tauMin);
+                t.tauHi = min(__float2int_rd(c0 + hw), tauMax);
+                t.tauLo = colLo + par;
+                const int nIter = __reduce_max_sync(0xffffffffu, max((t.tauHi - colLo + 2) >> 1, 0));
+                if (nIter == 0) continue;
+                // both ends of the lane's walk in bounds and free of special pixels -> unchecked loop
+                bool plain = true;
+                if (t.tauLo <= t.tauHi) {
+                    const int last = t.tauLo + ((t.tauHi - t.tauLo) & ~1);
 #pragma unroll
-                        for (int q = 0; q < K; ++q) {
-                            const float da = da0 - (float)q, db = db0 - (float)q;
-                            dxs[q] = kI * da * da;
-                            dys[q] = fmaf(kI * db, db, h2s);
-                        }
-                        // odd window origin: read plane B (B[j] = A[j+1]) at jAbs-1 so that pairs stay 16-byte aligned
-                        const int odd = jAbs & 1;
-                        const float2* p = sl + ((size_t)(iAbs * pitch + jAbs - odd) + (odd ? (size_t)geo.planeStride : 0));
-                        float accRe = 0.f, accIm = 0.f, accWt = 0.f;
-                        if (anySlow) d_stick_window<K, true>(p, pitch, dxs, dys, sMax, tblAdj, jc, ic, a.rimTab, accRe, accIm, accWt);
-                        else d_stick_window<K, false>(p, pitch, dxs, dys, sMax, tblAdj, jc, ic, a.rimTab, accRe, accIm, accWt);
-                        const int o = tau * 32 + lane;
-                        float2 v = accV[o];
-                        v.x += accRe;
-                        v.y += accIm;
-                        accV[o] = v;
-                        accW[o] = fmaf(weight, accWt, accW[o]);
-                        touched |= 1u << tau;
+                    for (int e = 0; e < 2; ++e) {
+                        int jw, iw;
+                        float ar, br, h;
+                        bool special;
+                        const bool inb = d_window_origin<K>(c, t, pl, e ? last : t.tauLo, jw, iw, ar, br, h, special);
+                        plain = plain && inb && !special;
                     }
                 }
+                if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                else touched |= d_task_run<K, true>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
             }
         }
 
-        // ---- write-out: one coalesced read-modify-write per touched brick of the stick (blocked layout)
-        touched = __reduce_or_sync(0xffffffffu, touched);
+        // ---- write-out: one coalesced reduction per touched brick of the stick (blocked layout)
+        touched = (uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)touched) |
+                  ((uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)(touched >> 32)) << 32);
         if (touched) {
             __syncwarp();
             const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
             // brick extents in (a, b, tau) and the lane's offsets inside the brick
-            int spanB, spanT, da, db, dt;
-            if (cls == 2) { spanB = 4; spanT = 2; da = lx; db = ly; dt = lz; }
-            else if (cls == 1) { spanB = 2; spanT = 4; da = lx; db = lz; dt = ly; }
-            else { spanB = 2; spanT = 4; da = ly; db = lz; dt = lx; }
-            const int nBa = kStickA / 4, nBb = kStickB / spanB, nBt = kStickL / spanT;
-            for (int q = 0; q < nBa * nBb * nBt; ++q) {
-                const int ba = q % nBa, bb = (q / nBa) % nBb, bt = q / (nBa * nBb);
-                const uint32_t rows = ((1u << spanT) - 1u) << (bt * spanT);
+            constexpr int spanB = (cls == 2) ? 4 : 2, spanT = (cls == 2) ? 2 : 4;
+            const int da = (cls == 0) ? ly : lx, db = (cls == 2) ? ly : lz, dt = (cls == 2) ? lz : (cls == 1 ? ly : lx);
+            constexpr int nBa = kStickA / 4, nBb = kStickB / spanB, nBt = kStickL / spanT;
+#pragma unroll 1
+            for (int bt = 0; bt < nBt; ++bt) {
+                const uint64_t rows = ((1ull << spanT) - 1ull) << (bt * spanT);
                 if (!(touched & rows)) continue;
-                const int av = ba * 4 + da, bv = bb * spanB + db, tau = bt * spanT + dt;
-                const int o = tau * 32 + av + kStickA * bv;
-                const float2 v = accV[o];
-                const float w = accW[o];
-                if (w != 0.f || v.x != 0.f || v.y != 0.f) {
-                    int X, Y, Zc;   // stored-offset coordinates
-                    if (cls == 2) { X = su.x + av; Y = su.y + bv; Zc = su.z + tau; }
-                    else if (cls == 1) { X = su.x + av; Zc = su.y + bv; Y = su.z + tau; }
-                    else { Y = su.x + av; Zc = su.y + bv; X = su.z + tau; }
-                    const size_t tile = ((size_t)(Zc / kTileZ) * geo.ty + (Y / kTileY)) * geo.tx + (X / kTileX);
-                    const size_t g = tile * kTileVox + d_tile_slot(X % kTileX, Y % kTileY, Zc % kTileZ);
-                    float2 gv = a.Vb[g];
-                    gv.x += v.x;
-                    gv.y += v.y;
-                    a.Vb[g] = gv;
-                    a.Wb[g] += w;
-                    if (a.Wb2) a.Wb2[g] += w;
-                    accV[o] = make_float2(0.f, 0.f);
-                    accW[o] = 0.f;
+#pragma unroll
+                for (int bb = 0; bb < nBb; ++bb) {
+#pragma unroll
+                    for (int ba = 0; ba < nBa; ++ba) {
+                        const int av = ba * 4 + da, bv = bb * spanB + db, tau = bt * spanT + dt;
+                        const int o = tau * kStickCols + av + kStickA * bv;
+                        const float2 v = accV[o];
+                        const float w = accW[o];
+                        if (w != 0.f || v.x != 0.f || v.y != 0.f) {
+                            int X, Y, Zc;   // stored-offset coordinates
+                            if (cls == 2) { X = su.x + av; Y = su.y + bv; Zc = su.z + tau; }
+                            else if (cls == 1) { X = su.x + av; Zc = su.y + bv; Y = su.z + tau; }
+                            else { Y = su.x + av; Zc = su.y + bv; X = su.z + tau; }
+                            const size_t tile = ((size_t)(Zc / kTileZ) * geo.ty + (Y / kTileY)) * geo.tx + (X / kTileX);
+                            const size_t g = tile * kTileVox + d_tile_slot(X % kTileX, Y % kTileY, Zc % kTileZ);
+                            d_red_add2(a.Vb + g, v.x, v.y);
+                            d_red_add(a.Wb + g, w);
+                            if (a.Wb2) d_red_add(a.Wb2 + g, w);
+                            accV[o] = make_float2(0.f, 0.f);
+                            accW[o] = 0.f;
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -408,11 +550,12 @@ struct Edge2Args {
     double iDeltaD;
 };
 
-// One thread per edge TARGET voxel (it walks the lattice points aliased onto that voxel), brute force over the
-// planes of the chunk, double precision positions.
+// One WARP per edge target voxel (it walks the lattice points aliased onto that voxel); the lanes split the planes of
+// the launch (brute force, double precision positions) and the partial sums are combined with a fixed shuffle tree,
+// so the result does not depend on scheduling.
 __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args a) {
     const Geometry& geo = a.geo;
-    int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (grp >= a.nGroups) return;
     const double r2 = (double)geo.r * (double)geo.r, rho = geo.rho, s2 = geo.s2;
     const double lim = geo.inplane_reach;
@@ -424,7 +567,7 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
     for (int it = i0; it < i1; ++it) {
         const EdgeItem e = a.items[it];
         const double ux = e.ux, uy = e.uy, uz = e.uz;
-        for (int k = 0; k < a.nPlanes; ++k) {
+        for (int k = lane; k < a.nPlanes; k += 32) {
             const PlaneD& pl = a.planesD[k];
             double h = ux * pl.n[0] + uy * pl.n[1] + uz * pl.n[2];
             double h2 = h * h;
@@ -471,7 +614,13 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
             accW += weight * wsum;
         }
     }
-    if (accW != 0 || accRe != 0 || accIm != 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        accRe += __shfl_xor_sync(0xffffffffu, accRe, o);
+        accIm += __shfl_xor_sync(0xffffffffu, accIm, o);
+        accW += __shfl_xor_sync(0xffffffffu, accW, o);
+    }
+    if (lane == 0 && (accW != 0 || accRe != 0 || accIm != 0)) {
         float2 v = a.Vb[store];
         v.x += (float)accRe;
         v.y += (float)accIm;
@@ -496,29 +645,54 @@ struct DampedArgs {
     unsigned long long* D2;      // same for the un-modulated weights (--iter > 1), or nullptr
 };
 
-// grid (ceil((R+1)*(2R+1)/256), nImg).  Every thread reads one entry; the warp then walks its flagged entries one
-// at a time (they are rare), the 32 lanes sharing the (2*ceil(r)+1)^3 candidate lattice points of the pixel.
-// This is the reference's scatter (RF.cpp:628-792) restricted to W of those pixels.
+// grid (ceil((R+1)*(2R+1)/(256*kDampedPerThread)), nImg).  Every thread reads kDampedPerThread entries (all loads in
+// flight together); the warp then walks its flagged entries one at a time (they are rare), the 32 lanes sharing the
+// (floor(2r)+1)^3 candidate lattice points of the pixel.  This is the reference's scatter (RF.cpp:628-792) restricted
+// to W of those pixels.
+constexpr int kDampedPerThread = 8;
 __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ DampedArgs a) {
     const Geometry& geo = a.geo;
     const int R = geo.R, Z = geo.Z;
     const int img = blockIdx.y;
     const int cols = R + 1, total = cols * (2 * R + 1);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    float d = -1.f, d2 = 0.f;
-    if (idx < total) {
-        d = __ldg(a.damped + (size_t)img * total + idx);
-        if (a.damped2) d2 = fmaxf(__ldg(a.damped2 + (size_t)img * total + idx), 0.f);
+    const int idx0 = blockIdx.x * (256 * kDampedPerThread) + threadIdx.x;
+    float dv[kDampedPerThread], dv2[kDampedPerThread];
+#pragma unroll
+    for (int e = 0; e < kDampedPerThread; ++e) {
+        const int idx = idx0 + 256 * e;
+        dv[e] = -1.f;
+        dv2[e] = 0.f;
+        if (idx < total) {
+            dv[e] = __ldg(a.damped + (size_t)img * total + idx);
+            if (a.damped2) dv2[e] = fmaxf(__ldg(a.damped2 + (size_t)img * total + idx), 0.f);
+        }
     }
-    unsigned m = __ballot_sync(0xffffffffu, d > 0.f || (d >= 0.f && d2 > 0.f));
-    if (!m) return;
     const int p0 = a.imgPlane0[img];
     if (p0 < 0) return;
     const double r = geo.r, r2 = r * r;
     const double voxPerPix = (double)Z / (double)geo.P;
     const double sc = voxPerPix * voxPerPix;
-    while (m) {
+    // candidate lattice points of a pixel: a cube of edge E = floor(2r)+1 from ceil(p - r); the lane's share of the
+    // cube is fixed, so its offsets are computed once (no integer division in the loops when E^3 <= 128)
+    const int E = (int)floor(2.0 * r) + 1, E3 = E * E * E;
+    int ox[4], oy[4], oz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int cidx = lane + 32 * i;
+        ox[i] = cidx % E; oy[i] = (cidx / E) % E; oz[i] = cidx / (E * E);
+    }
+    // |u| <= Z/2 + r + 1, so one conditional add wraps an index into [0, Z)
+    auto wrap1 = [Z](int x) { return x < 0 ? x + Z : (x >= Z ? x - Z : x); };
+#pragma unroll 1
+    for (int e = 0; e < kDampedPerThread; ++e) {
+      float d = -1.f, d2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < kDampedPerThread; ++q)
+          if (q == e) { d = dv[q]; d2 = dv2[q]; }
+      const int idx = idx0 + 256 * e;
+      unsigned m = __ballot_sync(0xffffffffu, d > 0.f || (d >= 0.f && d2 > 0.f));
+      while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const float dd = __shfl_sync(0xffffffffu, d, src), dd2 = __shfl_sync(0xffffffffu, d2, src);
@@ -531,46 +705,40 @@ __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ 
             const double px = (j * pl.e1[0] + ip * pl.e2[0]) * sc;
             const double py = (j * pl.e1[1] + ip * pl.e2[1]) * sc;
             const double pz = (j * pl.e1[2] + ip * pl.e2[2]) * sc;
-            const int x0 = (int)ceil(px - r), x1 = (int)floor(px + r);
-            const int y0 = (int)ceil(py - r), y1 = (int)floor(py + r);
-            const int z0 = (int)ceil(pz - r), z1 = (int)floor(pz + r);
-            const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-            if (nx <= 0 || ny <= 0 || nz <= 0) continue;
-            const int nc = nx * ny * nz;
-            for (int c = lane; c < nc; c += 32) {
-                const int ux = x0 + c % nx, uy = y0 + (c / nx) % ny, uz = z0 + c / (nx * ny);
+            const int x0 = (int)ceil(px - r), y0 = (int)ceil(py - r), z0 = (int)ceil(pz - r);
+            auto process = [&](int cx, int cy3, int cz3) {
+                const int ux = x0 + cx, uy = y0 + cy3, uz = z0 + cz3;
                 const double dx = ux - px, dy = uy - py, dz = uz - pz;
                 const double dist2 = dx * dx + dy * dy + dz * dz;
-                if (dist2 > r2) continue;
+                if (dist2 > r2) return;
                 const int ti = (int)(dist2 * a.iDeltaD + 0.5);                 // RF.cpp:725
                 const double tw = (double)__ldg(a.blobTable + ti);
                 const unsigned long long q = (unsigned long long)__double2ll_rn(tw * (double)dd * kFixedScale);
                 const unsigned long long q2 = (unsigned long long)__double2ll_rn(tw * (double)dd2 * kFixedScale);
+                const int wx = wrap1(ux), wy = wrap1(uy), wz = wrap1(uz);
                 // original at u
-                {
-                    const int sx = d_wrap(ux, Z);
-                    if (sx <= Z / 2) {
-                        int sy = d_wrap(uy, Z), sz = d_wrap(uz, Z);
-                        int cy = sy <= Z / 2 ? sy : sy - Z, cz = sz <= Z / 2 ? sz : sz - Z;
-                        const int64_t o = d_blocked_index(geo, sx, cy, cz);
-                        if (q) atomicAdd(a.D + o, q);
-                        if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
-                    }
+                if (wx <= Z / 2) {
+                    const int cy = wy <= Z / 2 ? wy : wy - Z, cz = wz <= Z / 2 ? wz : wz - Z;
+                    const int64_t o = d_blocked_index(geo, wx, cy, cz);
+                    if (q) atomicAdd(a.D + o, q);
+                    if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
                 }
                 // Hermitian mirror at -u
-                {
-                    const int sx = d_wrap(-ux, Z);
-                    int sy = d_wrap(-uy, Z), sz = d_wrap(-uz, Z);
-                    int cy = sy <= Z / 2 ? sy : sy - Z, cz = sz <= Z / 2 ? sz : sz - Z;
-                    const bool mirr = d_wrap(ux, Z) > Z / 2;                        // cond_mirr(-u)
-                    if (sx <= Z / 2 && (mirr || (sx == 0 && cy <= geo.yHalf))) {
-                        const int64_t o = d_blocked_index(geo, sx, cy, cz);
-                        if (q) atomicAdd(a.D + o, q);
-                        if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
-                    }
+                const int sx = wx ? Z - wx : 0, sy = wy ? Z - wy : 0, sz = wz ? Z - wz : 0;
+                const int cy = sy <= Z / 2 ? sy : sy - Z, cz = sz <= Z / 2 ? sz : sz - Z;
+                const bool mirr = wx > Z / 2;                                       // cond_mirr(-u)
+                if (sx <= Z / 2 && (mirr || (sx == 0 && cy <= geo.yHalf))) {
+                    const int64_t o = d_blocked_index(geo, sx, cy, cz);
+                    if (q) atomicAdd(a.D + o, q);
+                    if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
                 }
-            }
+            };
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (lane + 32 * i < E3) process(ox[i], oy[i], oz[i]);
+            for (int c = lane + 128; c < E3; c += 32) process(c % E, (c / E) % E, c / (E * E));
         }
+      }
     }
 }
 

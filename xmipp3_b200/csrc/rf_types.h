@@ -71,10 +71,12 @@ struct EdgeItem {
 };
 
 // ---- stick gather (rf_sticks.cuh) ------------------------------------------------------------------------
-// A stick is the unit of work of one warp: 8 x 4 columns (lane <-> column) running kStickL voxels along the
-// axis d that dominates the normal of the planes it processes.  Class 0: d = x, (a,b) = (y,z); class 1:
+// A stick is the unit of work of one warp: 4 x 4 columns running kStickL voxels along the axis d that dominates
+// the normal of the planes it processes; two lanes share a column (even / odd depth), so the 32 voxels a warp
+// handles at a time form a compact 4 x 4 x 2 sheet hugging the plane.  Class 0: d = x, (a,b) = (y,z); class 1:
 // d = y, (a,b) = (x,z); class 2: d = z, (a,b) = (x,y).
-constexpr int kStickA = 8, kStickB = 4;
+constexpr int kStickA = 4, kStickB = 4;
+constexpr int kStickCols = kStickA * kStickB;   // 16
 #ifndef RF_STICK_L
 #define RF_STICK_L 32
 #endif
