@@ -152,7 +152,7 @@ struct rfb200_handle_s {
     int gatherGrid = 0;             // resident CTAs of the persistent gather: SMs x occupancy
     // ---- stick gather (default path; RFB200_GATHER=tiles selects the first-generation tile gather)
     bool sticks = true;
-    float2* dSlices2 = nullptr;     // per image two float2 planes (A, and B = A shifted by one pixel)
+    float4* dSlices2 = nullptr;     // per image side x pitch entries (pixel(i,j), pixel(i,j+1))
     float2* dCol02 = nullptr;
     float* dDamped = nullptr;       // per image (2R+1) x (R+1) weights of the CTF-damped (flagged) pixels (use_ctf only)
     float* dDamped2 = nullptr;      // their un-modulated weights (use_ctf && n_iter_weight > 1)
@@ -761,9 +761,9 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMalloc(&h->dCol0, sizeof(float4) * nC0));
         RF_CUDA(h, cudaMemset(h->dCol0, 0, sizeof(float4) * nC0));
     } else {
-        const size_t nSl2 = CH * 2 * (size_t)g.planeStride;
-        RF_CUDA(h, cudaMalloc(&h->dSlices2, sizeof(float2) * nSl2 + 64));
-        RF_CUDA(h, cudaMemset(h->dSlices2, 0, sizeof(float2) * nSl2 + 64));
+        const size_t nSl2 = CH * (size_t)g.planeStride;
+        RF_CUDA(h, cudaMalloc(&h->dSlices2, sizeof(float4) * nSl2 + 64));
+        RF_CUDA(h, cudaMemset(h->dSlices2, 0, sizeof(float4) * nSl2 + 64));
         RF_CUDA(h, cudaMalloc(&h->dCol02, sizeof(float2) * nC0));
         RF_CUDA(h, cudaMemset(h->dCol02, 0, sizeof(float2) * nC0));
         RF_CUDA(h, cudaMalloc(&h->dRimTab, sizeof(int32_t) * rimTab.size()));
@@ -1189,12 +1189,12 @@ int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
     // format v2: plane A holds (re, im); the third channel is rebuilt from the validity table (multiplicity of the
     // pixel: 1 inside the resolution disc, 2 on column 0, 0 outside)
     const Geometry& g = h->geo;
-    std::vector<float2> A((size_t)g.planeStride);
-    RF_CUDA(h, cudaMemcpy(A.data(), h->dSlices2 + (size_t)idx * 2 * g.planeStride, sizeof(float2) * A.size(), cudaMemcpyDeviceToHost));
+    std::vector<float4> A((size_t)g.planeStride);
+    RF_CUDA(h, cudaMemcpy(A.data(), h->dSlices2 + (size_t)idx * g.planeStride, sizeof(float4) * A.size(), cudaMemcpyDeviceToHost));
     std::vector<int32_t> rim = host::build_rim_table(h->geo, h->jmax, h->iLo, h->iHi);
     for (int i = 0; i < g.side; ++i)
         for (int j = 0; j < g.side; ++j) {
-            const float2 v = A[(size_t)i * g.pitch + j];
+            const float4 v = A[(size_t)i * g.pitch + j];
             const int rt = rim[i], jc = j - g.Rp;
             const int jPos = (rt & 0x3fff) - 1, jNeg = ((rt >> 14) & 0x3fff) - 1;
             float m = jc > 0 ? (jc <= jPos ? 1.f : 0.f) : (jc < 0 ? (-jc <= jNeg ? 1.f : 0.f) : (float)(rt >> 28));

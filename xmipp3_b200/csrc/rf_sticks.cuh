@@ -1,7 +1,8 @@
 // rf_sticks.cuh — second-generation insertion kernels (sm_100a).
 //
-//   K1b' k_make_slices2     half-plane FFT -> two float2 full-plane slices (B is A shifted by one pixel, so every
-//                           candidate-window row is a run of 16-byte aligned pixel PAIRS in one of them) + the
+//   K1b' k_make_slices2     half-plane FFT -> full-plane slice of overlapping pixel PAIRS: entry (i,j) is the float4
+//                           (pixel(i,j), pixel(i,j+1)), so a candidate-window row is two 16-byte loads whatever the
+//                           parity of its origin, and neighbouring lanes share cache lines + the
 //                           true weights of the CTF-damped pixels (RF.cpp:600-625 hoisted)
 //   K2'  k_gather_sticks    voxel-centric gather, "column walk": a warp owns a stick of 4 x 4 columns that run
 //                           along the axis dominating the plane normal; two lanes per column (even / odd depth);
@@ -69,7 +70,7 @@ struct Slice2Args {
     SliceParams sp;
     int pitch, planeStride;
     const float2* fft;
-    float2* slices;       // per image: plane A then plane B
+    float4* slices;       // per image side x pitch entries (pixel(i,j), pixel(i,j+1))
     float2* col0;         // per image `side` originals-only entries of column j = 0
     float* damped;        // per image (2R+1) x (R+1): true weight of a flagged pixel, -1 if not flagged; nullptr without CTF
     float* damped2;       // same shape: un-modulated weight of a flagged pixel (only for --iter > 1), else nullptr
@@ -87,8 +88,9 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
     const float2* f = a.fft + (size_t)img * sp.P * sp.Xh;
     const CtfConsts* ctf = sp.useCtf ? a.ctfs + img : nullptr;
     const float weight = a.ip[img].weight;
-    float2* SA = a.slices + (size_t)img * 2 * a.planeStride;
-    float2* SB = SA + a.planeStride;
+    // as float2: entry (i,j) = elements 2*(i*pitch+j) [pixel (i,j)] and +1 [pixel (i,j+1)]; a pixel is written to
+    // its own entry and to the second half of the entry on its left: two adjacent 8-byte stores
+    float2* S2 = reinterpret_cast<float2*>(a.slices + (size_t)img * a.planeStride);
     const size_t dOff = (size_t)img * (2 * sp.R + 1) * (sp.R + 1);
     const int rowBase = blockIdx.y * (8 * kSliceRowsPerThread) + threadIdx.y;
 #pragma unroll 2
@@ -104,8 +106,8 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
             const size_t o2 = (size_t)(-ipx + sp.Rp) * a.pitch + (-j + sp.Rp);
             const float re = d_set_flag(c.x, flag);
             const float2 v = make_float2(re, c.y), vm = make_float2(re, -c.y);
-            SA[o1] = v;  SB[o1 - 1] = v;
-            SA[o2] = vm; SB[o2 - 1] = vm;
+            S2[2 * o1] = v;  S2[2 * o1 - 1] = v;
+            S2[2 * o2] = vm; S2[2 * o2 - 1] = vm;
         } else {
             // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference inserts this
             // column twice for x > 0 voxels.  The combined entry is flagged if either part is damped;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
             float4 m = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, 0, -ipx);
             flag = flag || (m.w != 0.f);
             const float2 v = make_float2(d_set_flag(c.x + m.x, flag), c.y - m.y);
-            SA[o1] = v; SB[o1 - 1] = v;
+            S2[2 * o1] = v; S2[2 * o1 - 1] = v;
             a.col0[(size_t)img * sp.side + (ipx + sp.Rp)] = make_float2(d_set_flag(c.x, flag), c.y);
         }
         if (a.damped) a.damped[dOff + (size_t)r * (sp.R + 1) + j] = flag ? c.z : -1.f;
@@ -132,7 +134,7 @@ struct StickArgs {
     const float* blobTable;
     const PlaneD* planesDp;      // same order and permutation as c_planesS, double precision
     const float* planesSoA;      // 9 x kMaxPlanes floats, same order and permutation (culling phase, lane <-> plane)
-    const float2* slices;        // slice format v2
+    const float4* slices;        // slice format v2: overlapping pixel pairs
     const int* rimTab;           // already offset by +Rp: index with the centred row
     float2* Vb;
     float* Wb;
@@ -194,7 +196,7 @@ __device__ __forceinline__ void d_candidate1(const float S, const float sMax, co
 // resolution disc, 2 on column j = 0), looked up per window row.  Two accumulator sets (even / odd candidates)
 // halve the length of the dependent FMA chains.
 template <int K, bool kSlow>
-__device__ __forceinline__ void d_stick_window(const float2* __restrict__ p, const int pitch, const float (&dxs)[K], const float (&dys)[K],
+__device__ __forceinline__ void d_stick_window(const float4* __restrict__ p, const int pitch, const float (&dxs)[K], const float (&dys)[K],
                                                const float sMax, const uint32_t tblAdj, const int jc, const int ic,
                                                const int* __restrict__ rimTab, float& accRe, float& accIm, float& accW) {
     constexpr int NP = (K + 1) / 2;
@@ -203,7 +205,7 @@ __device__ __forceinline__ void d_stick_window(const float2* __restrict__ p, con
 #pragma unroll
     for (int ti = 0; ti < K; ++ti) {
 #pragma unroll
-        for (int q = 0; q < NP; ++q) px[ti][q] = __ldg(reinterpret_cast<const float4*>(p + ti * pitch + 2 * q));
+        for (int q = 0; q < NP; ++q) px[ti][q] = __ldg(p + ti * pitch + 2 * q);
     }
 #else
     // A pixel pair is fetched only if one of its two candidates is accepted: fewer lanes per load instruction means
@@ -218,7 +220,7 @@ __device__ __forceinline__ void d_stick_window(const float2* __restrict__ p, con
             bool in = dys[ti] + dxs[t0] <= sMax;
             if (t1 < K) in = in || (dys[ti] + dxs[t1] <= sMax);
             px[ti][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in) px[ti][q] = __ldg(reinterpret_cast<const float4*>(p + ti * pitch + t0));
+            if (in) px[ti][q] = __ldg(p + ti * pitch + t0);
         }
     }
 #endif
@@ -293,21 +295,19 @@ __device__ __forceinline__ bool d_window_origin(const StickConsts& c, const Stic
     return (unsigned)jAbs <= (unsigned)(c.side - K) && (unsigned)iAbs <= (unsigned)(c.side - K);
 }
 template <int K>
-__device__ __forceinline__ const float2* d_window_ptr(const StickConsts& c, const float2* sl, const StickTask& t, int jw, int iw) {
+__device__ __forceinline__ const float4* d_window_ptr(const StickConsts& c, const float4* sl, const StickTask& t, int jw, int iw) {
     const int jAbs = t.ja0 + jw + c.Rp, iAbs = t.jb0 + iw + c.Rp;
-    // odd window origin: read plane B (B[j] = A[j+1]) at jAbs-1 so that pairs stay 16-byte aligned
-    const int odd = jAbs & 1;
-    return sl + (iAbs * c.pitch + jAbs - odd + (odd ? c.planeStride : 0));
+    return sl + (iAbs * c.pitch + jAbs);
 }
 
 // Walk the columns of one task, two depths per column and iteration.  kChecked = false: every step of every
 // active lane is known to be in bounds and to need no multiplicity handling (both ends of each column were
 // tested; the conditions are convex along it).
 template <int K, bool kChecked>
-__device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const StickTask& t, const int nIter, const float2* __restrict__ slices,
+__device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const StickTask& t, const int nIter, const float4* __restrict__ slices,
                                                const int imgStride, const int* __restrict__ rimTab, float2* accV, float* accW, const int col) {
     const PlaneS& pl = c_planesS[t.k];
-    const float2* sl = slices + (size_t)pl.img * imgStride;
+    const float4* sl = slices + (size_t)pl.img * imgStride;
     const float weight = pl.weight;
     uint64_t touched = 0;
     for (int s = 0; s < nIter; ++s) {
@@ -329,7 +329,7 @@ __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const Stick
                 dxs[q] = c.kI * da * da;
                 dys[q] = fmaf(c.kI * db, db, h2s);
             }
-            const float2* p = d_window_ptr<K>(c, sl, t, jw, iw);
+            const float4* p = d_window_ptr<K>(c, sl, t, jw, iw);
             float accRe = 0.f, accIm = 0.f, accWt = 0.f;
             if (kChecked && anySlow)
                 d_stick_window<K, true>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
@@ -390,7 +390,7 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
     const float hA = 0.5f * (kStickA - 1), hB = 0.5f * (kStickB - 1), hD = 0.5f * (kStickL - 1);
     const float inLim = geo.inplane_reach + sqrtf(hA * hA + hB * hB + hD * hD) * sqrtf(1.0f / geo.s2) + 1.0f;
     const float inLim2 = inLim * inLim;
-    const int imgStride = 2 * geo.planeStride;
+    const int imgStride = geo.planeStride;
 
     for (;;) {
         int u = 0;
@@ -541,7 +541,7 @@ struct Edge2Args {
     const ImgParams* img;
     int nPlanes;
     const float* blobTable;
-    const float2* slices;        // format v2 (plane A is read)
+    const float4* slices;        // format v2 (the first pixel of an entry is read)
     const float2* col0;
     const int* rimTab;           // offset by +Rp
     float2* Vb;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
     const double r2 = (double)geo.r * (double)geo.r, rho = geo.rho, s2 = geo.s2;
     const double lim = geo.inplane_reach;
     const int Rp = geo.Rp, side = geo.side, K = geo.K, pitch = geo.pitch;
-    const size_t imgStride = 2 * (size_t)geo.planeStride;
+    const size_t imgStride = (size_t)geo.planeStride;
     double accRe = 0, accIm = 0, accW = 0;
     const int i0 = a.groupStart[grp], i1 = a.groupStart[grp + 1];
     const int64_t store = a.items[i0].store;
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
             int jw = (int)ceil(al - rho), iw = (int)ceil(be - rho);
             const int img = a.planeImg[k];
             const double weight = a.img[img].weight;
-            const float2* S = a.slices + (size_t)img * imgStride;
+            const float4* S = a.slices + (size_t)img * imgStride;
             const float2* C0 = a.col0 + (size_t)img * side;
             double wsum = 0;
             for (int ti = 0; ti < K; ++ti) {
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
                         px = __ldg(C0 + (ip + Rp));
                         mult = ((rt & 0x3fff) - 1) >= 0 ? 1.f : 0.f;   // original (0, ip) valid?
                     } else {
-                        px = __ldg(S + (size_t)(ip + Rp) * pitch + (j + Rp));
+                        px = __ldg(reinterpret_cast<const float2*>(S + (size_t)(ip + Rp) * pitch + (j + Rp)));
                         mult = d_rim_mult(rt, j);
                     }
                     accRe += (double)w * px.x;

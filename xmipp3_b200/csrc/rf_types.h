@@ -111,9 +111,9 @@ struct Geometry {
     float sMax;                    // r^2 * iDelta: largest scaled squared distance inside the blob
     float reach;                   // maxRes*Z + r: no lattice point farther than this is touched
     float inplane_reach;           // R + rho (pixel units)
-    // slice format v2 (stick gather): two float2 planes per image, B[i][j] = A[i][j+1] (16-byte aligned pairs)
-    int32_t pitch;                 // row pitch of a slice plane in float2 units (even)
-    int32_t planeStride;           // side * pitch (float2 units); an image holds 2 planes
+    // slice format v2 (stick gather): per image side x pitch float4 entries (pixel(i,j), pixel(i,j+1))
+    int32_t pitch;                 // row pitch in entries
+    int32_t planeStride;           // side * pitch entries per image
     int32_t xOwnMax;               // largest ux owned by the main gather (originals and mirrors both land there)
     float rimIn2;                  // (pixel radius)^2 inside which every candidate of a window is a valid pixel
                                    // with multiplicity 1 unless the window touches column j = 0
