@@ -296,7 +296,8 @@ def main():
     value = world * K * B / (ms * 1e-3)
     launches = int(tm["kernel_launches"])
 
-    # per-kernel roofline of the dominant kernel (k_gather), from CUDA events on its stream
+    # per-kernel roofline of the dominant kernel (k_gather_sticks: one launch per plane class and per sub-range of
+    # <= 512 planes), from CUDA events on its stream
     g_launches = max(1, int(tm["gather_launches"]))
     g_ms = tm["gather_ms"] / g_launches
     imgs_per_launch = K * B / g_launches
@@ -309,21 +310,26 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    traffic = None
+    prof = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "gather_ncu.json")))
     except Exception:
         pass
+    traffic = prof.get("dram_bytes_per_launch")
     cs = clocks.summary()
     sm_mhz = cs.get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {"kernel": "k_gather<4>", "bound": "hbm", "achieved": alg_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak,
+    roofline = {"kernel": "k_gather_sticks<4,cls>", "bound": "hbm", "achieved": alg_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": alg_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": g_ms, "particles_per_launch": imgs_per_launch,
-                "note": "the gather is bound by FP32 issue, not HBM; see fp32"}
+                "note": "the gather is bound by the L1/shared-memory data pipe (per-pair pixel and blob-table fetches), "
+                        "not by HBM or FP32: see l1_data_pipe (ncu) and fp32"}
     fp32 = {"achieved": alg_flops / (g_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": alg_flops / (g_ms * 1e-3) / 1e12 / fp32_peak,
             "peak_source": "148 SM x 128 lanes x 2 x %.0f MHz (median SM clock during the run)" % sm_mhz}
+    l1_pipe = {"frac": prof.get("l1_data_pipe_frac"), "issue_frac": prof.get("issue_active_frac"),
+               "source": prof.get("source", "no ncu summary in profiles/gather_ncu.json"),
+               "note": "ncu l1tex__data_pipe_lsu_wavefronts / smsp__issue_active of the same kernel (cold, serialised)"}
     stage_ms = {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}
 
     # ---------------- end to end through the C ABI with pinned host buffers
@@ -400,7 +406,7 @@ def main():
                        "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
                        "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
                        "stage_ms_per_step": stage_ms},
-            "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu_baseline,
+            "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32": fp32, "l1_data_pipe": l1_pipe, "cpu_baseline": cpu_baseline,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)

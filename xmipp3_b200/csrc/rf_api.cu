@@ -3,8 +3,8 @@
 // rf_kernels.cuh (device) and rf_host.hpp (double-precision precompute).
 //
 // Stream structure per handle: `copy` stream (H2D of raw particles, double buffered) and
-// `compute` stream (K1a -> cuFFT R2C -> K1b -> K2 -> K2e per chunk), linked by events, so
-// the PCIe transfer of chunk c+1 overlaps the kernels of chunk c.
+// `compute` stream (K1a -> cuFFT R2C -> K1b' -> K2' x3 classes -> K2e' -> K2r per chunk), linked by
+// events, so the PCIe transfer of chunk c+1 overlaps the kernels of chunk c.
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <dlfcn.h>
@@ -43,8 +43,6 @@ struct ParamSlot {      // pinned host staging for one chunk's parameters
     ImgParams* img = nullptr;
     CtfConsts* ctf = nullptr;
     PlaneD* planesD = nullptr;
-    PlaneF* planesF = nullptr;
-    float* planesSoA = nullptr;
     int* planeImg = nullptr;
     // stick gather: class-sorted, (a,b,d)-permuted copies, one region per launch sub-range
     PlaneD* planesDp = nullptr;
@@ -100,12 +98,9 @@ struct rfb200_handle_s {
     // static device data
     float* dBlobTable = nullptr;
     int* dJmax = nullptr;
-    int32_t* dTileList = nullptr;
-    int nTiles = 0;
     EdgeItem* dEdge = nullptr;
     int32_t* dEdgeGroups = nullptr;
     int nEdge = 0, nEdgeGroups = 0;
-    int* dTileCounter = nullptr;
     float* dG = nullptr;
     // accumulators (blocked layout)
     float2* dVb = nullptr;
@@ -122,13 +117,9 @@ struct rfb200_handle_s {
     float* dPad = nullptr;
     float* dCoef = nullptr;          // B-spline coefficients of the chunk (allocated on first fractional shift)
     float2* dFft = nullptr;
-    float4* dSlices = nullptr;
-    float4* dCol0 = nullptr;
     ImgParams* dImg = nullptr;
     CtfConsts* dCtf = nullptr;
     PlaneD* dPlanesD = nullptr;
-    float* dPlanesSoA = nullptr;
-    PlaneF* dPlanesFStage = nullptr;   // device staging of the __constant__ plane table
     int* dPlaneImg = nullptr;
     ParamSlot slots[2];
     int slotIdx = 0;
@@ -149,9 +140,7 @@ struct rfb200_handle_s {
     ncclComm_t comm = nullptr;
 #endif
     int nRanks = 1, rank = 0;
-    int gatherGrid = 0;             // resident CTAs of the persistent gather: SMs x occupancy
-    // ---- stick gather (default path; RFB200_GATHER=tiles selects the first-generation tile gather)
-    bool sticks = true;
+    // ---- stick gather
     float4* dSlices2 = nullptr;     // per image side x pitch entries (pixel(i,j), pixel(i,j+1))
     float2* dCol02 = nullptr;
     float* dDamped = nullptr;       // per image (2R+1) x (R+1) weights of the CTF-damped (flagged) pixels (use_ctf only)
@@ -253,32 +242,6 @@ int fetch_params(rfb200_handle h, void* dst, const void* srcPinned, size_t bytes
     return RFB200_OK;
 }
 
-template <int K>
-int launch_gather_k(rfb200_handle h, const GatherArgs& a, int grid) {
-    if (a.Wb2) {
-        RF_CUDA(h, cudaFuncSetAttribute(k_gather<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
-        k_gather<K, true><<<grid, kGatherThreads, kGatherSmem, h->compute>>>(a);
-    } else {
-        RF_CUDA(h, cudaFuncSetAttribute(k_gather<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
-        k_gather<K, false><<<grid, kGatherThreads, kGatherSmem, h->compute>>>(a);
-    }
-    RF_CUDA(h, cudaGetLastError());
-    return RFB200_OK;
-}
-int launch_gather(rfb200_handle h, const GatherArgs& a, int grid) {
-    switch (h->geo.K) {
-        case 1: return launch_gather_k<1>(h, a, grid);
-        case 2: return launch_gather_k<2>(h, a, grid);
-        case 3: return launch_gather_k<3>(h, a, grid);
-        case 4: return launch_gather_k<4>(h, a, grid);
-        case 5: return launch_gather_k<5>(h, a, grid);
-        case 6: return launch_gather_k<6>(h, a, grid);
-        case 7: return launch_gather_k<7>(h, a, grid);
-        case 8: return launch_gather_k<8>(h, a, grid);
-    }
-    return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
-}
-
 template <int K, int CLS>
 int launch_sticks_kc(rfb200_handle h, const StickArgs& a, int grid) {
     RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
@@ -371,7 +334,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
                                       p.DeltaR, p.Q0, p.K, p.envR0, p.envR1, p.envR2, p.phase_shift, p.vpp_radius);
         if (q.skip) continue;
         for (int sIdx = 0; sIdx < h->nSymTot; ++sIdx) {
-            host::make_plane(&h->sym[9 * sIdx], p.rot, p.tilt, p.psi, pixPerVox, i, s.planesD[np], s.planesF[np]);
+            host::make_plane(&h->sym[9 * sIdx], p.rot, p.tilt, p.psi, pixPerVox, s.planesD[np]);
             s.planeImg[np] = i;
             ++np;
         }
@@ -382,7 +345,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         rcf = fetch_params(h, h->dPlanesD, s.planesD, sizeof(PlaneD) * np);
         if (!rcf) rcf = fetch_params(h, h->dPlaneImg, s.planeImg, sizeof(int) * np);
     }
-    if (!rcf && h->sticks) {
+    if (!rcf) {
         // per launch sub-range: stable sort of the planes by class (axis dominating the normal), components
         // permuted to the (a,b,d) order of the class
         for (int p0 = 0; p0 < np; p0 += kMaxPlanes) {
@@ -451,6 +414,7 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
         if (!rc) rc = fetch_params(h, h->dPlanesSStage, slot->planesS + p0, sizeof(PlaneS) * np);
         if (rc) return rc;
         RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planesS, h->dPlanesSStage, sizeof(PlaneS) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
+        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planesD, h->dPlanesDp + p0, sizeof(PlaneD) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
         RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, 3 * sizeof(int), h->compute));
         int start[4] = {0, 0, 0, 0};
         for (int k = 0; k < np; ++k) start[host::plane_class(slot->planesD[p0 + k]) + 1]++;
@@ -465,12 +429,13 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
                 a.units = h->dUnits[cls]; a.nUnits = h->nUnits[cls]; a.counter = h->dStickCounters + cls;
                 a.cls = cls; a.kBegin = start[cls]; a.kEnd = start[cls + 1];
                 a.blobTable = h->dBlobTable;
-                a.planesDp = h->dPlanesDp + p0; a.planesSoA = h->dPlanesSoAp;
+                a.planesSoA = h->dPlanesSoAp;
                 a.slices = h->dSlices2; a.rimTab = h->dRimTab + g.Rp;
                 a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
                 rc = launch_sticks(h, a, std::min(h->stickGrid, (h->nUnits[cls] + kStickWarps - 1) / kStickWarps));
                 if (rc) return rc;
                 h->nKernelLaunches += 1;
+                h->nGatherLaunches += 1;
             }
         }
         if (h->nEdge) {
@@ -486,7 +451,6 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
             RF_CUDA(h, cudaGetLastError());
             h->nKernelLaunches += 1;
         }
-        h->nGatherLaunches += 1;
     }
     if (h->dDamped && nPlanes) {
         StageTimer t(h, Stage::EDGE, h->compute);
@@ -533,81 +497,8 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
         if (rc) return rc;
         RF_CUFFT(h, cufftExecR2C(plan, h->dPad, reinterpret_cast<cufftComplex*>(h->dFft)));
     }
-    if (h->sticks) {
-        rc = insert_planes_sticks(h, slot, n, nPlanes);
-        if (rc) return rc;
-        RF_CUDA(h, cudaEventRecord(slot->done, h->compute));
-        h->nImages += n;
-        h->nPlanes += nPlanes;
-        h->lastChunkImages = n;
-        return RFB200_OK;
-    }
-    {
-        StageTimer t(h, Stage::SLICE, h->compute);
-        SliceParams sp{};
-        sp.P = g.P; sp.Xh = g.P / 2 + 1; sp.iLo = h->iLo; sp.iHi = h->iHi;
-        sp.R = g.R; sp.Rp = g.Rp; sp.side = g.side;
-        sp.useCtf = h->cfg.use_ctf; sp.phaseFlipped = h->cfg.phase_flipped;
-        const double aStep = (h->cfg.use_ctf ? 1.0 / h->cfg.sampling : 1.0) / (double)g.P;
-        sp.a2 = aStep * aStep;
-        sp.a = (float)aStep;
-        sp.minCtfF = (float)h->cfg.min_ctf;
-        sp.minCtf = h->cfg.min_ctf;
-        sp.invP2 = (float)(1.0 / ((double)g.P * (double)g.P));
-        dim3 grid((g.R + 1 + 31) / 32, (2 * g.R + 1 + 8 * kSliceRowsPerThread - 1) / (8 * kSliceRowsPerThread), n);
-        k_make_slices<<<grid, dim3(32, 8), 0, h->compute>>>(h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dJmax, sp);
-        RF_CUDA(h, cudaGetLastError());
-    }
-    h->nKernelLaunches += 2;
-    // gather launches over sub-ranges of at most kMaxPlanes planes
-    for (int p0 = 0; p0 < nPlanes; p0 += kMaxPlanes) {
-        int np = std::min(kMaxPlanes, nPlanes - p0);
-        // SoA copy for the culling phase (coalesced by plane index)
-        float* soa = slot->planesSoA;
-        // each sub-range needs its own staging region because the async copies read it later
-        float* soaChunk = soa + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
-        for (int k = 0; k < np; ++k) {
-            const PlaneF& f = slot->planesF[p0 + k];
-            for (int c = 0; c < 3; ++c) {
-                soaChunk[(0 + c) * kMaxPlanes + k] = f.e1[c];
-                soaChunk[(3 + c) * kMaxPlanes + k] = f.e2[c];
-                soaChunk[(6 + c) * kMaxPlanes + k] = f.n[c];
-            }
-        }
-        rc = fetch_params(h, h->dPlanesSoA, soaChunk, sizeof(float) * 9 * kMaxPlanes);
-        if (!rc) rc = fetch_params(h, h->dPlanesFStage, slot->planesF + p0, sizeof(PlaneF) * np);
-        if (rc) return rc;
-        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planes, h->dPlanesFStage, sizeof(PlaneF) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
-        RF_CUDA(h, cudaMemsetAsync(h->dTileCounter, 0, sizeof(int), h->compute));
-        {
-            StageTimer t(h, Stage::GATHER, h->compute);
-            GatherArgs a{};
-            a.geo = g;
-            a.tileList = h->dTileList; a.nTiles = h->nTiles; a.tileCounter = h->dTileCounter;
-            a.blobTable = h->dBlobTable;
-            a.planesD = h->dPlanesD + p0; a.planesSoA = h->dPlanesSoA; a.nPlanes = np;
-            a.slices = h->dSlices; a.sliceStride = (size_t)g.side * g.side;
-            a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
-            rc = launch_gather(h, a, std::min(h->gatherGrid, h->nTiles));
-            if (rc) return rc;
-        }
-        if (h->nEdge) {
-            StageTimer t(h, Stage::EDGE, h->compute);
-            EdgeArgs e{};
-            e.geo = g;
-            e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
-            e.planesD = h->dPlanesD + p0; e.planeImg = h->dPlaneImg + p0; e.nPlanes = np;
-            e.blobTable = h->dBlobTable; e.slices = h->dSlices; e.col0 = h->dCol0;
-            e.sliceStride = (size_t)g.side * g.side;
-            e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
-            e.iDeltaD = h->tables.iDeltaSqrt;
-            k_edge<<<(h->nEdgeGroups + 127) / 128, 128, 0, h->compute>>>(e);
-            RF_CUDA(h, cudaGetLastError());
-            h->nKernelLaunches += 1;
-        }
-        h->nGatherLaunches += 1;
-        h->nKernelLaunches += 1;
-    }
+    rc = insert_planes_sticks(h, slot, n, nPlanes);
+    if (rc) return rc;
     RF_CUDA(h, cudaEventRecord(slot->done, h->compute));
     h->nImages += n;
     h->nPlanes += nPlanes;
@@ -643,13 +534,13 @@ void free_all(rfb200_handle h) {
     if (h->hSum) cudaFreeHost(h->hSum);
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
-    void* dev[] = {h->dBlobTable, h->dJmax, h->dTileList, h->dEdge, h->dEdgeGroups, h->dTileCounter, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
-                   h->dPad, h->dCoef, h->dFft, h->dSlices, h->dCol0, h->dImg, h->dCtf, h->dPlanesD, h->dPlanesSoA, h->dPlanesFStage, h->dPlaneImg, h->dNorm,
+    void* dev[] = {h->dBlobTable, h->dJmax, h->dEdge, h->dEdgeGroups, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
+                   h->dPad, h->dCoef, h->dFft, h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
                    h->dStickCounters, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
-        void* hp[] = {s.img, s.ctf, s.planesD, s.planesF, s.planesSoA, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0};
+        void* hp[] = {s.img, s.ctf, s.planesD, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0};
         for (void* p : hp) if (p) cudaFreeHost(p);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -688,14 +579,8 @@ int do_create(rfb200_handle h) {
     h->geo = host::make_geometry(c.img_size, c.pad_proj, c.pad_vol, c.max_resolution, c.blob_radius, R);
     Geometry& g = h->geo;
     if (g.K > kMaxWin) return fail(h, RFB200_ERR_ARG, "blob radius too large for the interpolation window (max 8 pixels)");
-    {
-        const char* e = getenv("RFB200_GATHER");      // developer switch: "tiles" = first-generation tile gather
-        h->sticks = !(e && std::string(e) == "tiles");
-    }
     std::vector<int32_t> rimTab = host::build_rim_table(g, h->jmax, h->iLo, h->iHi);
-    std::vector<int32_t> tiles = host::build_tile_list(g);
     std::vector<EdgeItem> edge = host::build_edge_items(g);
-    h->nTiles = (int)tiles.size();
     h->nEdge = (int)edge.size();
     double meanF2 = 0;
     std::vector<float> G = host::build_gridding_table(c.img_size, c.pad_proj, c.pad_vol, h->tables, c.n_iter_weight, &meanF2);
@@ -718,8 +603,6 @@ int do_create(rfb200_handle h) {
     RF_CUDA(h, cudaMemcpy(h->dBlobTable, blobF.data(), sizeof(float) * kBlobTable, cudaMemcpyHostToDevice));
     RF_CUDA(h, cudaMalloc(&h->dJmax, sizeof(int) * h->jmax.size()));
     RF_CUDA(h, cudaMemcpy(h->dJmax, h->jmax.data(), sizeof(int) * h->jmax.size(), cudaMemcpyHostToDevice));
-    RF_CUDA(h, cudaMalloc(&h->dTileList, sizeof(int32_t) * std::max<size_t>(1, tiles.size())));
-    if (!tiles.empty()) RF_CUDA(h, cudaMemcpy(h->dTileList, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice));
     if (!edge.empty()) {
         RF_CUDA(h, cudaMalloc(&h->dEdge, sizeof(EdgeItem) * edge.size()));
         RF_CUDA(h, cudaMemcpy(h->dEdge, edge.data(), sizeof(EdgeItem) * edge.size(), cudaMemcpyHostToDevice));
@@ -728,7 +611,6 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMalloc(&h->dEdgeGroups, sizeof(int32_t) * starts.size()));
         RF_CUDA(h, cudaMemcpy(h->dEdgeGroups, starts.data(), sizeof(int32_t) * starts.size(), cudaMemcpyHostToDevice));
     }
-    RF_CUDA(h, cudaMalloc(&h->dTileCounter, sizeof(int)));
     RF_CUDA(h, cudaMalloc(&h->dSum, sizeof(double) * 1025));
     RF_CUDA(h, cudaMallocHost(&h->hSum, sizeof(double)));
     RF_CUDA(h, cudaEventCreate(&h->swStart));
@@ -750,17 +632,12 @@ int do_create(rfb200_handle h) {
     // ---- per-chunk buffers
     const size_t CH = h->chunkImages;
     const size_t nRaw = CH * g.N * g.N, nPad = CH * (size_t)g.P * g.P, nFft = CH * (size_t)g.P * (g.P / 2 + 1);
-    const size_t nSl = CH * (size_t)g.side * g.side, nC0 = CH * (size_t)g.side;
+    const size_t nC0 = CH * (size_t)g.side;
     for (int i = 0; i < 2; ++i) RF_CUDA(h, cudaMalloc(&h->dRaw[i], sizeof(float) * nRaw));
     RF_CUDA(h, cudaMalloc(&h->dPad, sizeof(float) * nPad));
     RF_CUDA(h, cudaMemset(h->dPad, 0, sizeof(float) * nPad));
     RF_CUDA(h, cudaMalloc(&h->dFft, sizeof(float2) * nFft));
-    if (!h->sticks) {
-        RF_CUDA(h, cudaMalloc(&h->dSlices, sizeof(float4) * nSl));
-        RF_CUDA(h, cudaMemset(h->dSlices, 0, sizeof(float4) * nSl));
-        RF_CUDA(h, cudaMalloc(&h->dCol0, sizeof(float4) * nC0));
-        RF_CUDA(h, cudaMemset(h->dCol0, 0, sizeof(float4) * nC0));
-    } else {
+    {
         const size_t nSl2 = CH * (size_t)g.planeStride;
         RF_CUDA(h, cudaMalloc(&h->dSlices2, sizeof(float4) * nSl2 + 64));
         RF_CUDA(h, cudaMemset(h->dSlices2, 0, sizeof(float4) * nSl2 + 64));
@@ -793,9 +670,7 @@ int do_create(rfb200_handle h) {
     const size_t nSub = (maxPlanes + kMaxPlanes - 1) / kMaxPlanes;
     RF_CUDA(h, cudaMalloc(&h->dPlanesD, sizeof(PlaneD) * maxPlanes + 16));
     RF_CUDA(h, cudaMalloc(&h->dPlaneImg, sizeof(int) * maxPlanes + 16));
-    RF_CUDA(h, cudaMalloc(&h->dPlanesSoA, sizeof(float) * 9 * kMaxPlanes));
-    RF_CUDA(h, cudaMalloc(&h->dPlanesFStage, sizeof(PlaneF) * kMaxPlanes));
-    if (h->sticks) {
+    {
         RF_CUDA(h, cudaMalloc(&h->dPlanesDp, sizeof(PlaneD) * maxPlanes + 16));
         RF_CUDA(h, cudaMalloc(&h->dPlanesSoAp, sizeof(float) * 9 * kMaxPlanes));
         RF_CUDA(h, cudaMalloc(&h->dPlanesSStage, sizeof(PlaneS) * kMaxPlanes));
@@ -805,10 +680,8 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
         RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));
         RF_CUDA(h, cudaMallocHost(&s.planesD, sizeof(PlaneD) * maxPlanes + 16));
-        RF_CUDA(h, cudaMallocHost(&s.planesF, sizeof(PlaneF) * maxPlanes));
-        RF_CUDA(h, cudaMallocHost(&s.planesSoA, sizeof(float) * 9 * kMaxPlanes * nSub));
         RF_CUDA(h, cudaMallocHost(&s.planeImg, sizeof(int) * maxPlanes + 16));
-        if (h->sticks) {
+        {
             RF_CUDA(h, cudaMallocHost(&s.planesDp, sizeof(PlaneD) * maxPlanes + 16));
             RF_CUDA(h, cudaMallocHost(&s.planesS, sizeof(PlaneS) * maxPlanes + 16));
             RF_CUDA(h, cudaMallocHost(&s.soaP, sizeof(float) * 9 * kMaxPlanes * nSub));
@@ -816,22 +689,7 @@ int do_create(rfb200_handle h) {
         }
         RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
-    // persistent grid: as many CTAs as fit
-    int occ = 0;
-    int rcK = RFB200_OK;
-    switch (g.K) {
-#define OCC_CASE(KK)                                                                                              \
-    case KK:                                                                                                      \
-        RF_CUDA(h, cudaFuncSetAttribute(k_gather<KK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem)); \
-        RF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather<KK, false>, kGatherThreads, kGatherSmem));  \
-        break;
-        OCC_CASE(1) OCC_CASE(2) OCC_CASE(3) OCC_CASE(4) OCC_CASE(5) OCC_CASE(6) OCC_CASE(7) OCC_CASE(8)
-#undef OCC_CASE
-        default: rcK = RFB200_ERR_ARG;
-    }
-    if (rcK) return fail(h, rcK, "unsupported interpolation window");
-    if (occ < 1) occ = 1;
-    h->gatherGrid = prop.multiProcessorCount * occ;
+    // persistent grid: one CTA per SM
     h->stickGrid = prop.multiProcessorCount;
     RF_CUDA(h, cudaDeviceSynchronize());
     return RFB200_OK;
@@ -885,7 +743,7 @@ int rfb200_get_info(rfb200_handle h, rfb200_info* info) {
     info->tiles_x = g.tx; info->tiles_y = g.ty; info->tiles_z = g.tz; info->tile = kTileX;
     info->n_blocked = h->nBlocked;
     info->chunk_images = h->chunkImages;
-    info->n_tiles_active = h->nTiles;
+    info->n_tiles_active = h->nUnits[0] + h->nUnits[1] + h->nUnits[2];   // work units (sticks) of the gather
     info->n_edge_items = h->nEdge;
     return RFB200_OK;
 }
@@ -1180,12 +1038,7 @@ int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radiu
 int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
     if (!h || !out4 || idx < 0 || idx >= h->lastChunkImages) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
-    size_t n = (size_t)h->geo.side * h->geo.side;
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
-    if (!h->sticks) {
-        RF_CUDA(h, cudaMemcpy(out4, h->dSlices + (size_t)idx * n, sizeof(float4) * n, cudaMemcpyDeviceToHost));
-        return RFB200_OK;
-    }
     // format v2: plane A holds (re, im); the third channel is rebuilt from the validity table (multiplicity of the
     // pixel: 1 inside the resolution disc, 2 on column 0, 0 outside)
     const Geometry& g = h->geo;

@@ -178,7 +178,7 @@ inline void euler_matrix(double rot, double tilt, double psi, double A[9]) {
 }
 
 // Plane of (image, symmetry): M = R * A^T (RF.cpp:411-412, 936); e1, e2 scaled to pixel units.
-inline void make_plane(const double R[9], double rot, double tilt, double psi, double pixPerVox, int img, PlaneD& pd, PlaneF& pf) {
+inline void make_plane(const double R[9], double rot, double tilt, double psi, double pixPerVox, PlaneD& pd) {
     double A[9], M[9];
     euler_matrix(rot, tilt, psi, A);
     for (int i = 0; i < 3; ++i)
@@ -194,12 +194,7 @@ inline void make_plane(const double R[9], double rot, double tilt, double psi, d
         // e1 x e2 for a proper rotation and -(e1 x e2) for an improper one — the sign is irrelevant
         // because only |h| enters.  Use the third column directly.
         pd.n[c] = M[c * 3 + 2];
-        pf.e1[c] = (float)pd.e1[c];
-        pf.e2[c] = (float)pd.e2[c];
-        pf.n[c] = (float)pd.n[c];
     }
-    pf.img = img;
-    pf.pad0 = pf.pad1 = 0.f;
 }
 
 // ctf.cpp:645-680 (produceSideInfo) and :1392-1404
@@ -364,9 +359,8 @@ inline void permute_plane(const PlaneD& pd, int cls, int img, float weight, Plan
     ps.invNd = (float)(1.0 / pdp.n[2]);
 }
 
-// local voxel (vx,vy,vz) in [0,16)x[0,16)x[0,8) -> slot inside a tile: brick * 32 + lane.  A warp owns a 4x4x2
-// brick so that its 32 voxels are compact in space (fewer wasted lanes per plane) and its 32 slots are
-// contiguous in memory.
+// local voxel (vx,vy,vz) in [0,16)x[0,16)x[0,8) -> slot inside a tile: brick * 32 + lane (4x4x2 bricks whose 32
+// slots are contiguous in memory)
 inline int tile_slot(int vx, int vy, int vz) {
     int brick = (vx >> 2) | ((vy >> 2) << 2) | ((vz >> 1) << 4);
     int lane = (vx & 3) | ((vy & 3) << 2) | ((vz & 1) << 4);
@@ -387,30 +381,6 @@ inline bool cond_mirr(const Geometry& g, int ux) { return wrapi(-ux, g.Z) > g.Z 
 inline bool main_owns(const Geometry& g, int ux, int uy, int /*uz*/) {
     if (ux == 0) return uy <= g.yHalf;
     return cond_orig(g, ux) && cond_mirr(g, ux);
-}
-
-// Active tiles: those whose clipped box comes within `reach` of the origin; sorted by distance so that
-// concurrently running CTAs work on the same shell (the slices' rings stay in L2) and the heavy
-// central tiles start first.
-inline std::vector<int32_t> build_tile_list(const Geometry& g) {
-    struct T { float d; int32_t id; };
-    std::vector<T> v;
-    for (int tz = 0; tz < g.tz; ++tz)
-        for (int ty = 0; ty < g.ty; ++ty)
-            for (int tx = 0; tx < g.tx; ++tx) {
-                int x0 = tx * kTileX, x1 = std::min(x0 + kTileX - 1, g.Z / 2);
-                int y0 = g.lo + ty * kTileY, y1 = std::min(y0 + kTileY - 1, g.hi);
-                int z0 = g.lo + tz * kTileZ, z1 = std::min(z0 + kTileZ - 1, g.hi);
-                auto axis = [](int a, int b) { return (a > 0) ? (double)a : (b < 0 ? (double)-b : 0.0); };
-                double dx = axis(x0, x1), dy = axis(y0, y1), dz = axis(z0, z1);
-                double d = std::sqrt(dx * dx + dy * dy + dz * dz);
-                if (d > g.reach + 1e-3) continue;
-                v.push_back({(float)d, (tz * g.ty + ty) * g.tx + tx});
-            }
-    std::stable_sort(v.begin(), v.end(), [](const T& a, const T& b) { return a.d < b.d; });
-    std::vector<int32_t> out(v.size());
-    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].id;
-    return out;
 }
 
 // Edge items: natural lattice points the main gather does not own, and the

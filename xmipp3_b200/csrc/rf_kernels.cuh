@@ -1,13 +1,9 @@
-// rf_kernels.cuh — hand-written sm_100a kernels of the direct Fourier reconstruction.
+// rf_kernels.cuh — hand-written sm_100a kernels of the direct Fourier reconstruction (everything except the
+// insertion itself, which lives in rf_sticks.cuh).
 //
 //   K1a k_pad_images     raw N x N particle -> zero-padded, centred, shifted P x P image  (RF.cpp:388-402)
 //   (cuFFT R2C batched)                                                                  (RF.cpp:405-407)
-//   K1b k_make_slices    half-plane FFT -> resolution-cropped, CTF-weighted FULL-plane slice
-//                        (originals + Hermitian mirrors), RF.cpp:594-625 hoisted out of the insertion
-//   K2  k_gather         voxel-centric gather with Kaiser-Bessel blob interpolation; replaces the
-//                        scatter loop RF.cpp:586-792.  One CTA owns an 8^3 tile of the half volume,
-//                        each thread one voxel; accumulators live in registers; no atomics.
-//   K2e k_edge           lattice points the tile gather does not own (orig-only planes, Nyquist wraps)
+//   CTF device functions per-pixel wCTF / wModulator (RF.cpp:600-625, data/ctf.h:452-502) used by K1b'
 //   K3a k_normalize      weight symmetrisation + normalisation (RF.cpp:1056-1101, 453-479, 1188-1221)
 //   (cuFFT C2R 3-D)                                                                      (RF.cpp:1145)
 //   K3b k_crop_correct   CenterFFT + crop + gridding correction (RF.cpp:1146-1178)
@@ -18,8 +14,6 @@
 #include "rf_types.h"
 
 namespace rfb200 {
-
-__constant__ PlaneF c_planes[kMaxPlanes];   // per-(image,symmetry) rotation data, 48 KB
 
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ int d_wrap(int x, int n) {
@@ -254,348 +248,7 @@ __device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const SlicePar
     d_ctf_rules<float>(v, sp.minCtfF, sp.phaseFlipped, j, ip, wCTF, wMod);
 }
 
-// contribution of original half-plane pixel (j >= 0, ip): (re, im, m) = (wCTF*w*F, w), w = weight*wModulator
-__device__ __forceinline__ float4 d_pixel_contrib(const float2* __restrict__ fft, const int* __restrict__ jmax,
-                                                  const SliceParams& sp, const CtfConsts* ctf, float weight, int j, int ip) {
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ip < sp.iLo || ip > sp.iHi) return out;
-    if (j > jmax[ip - sp.iLo]) return out;            // resolution cut-off, RF.cpp:597
-    int row = ip < 0 ? ip + sp.P : ip;
-    float2 F = __ldg(fft + (size_t)row * sp.Xh + j);
-    float wc = 1.f, wm = 1.f;
-    if (sp.useCtf) d_ctf_weights(*ctf, sp, j, ip, wc, wm);
-    float w = weight * wm;
-    float s = w * wc * sp.invP2;
-    out.x = F.x * s;
-    out.y = F.y * s;
-    out.z = w;
-    out.w = weight;      // weight without the CTF modulator: what a --iter > 1 re-insertion pass adds (RF.cpp:770-775)
-    return out;
-}
-
-// grid (ceil((R+1)/32), ceil((2R+1)/32), nImg), block (32, 8): threadIdx.x runs along j (coalesced reads of
-// the FFT rows and writes of the slice rows), every thread handles 4 rows.  A thread owns original half-plane
-// pixels (j >= 0, ip) inside the bounding square; it writes its own entry and the Hermitian mirror entry of
-// the full-plane slice.
-constexpr int kSliceRowsPerThread = 4;
-__global__ void __launch_bounds__(256, 4) k_make_slices(const float2* __restrict__ fft, float4* __restrict__ slices,
-                                                     float4* __restrict__ col0, const ImgParams* __restrict__ ip,
-                                                     const CtfConsts* __restrict__ ctfs, const int* __restrict__ jmax,
-                                                     const __grid_constant__ SliceParams sp) {
-    const int j = blockIdx.x * 32 + threadIdx.x;
-    if (j > sp.R) return;
-    const int img = blockIdx.z;
-    const float2* f = fft + (size_t)img * sp.P * sp.Xh;
-    const CtfConsts* ctf = sp.useCtf ? ctfs + img : nullptr;
-    const float weight = ip[img].weight;
-    float4* S = slices + (size_t)img * sp.side * sp.side;
-    const int rowBase = blockIdx.y * (8 * kSliceRowsPerThread) + threadIdx.y;
-#pragma unroll 2
-    for (int q = 0; q < kSliceRowsPerThread; ++q) {
-        const int r = rowBase + 8 * q;
-        if (r > 2 * sp.R) break;
-        const int ipx = r - sp.R;
-        float4 c = d_pixel_contrib(f, jmax, sp, ctf, weight, j, ipx);
-        if (j > 0) {
-            S[(size_t)(ipx + sp.Rp) * sp.side + (j + sp.Rp)] = c;
-            S[(size_t)(-ipx + sp.Rp) * sp.side + (-j + sp.Rp)] = make_float4(c.x, -c.y, c.z, c.w);
-        } else {
-            // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference
-            // inserts this column twice for x > 0 voxels
-            float4 m = d_pixel_contrib(f, jmax, sp, ctf, weight, 0, -ipx);
-            S[(size_t)(ipx + sp.Rp) * sp.side + sp.Rp] = make_float4(c.x + m.x, c.y - m.y, c.z + m.z, c.w + m.w);
-            col0[(size_t)img * sp.side + (ipx + sp.Rp)] = c;
-        }
-    }
-}
-
-// ================================================================== K2
-struct GatherArgs {
-    Geometry geo;
-    const int32_t* tileList;
-    int nTiles;
-    int* tileCounter;
-    const float* blobTable;      // kBlobTable floats
-    const PlaneD* planesD;       // nPlanes
-    const float* planesSoA;      // 9 x kMaxPlanes floats: e1x,e1y,e1z,e2x,e2y,e2z,nx,ny,nz
-    int nPlanes;
-    const float4* slices;        // per image side*side float4
-    size_t sliceStride;          // side*side
-    float2* Vb;
-    float* Wb;
-    float* Wb2;                  // un-modulated weight sum, only for --iter > 1 with CTF (else nullptr)
-};
-
-#ifndef RF_GATHER_THREADS
-#define RF_GATHER_THREADS 512
-#endif
-constexpr int kGatherThreads = RF_GATHER_THREADS;   // warps take bricks of the tile from a shared counter
-constexpr size_t kGatherSmem = kMaxPlanes * sizeof(Hit) + 64 * sizeof(int);   // dynamic part (the blob table is static)
-#ifndef RF_GATHER_CTAS
-#define RF_GATHER_CTAS 2
-#endif
-static_assert(kMaxPlanes <= kGatherThreads, "phase A maps one thread to one plane");
-
-template <int K, bool kTwoW>
-__global__ void __launch_bounds__(kGatherThreads, RF_GATHER_CTAS) k_gather(const __grid_constant__ GatherArgs a) {
-    const Geometry& c_geo = a.geo;
-    __shared__ float tbl[kBlobTable];          // static: its shared address is a compile-time constant
-    extern __shared__ __align__(16) unsigned char smem[];
-    Hit* hits = reinterpret_cast<Hit*>(smem);
-    int* sInt = reinterpret_cast<int*>(smem + kMaxPlanes * sizeof(Hit));
-    // sInt[0..31] warp counts, sInt[32] tile, sInt[33] hit count, sInt[34] next brick, sInt[40] table address
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kBlobTable; i += kGatherThreads) tbl[i] = __ldg(a.blobTable + i);
-
-    const int Z = c_geo.Z, lo = c_geo.lo, hi = c_geo.hi;
-    const float r2 = c_geo.r2, rho = c_geo.rho, s2 = c_geo.s2, iDelta = c_geo.iDelta, rr = c_geo.r;
-    const float kI = s2 * iDelta, sMax = c_geo.sMax;
-    // Shared byte address of tbl[0] minus (bits(2^23) << 2), modulo 2^32 (see the lookup below).  Routed through
-    // shared memory so that the compiler treats it as an opaque value: the lookup address is then one LEA.
-    if (threadIdx.x == 0) sInt[40] = (int)((uint32_t)__cvta_generic_to_shared(tbl) - (0x4B000000u << 2));
-    __syncthreads();
-    const uint32_t tblAdj = (uint32_t)((volatile int*)sInt)[40];
-    const int Rp = c_geo.Rp, side = c_geo.side;
-    // lane -> voxel inside a 4x4x2 brick
-    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
-    // tile-level culling constants: half extents of the 16x16x8 lattice box around its centre
-    const float hx = 0.5f * (kTileX - 1), hy = 0.5f * (kTileY - 1), hz = 0.5f * (kTileZ - 1);
-    const float inplaneLim = c_geo.inplane_reach + sqrtf(hx * hx + hy * hy + hz * hz) * sqrtf(1.0f / s2) + 1.0f;
-    const float reach2 = c_geo.reach * c_geo.reach + 1.0f;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) { sInt[32] = atomicAdd(a.tileCounter, 1); sInt[33] = 0; sInt[34] = 0; }
-        __syncthreads();
-        const int t = sInt[32];
-        if (t >= a.nTiles) break;
-        const int tileId = __ldg(a.tileList + t);
-        const int ttx = tileId % c_geo.tx, tty = (tileId / c_geo.tx) % c_geo.ty, ttz = tileId / (c_geo.tx * c_geo.ty);
-        const int ox = ttx * kTileX, oy = lo + tty * kTileY, oz = lo + ttz * kTileZ;
-
-        // ---------------- phase A: which planes of the chunk come near this tile? (thread <-> plane)
-        {
-            const float cx = ox + hx, cy = oy + hy, cz = oz + hz;
-            const int k = tid;
-            bool hit = false;
-            Hit e;
-            if (k < a.nPlanes) {
-                const float* s = a.planesSoA + k;
-                const float nx = __ldg(s + 6 * kMaxPlanes), ny = __ldg(s + 7 * kMaxPlanes), nz = __ldg(s + 8 * kMaxPlanes);
-                const float hc = cx * nx + cy * ny + cz * nz;
-                const float supp = hx * fabsf(nx) + hy * fabsf(ny) + hz * fabsf(nz);
-                if (fabsf(hc) <= rr + supp + 1e-2f) {
-                    float ac = cx * __ldg(s) + cy * __ldg(s + kMaxPlanes) + cz * __ldg(s + 2 * kMaxPlanes);
-                    float bc = cx * __ldg(s + 3 * kMaxPlanes) + cy * __ldg(s + 4 * kMaxPlanes) + cz * __ldg(s + 5 * kMaxPlanes);
-                    if (fabsf(ac) <= inplaneLim && fabsf(bc) <= inplaneLim) {
-                        const PlaneD pd = a.planesD[k];
-                        double a0 = ox * pd.e1[0] + oy * pd.e1[1] + oz * pd.e1[2];
-                        double b0 = ox * pd.e2[0] + oy * pd.e2[1] + oz * pd.e2[2];
-                        double h0 = ox * pd.n[0] + oy * pd.n[1] + oz * pd.n[2];
-                        double ja = rint(a0), jb = rint(b0);
-                        e.k = k;
-                        e.ja0 = (int)ja;
-                        e.jb0 = (int)jb;
-                        e.fa = (float)(a0 - ja);
-                        e.fb = (float)(b0 - jb);
-                        e.h0 = (float)h0;
-                        // brick mask: bricks whose 4x4x2 box comes within the blob radius of the plane
-                        const float bs = 1.5f * fabsf(nx) + 1.5f * fabsf(ny) + 0.5f * fabsf(nz) + rr + 1e-2f;
-                        const float hb0 = e.h0 + 1.5f * nx + 1.5f * ny + 0.5f * nz;   // centre of brick (0,0,0)
-                        uint32_t mlo = 0, mhi = 0;
-#pragma unroll
-                        for (int bk = 0; bk < 4; ++bk)
-#pragma unroll
-                            for (int bj = 0; bj < 4; ++bj)
-#pragma unroll
-                                for (int bi = 0; bi < 4; ++bi) {
-                                    const float hb = hb0 + 4.0f * bi * nx + 4.0f * bj * ny + 2.0f * bk * nz;
-                                    const int b = bi | (bj << 2) | (bk << 4);
-                                    if (fabsf(hb) <= bs) {
-                                        if (b < 32) mlo |= 1u << b;
-                                        else mhi |= 1u << (b - 32);
-                                    }
-                                }
-                        e.maskLo = mlo;
-                        e.maskHi = mhi;
-                        hit = (mlo | mhi) != 0;
-                    }
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) sInt[warp] = __popc(m);
-            __syncthreads();
-            int off = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kGatherThreads / 32; ++w) {
-                int c = sInt[w];
-                if (w < warp) off += c;
-                total += c;
-            }
-            if (hit) hits[off + __popc(m & ((1u << lane) - 1u))] = e;
-            if (tid == 0) sInt[33] = total;
-        }
-        __syncthreads();
-        const int nHits = sInt[33];
-        if (nHits == 0) continue;
-
-        // ---------------- phase B: warps take bricks from a shared counter; every lane gathers for its own voxel
-        for (;;) {
-            int brick = 0;
-            if (lane == 0) brick = atomicAdd(&sInt[34], 1);
-            brick = __shfl_sync(0xffffffffu, brick, 0);
-            if (brick >= kBricks) break;
-            const int vx = ((brick & 3) << 2) | lx, vy = (((brick >> 2) & 3) << 2) | ly, vz = ((brick >> 4) << 1) | lz;
-            const int ux = ox + vx, uy = oy + vy, uz = oz + vz;
-            bool owned = (ux <= Z / 2) && (uy <= hi) && (uz <= hi) && d_main_owns(c_geo, ux, uy);
-            owned = owned && ((float)ux * ux + (float)uy * uy + (float)uz * uz <= reach2);
-            if (!__any_sync(0xffffffffu, owned)) continue;
-            const float vxf = (float)vx, vyf = (float)vy, vzf = (float)vz;
-            const uint32_t bitLo = brick < 32 ? (1u << brick) : 0u, bitHi = brick < 32 ? 0u : (1u << (brick - 32));
-            float accRe = 0.f, accIm = 0.f, accW = 0.f, accW2 = 0.f;
-            for (int eI = 0; eI < nHits; ++eI) {
-                const uint2 mk = *reinterpret_cast<const uint2*>(&hits[eI].maskLo);
-                if (((mk.x & bitLo) | (mk.y & bitHi)) == 0) continue;
-                const Hit H = hits[eI];
-                const PlaneF& pl = c_planes[H.k];
-                const float h = fmaf(vzf, pl.n[2], fmaf(vyf, pl.n[1], fmaf(vxf, pl.n[0], H.h0)));
-                const float h2 = h * h;
-                const bool in = owned && (h2 <= r2);
-                if (!__any_sync(0xffffffffu, in)) continue;
-                if (in) {
-                    const float ar = fmaf(vzf, pl.e1[2], fmaf(vyf, pl.e1[1], fmaf(vxf, pl.e1[0], H.fa)));
-                    const float br = fmaf(vzf, pl.e2[2], fmaf(vyf, pl.e2[1], fmaf(vxf, pl.e2[0], H.fb)));
-                    const int jw = __float2int_ru(ar - rho);
-                    const int iw = __float2int_ru(br - rho);
-                    const int jAbs = H.ja0 + jw + Rp, iAbs = H.jb0 + iw + Rp;   // slice coordinates of the window origin
-                    if ((unsigned)jAbs <= (unsigned)(side - K) && (unsigned)iAbs <= (unsigned)(side - K)) {
-                        // squared distances pre-scaled by iDelta: S = d^2 * iDelta is directly the table coordinate
-                        float dxs[K], dys[K];
-                        const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
-                        const float h2s = h2 * iDelta;
-#pragma unroll
-                        for (int q = 0; q < K; ++q) {
-                            float da = da0 - (float)q, db = db0 - (float)q;
-                            dxs[q] = kI * da * da;
-                            dys[q] = fmaf(kI * db, db, h2s);
-                        }
-                        const float4* p = a.slices + ((size_t)pl.img * a.sliceStride + (size_t)(iAbs * side + jAbs));
-#pragma unroll
-                        for (int ti = 0; ti < K; ++ti) {
-#pragma unroll
-                            for (int tj = 0; tj < K; ++tj) {
-                                const float S = dys[ti] + dxs[tj];
-                                if (S <= sMax) {
-                                    // (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in
-                                    // the mantissa; (bits << 2) + tblAdj is then the shared-memory byte address of the entry
-                                    const uint32_t addr = (__float_as_uint(S + 8388608.0f) << 2) + tblAdj;
-                                    float w;
-                                    asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(addr));
-                                    const float4 px = __ldg(p + tj);
-                                    accRe = fmaf(w, px.x, accRe);
-                                    accIm = fmaf(w, px.y, accIm);
-                                    accW = fmaf(w, px.z, accW);
-                                    if (kTwoW) accW2 = fmaf(w, px.w, accW2);
-                                }
-                            }
-                            p += side;
-                        }
-                    }
-                }
-            }
-            // one coalesced read-modify-write of the brick (blocked layout: 32 consecutive slots)
-            if (owned && (accW != 0.f || accRe != 0.f || accIm != 0.f)) {
-                const size_t o = (size_t)tileId * kTileVox + (size_t)brick * 32 + lane;
-                float2 v = a.Vb[o];
-                v.x += accRe;
-                v.y += accIm;
-                a.Vb[o] = v;
-                a.Wb[o] += accW;
-                if (kTwoW) a.Wb2[o] += accW2;
-            }
-        }
-    }
-}
-
-// ================================================================== K2e
-struct EdgeArgs {
-    Geometry geo;
-    const EdgeItem* items;       // sorted by target voxel
-    const int32_t* groupStart;   // nGroups+1 offsets: items of one group share the target
-    int nGroups;
-    const PlaneD* planesD;
-    const int* planeImg;
-    int nPlanes;
-    const float* blobTable;
-    const float4* slices;
-    const float4* col0;
-    size_t sliceStride;
-    float2* Vb;
-    float* Wb;
-    float* Wb2;                  // may be nullptr
-    double iDeltaD;
-};
-
-// One thread per edge TARGET voxel (it walks the lattice points aliased onto that voxel), brute force
-// over the planes of the chunk, double precision positions.  These points are few: caps of the reach
-// sphere poking through the Nyquist faces, the x = Z/2 plane and one row of the x = 0 plane.
-__global__ void __launch_bounds__(128) k_edge(const __grid_constant__ EdgeArgs a) {
-    const Geometry& c_geo = a.geo;
-    int grp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp >= a.nGroups) return;
-    const double r2 = (double)c_geo.r * (double)c_geo.r, rho = c_geo.rho, s2 = c_geo.s2;
-    const double lim = c_geo.inplane_reach;
-    const int Rp = c_geo.Rp, side = c_geo.side, K = c_geo.K;
-    double accRe = 0, accIm = 0, accW = 0, accW2 = 0;
-    const int i0 = a.groupStart[grp], i1 = a.groupStart[grp + 1];
-    const int64_t store = a.items[i0].store;
-    for (int it = i0; it < i1; ++it) {
-        const EdgeItem e = a.items[it];
-        const double ux = e.ux, uy = e.uy, uz = e.uz;
-        for (int k = 0; k < a.nPlanes; ++k) {
-            const PlaneD& pl = a.planesD[k];
-            double h = ux * pl.n[0] + uy * pl.n[1] + uz * pl.n[2];
-            double h2 = h * h;
-            if (h2 > r2) continue;
-            double al = ux * pl.e1[0] + uy * pl.e1[1] + uz * pl.e1[2];
-            double be = ux * pl.e2[0] + uy * pl.e2[1] + uz * pl.e2[2];
-            if (fabs(al) > lim || fabs(be) > lim) continue;
-            int jw = (int)ceil(al - rho), iw = (int)ceil(be - rho);
-            const int img = a.planeImg[k];
-            const float4* S = a.slices + (size_t)img * a.sliceStride;
-            const float4* C0 = a.col0 + (size_t)img * side;
-            for (int ti = 0; ti < K; ++ti) {
-                int ip = iw + ti;
-                double db = be - ip;
-                double rowd2 = h2 + s2 * db * db;
-                if (rowd2 > r2) continue;
-                for (int tj = 0; tj < K; ++tj) {
-                    int j = jw + tj;
-                    double da = al - j;
-                    double d2 = rowd2 + s2 * da * da;
-                    if (d2 > r2) continue;
-                    if (e.mode == 1 && j < 0) continue;                 // originals only
-                    int idx = (int)(d2 * a.iDeltaD + 0.5);              // RF.cpp:725
-                    float w = __ldg(a.blobTable + idx);
-                    float4 px = (e.mode == 1 && j == 0) ? __ldg(C0 + (ip + Rp)) : __ldg(S + (size_t)(ip + Rp) * side + (j + Rp));
-                    accRe += (double)w * px.x;
-                    accIm += (double)w * px.y;
-                    accW += (double)w * px.z;
-                    accW2 += (double)w * px.w;
-                }
-            }
-        }
-    }
-    if (accW != 0 || accRe != 0 || accIm != 0 || accW2 != 0) {
-        float2 v = a.Vb[store];
-        v.x += (float)accRe;
-        v.y += (float)accIm;
-        a.Vb[store] = v;
-        a.Wb[store] += (float)accW;
-        if (a.Wb2) a.Wb2[store] += (float)accW2;
-    }
-}
+constexpr int kSliceRowsPerThread = 4;   // rows handled by one thread of the slice kernel
 
 // ================================================================== K3a
 struct NormArgs {

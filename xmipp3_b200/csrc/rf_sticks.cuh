@@ -23,7 +23,10 @@
 
 namespace rfb200 {
 
-__constant__ PlaneS c_planesS[kMaxPlanes];   // class-sorted planes of one launch, components permuted to (a,b,d)
+// class-sorted planes of one launch, components permuted to (a,b,d): FP32 for the per-voxel arithmetic, FP64 for the
+// projection of the stick origins (24 KB + 36 KB of the 64 KB constant bank; every access is warp-uniform)
+__constant__ PlaneS c_planesS[kMaxPlanes];
+__constant__ PlaneD c_planesD[kMaxPlanes];
 
 #ifndef RF_STICK_WARPS
 #define RF_STICK_WARPS 16
@@ -132,7 +135,6 @@ struct StickArgs {
     int cls;                     // 0: d = x, 1: d = y, 2: d = z
     int kBegin, kEnd;            // planes [kBegin, kEnd) of c_planesS belong to this class
     const float* blobTable;
-    const PlaneD* planesDp;      // same order and permutation as c_planesS, double precision
     const float* planesSoA;      // 9 x kMaxPlanes floats, same order and permutation (culling phase, lane <-> plane)
     const float4* slices;        // slice format v2: overlapping pixel pairs
     const int* rimTab;           // already offset by +Rp: index with the centred row
@@ -449,7 +451,7 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
                 m &= m - 1;
                 // ---- set up task k
                 const PlaneS& pl = c_planesS[k];
-                const PlaneD pd = a.planesDp[k];
+                const PlaneD& pd = c_planesD[k];
                 const double a0 = A0c * pd.e1[0] + B0c * pd.e1[1] + T0c * pd.e1[2];
                 const double b0 = A0c * pd.e2[0] + B0c * pd.e2[1] + T0c * pd.e2[2];
                 const double h0 = A0c * pd.n[0] + B0c * pd.n[1] + T0c * pd.n[2];

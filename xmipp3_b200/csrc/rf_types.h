@@ -5,11 +5,10 @@
 
 namespace rfb200 {
 
-// A tile is the unit of work of one CTA: 16 x 16 x 8 voxels = 64 bricks of 4 x 4 x 2 voxels.  A warp owns one
-// brick at a time (lane <-> voxel), so a brick is compact in space and its 32 accumulators are contiguous.
+// Blocked accumulator layout: tiles of 16 x 16 x 8 voxels, each made of 64 bricks of 4 x 4 x 2 voxels whose 32
+// accumulators are contiguous (one coalesced warp access per brick).
 constexpr int kTileX = 16, kTileY = 16, kTileZ = 8;
 constexpr int kTileVox = kTileX * kTileY * kTileZ;   // 2048
-constexpr int kBricks = kTileVox / 32;               // 64: one bit each in Hit::mask
 constexpr int kMaxPlanes = 512;              // (image, symmetry) planes per gather launch; fits __constant__
 constexpr int kBlobTable = 10000;            // BLOB_TABLE_SIZE_SQRT (reconstruct_fourier.h:41-44)
 constexpr int kMaxWin = 8;                   // largest candidate window edge supported by the gather
@@ -20,14 +19,7 @@ constexpr int kMaxWin = 8;                   // largest candidate window edge su
 //   beta  = u . e2   (pixel units along image y)
 //   h     = u . n    (voxel units, signed distance to the plane)
 // with e1 = M[:,0]*(P/Z), e2 = M[:,1]*(P/Z), n = M[:,2].
-struct PlaneF {            // 48 B, lives in __constant__ memory
-    float e1[3];
-    float e2[3];
-    float n[3];
-    int32_t img;           // image index inside the chunk
-    float pad0, pad1;
-};
-struct PlaneD {            // 72 B, global memory (tile-origin projections are done in double)
+struct PlaneD {            // 72 B: double-precision plane (stick-origin projections, edge and damped-weight kernels)
     double e1[3];
     double e2[3];
     double n[3];
@@ -50,16 +42,6 @@ struct ImgParams {         // per image of a chunk
     int32_t spline;        // 1: cubic B-spline interpolation (a shift is fractional), 0: exact circular shift
     int32_t skip;          // weight == 0 -> image not inserted (RF.cpp:483-484)
     int32_t pad0;
-};
-
-// A CTA-level hit: plane `k` intersects the tile.  Tile-origin projection split into
-// integer pixel + fraction so that the per-voxel FP32 arithmetic only sees small numbers.
-struct Hit {                // 32 B
-    int32_t k;             // plane index in the chunk
-    int32_t ja0, jb0;      // rint(alpha0), rint(beta0) of the tile origin
-    float fa, fb;          // alpha0 - ja0, beta0 - jb0   in [-0.5, 0.5]
-    float h0;              // height of the tile origin
-    uint32_t maskLo, maskHi;   // bricks of the tile whose voxels can lie within the blob radius of the plane
 };
 
 // Edge work item: a lattice point that the main gather does not own (orig-only planes
