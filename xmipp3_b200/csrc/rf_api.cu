@@ -145,6 +145,7 @@ struct rfb200_handle_s {
     float2* dCol02 = nullptr;
     float* dDamped = nullptr;       // per image (2R+1) x (R+1) weights of the CTF-damped (flagged) pixels (use_ctf only)
     float* dDamped2 = nullptr;      // their un-modulated weights (use_ctf && n_iter_weight > 1)
+    uint32_t* dDampedMask = nullptr;   // per image (2R+1) x ceil((R+1)/32) words: which pixels are flagged
     unsigned long long* dD = nullptr;   // blocked volume of 2^32 fixed-point damped-pixel weights (use_ctf only)
     unsigned long long* dD2 = nullptr;  // same for the un-modulated weights
     bool dampedDirty = false;
@@ -400,7 +401,7 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
         Slice2Args a{};
         a.sp = make_slice_params(h);
         a.pitch = g.pitch; a.planeStride = g.planeStride;
-        a.fft = h->dFft; a.slices = h->dSlices2; a.col0 = h->dCol02; a.damped = h->dDamped; a.damped2 = h->dDamped2;
+        a.fft = h->dFft; a.slices = h->dSlices2; a.col0 = h->dCol02; a.damped = h->dDamped; a.damped2 = h->dDamped2; a.dampedMask = h->dDampedMask;
         a.ip = h->dImg; a.ctfs = h->dCtf; a.jmax = h->dJmax;
         dim3 grid((g.R + 1 + 31) / 32, (2 * g.R + 1 + 8 * kSliceRowsPerThread - 1) / (8 * kSliceRowsPerThread), n);
         k_make_slices2<<<grid, dim3(32, 8), 0, h->compute>>>(a);
@@ -456,11 +457,11 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
         StageTimer t(h, Stage::EDGE, h->compute);
         DampedArgs d{};
         d.geo = g;
-        d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
+        d.mask = h->dDampedMask; d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
         d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
         d.D = h->dD; d.D2 = h->dD2;
-        const int total = (g.R + 1) * (2 * g.R + 1);
-        k_damped_scatter<<<dim3((total + 256 * kDampedPerThread - 1) / (256 * kDampedPerThread), n), 256, 0, h->compute>>>(d);
+        const int nWords = ((g.R + 1 + 31) / 32) * (2 * g.R + 1);
+        k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, h->compute>>>(d);
         RF_CUDA(h, cudaGetLastError());
         h->nKernelLaunches += 1;
         h->dampedDirty = true;
@@ -536,7 +537,7 @@ void free_all(rfb200_handle h) {
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dEdge, h->dEdgeGroups, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
                    h->dPad, h->dCoef, h->dFft, h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dNorm,
-                   h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
+                   h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dDampedMask, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
                    h->dStickCounters, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
@@ -647,6 +648,7 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMemcpy(h->dRimTab, rimTab.data(), sizeof(int32_t) * rimTab.size(), cudaMemcpyHostToDevice));
         if (c.use_ctf) {
             RF_CUDA(h, cudaMalloc(&h->dDamped, sizeof(float) * CH * (size_t)(2 * g.R + 1) * (g.R + 1)));
+            RF_CUDA(h, cudaMalloc(&h->dDampedMask, sizeof(uint32_t) * CH * (size_t)(2 * g.R + 1) * ((g.R + 1 + 31) / 32)));
             RF_CUDA(h, cudaMalloc(&h->dD, sizeof(unsigned long long) * h->nBlocked));
             RF_CUDA(h, cudaMemset(h->dD, 0, sizeof(unsigned long long) * h->nBlocked));
             if (c.n_iter_weight > 1) {

@@ -77,6 +77,7 @@ struct Slice2Args {
     float2* col0;         // per image `side` originals-only entries of column j = 0
     float* damped;        // per image (2R+1) x (R+1): true weight of a flagged pixel, -1 if not flagged; nullptr without CTF
     float* damped2;       // same shape: un-modulated weight of a flagged pixel (only for --iter > 1), else nullptr
+    uint32_t* dampedMask; // per image (2R+1) x ceil((R+1)/32) words: bit b of word w of a row <-> column 32w+b is flagged
     const ImgParams* ip;
     const CtfConsts* ctfs;
     const int* jmax;
@@ -86,7 +87,7 @@ struct Slice2Args {
 __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__ Slice2Args a) {
     const SliceParams& sp = a.sp;
     const int j = blockIdx.x * 32 + threadIdx.x;
-    if (j > sp.R) return;
+    const bool active = j <= sp.R;          // a warp = 32 consecutive columns of one row; no early exit (ballots below)
     const int img = blockIdx.z;
     const float2* f = a.fft + (size_t)img * sp.P * sp.Xh;
     const CtfConsts* ctf = sp.useCtf ? a.ctfs + img : nullptr;
@@ -95,34 +96,42 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
     // its own entry and to the second half of the entry on its left: two adjacent 8-byte stores
     float2* S2 = reinterpret_cast<float2*>(a.slices + (size_t)img * a.planeStride);
     const size_t dOff = (size_t)img * (2 * sp.R + 1) * (sp.R + 1);
+    const int wordsPerRow = (sp.R + 1 + 31) / 32;
     const int rowBase = blockIdx.y * (8 * kSliceRowsPerThread) + threadIdx.y;
 #pragma unroll 2
     for (int q = 0; q < kSliceRowsPerThread; ++q) {
         const int r = rowBase + 8 * q;
         if (r > 2 * sp.R) break;
         const int ipx = r - sp.R;
-        float4 c = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, j, ipx);
-        const size_t o1 = (size_t)(ipx + sp.Rp) * a.pitch + (j + sp.Rp);
-        bool flag = c.w != 0.f;
-        float unmod = (c.z != 0.f || flag) ? weight : 0.f;       // weight of a valid pixel without the CTF modulator
-        if (j > 0) {
-            const size_t o2 = (size_t)(-ipx + sp.Rp) * a.pitch + (-j + sp.Rp);
-            const float re = d_set_flag(c.x, flag);
-            const float2 v = make_float2(re, c.y), vm = make_float2(re, -c.y);
-            S2[2 * o1] = v;  S2[2 * o1 - 1] = v;
-            S2[2 * o2] = vm; S2[2 * o2 - 1] = vm;
-        } else {
-            // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference inserts this
-            // column twice for x > 0 voxels.  The combined entry is flagged if either part is damped;
-            // the damped-weight pass then supplies the weights of both parts.
-            float4 m = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, 0, -ipx);
-            flag = flag || (m.w != 0.f);
-            const float2 v = make_float2(d_set_flag(c.x + m.x, flag), c.y - m.y);
-            S2[2 * o1] = v; S2[2 * o1 - 1] = v;
-            a.col0[(size_t)img * sp.side + (ipx + sp.Rp)] = make_float2(d_set_flag(c.x, flag), c.y);
+        bool flag = false;
+        if (active) {
+            float4 c = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, j, ipx);
+            const size_t o1 = (size_t)(ipx + sp.Rp) * a.pitch + (j + sp.Rp);
+            flag = c.w != 0.f;
+            float unmod = (c.z != 0.f || flag) ? weight : 0.f;       // weight of a valid pixel without the CTF modulator
+            if (j > 0) {
+                const size_t o2 = (size_t)(-ipx + sp.Rp) * a.pitch + (-j + sp.Rp);
+                const float re = d_set_flag(c.x, flag);
+                const float2 v = make_float2(re, c.y), vm = make_float2(re, -c.y);
+                S2[2 * o1] = v;  S2[2 * o1 - 1] = v;
+                S2[2 * o2] = vm; S2[2 * o2 - 1] = vm;
+            } else {
+                // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference inserts this
+                // column twice for x > 0 voxels.  The combined entry is flagged if either part is
+                // damped; the damped-weight pass then supplies the weights of both parts.
+                float4 m = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, 0, -ipx);
+                flag = flag || (m.w != 0.f);
+                const float2 v = make_float2(d_set_flag(c.x + m.x, flag), c.y - m.y);
+                S2[2 * o1] = v; S2[2 * o1 - 1] = v;
+                a.col0[(size_t)img * sp.side + (ipx + sp.Rp)] = make_float2(d_set_flag(c.x, flag), c.y);
+            }
+            if (a.damped && flag) a.damped[dOff + (size_t)r * (sp.R + 1) + j] = c.z;
+            if (a.damped2 && flag) a.damped2[dOff + (size_t)r * (sp.R + 1) + j] = unmod;
         }
-        if (a.damped) a.damped[dOff + (size_t)r * (sp.R + 1) + j] = flag ? c.z : -1.f;
-        if (a.damped2) a.damped2[dOff + (size_t)r * (sp.R + 1) + j] = flag ? unmod : -1.f;
+        if (a.dampedMask) {
+            const unsigned mw = __ballot_sync(0xffffffffu, flag);
+            if (threadIdx.x == 0) a.dampedMask[((size_t)img * (2 * sp.R + 1) + r) * wordsPerRow + blockIdx.x] = mw;
+        }
     }
 }
 
@@ -635,7 +644,8 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
 // ================================================================== K2r
 struct DampedArgs {
     Geometry geo;
-    const float* damped;         // per image (2R+1) x (R+1): weight of a flagged pixel, -1 if not flagged
+    const uint32_t* mask;        // per image (2R+1) x ceil((R+1)/32) words of flagged columns
+    const float* damped;         // per image (2R+1) x (R+1): weight of a flagged pixel (only flagged entries are valid)
     const float* damped2;        // un-modulated weights (with D2), or nullptr
     int nImg;
     const int* imgPlane0;        // first plane of image i in planesD (-1: image skipped)
@@ -647,29 +657,21 @@ struct DampedArgs {
     unsigned long long* D2;      // same for the un-modulated weights (--iter > 1), or nullptr
 };
 
-// grid (ceil((R+1)*(2R+1)/(256*kDampedPerThread)), nImg).  Every thread reads kDampedPerThread entries (all loads in
-// flight together); the warp then walks its flagged entries one at a time (they are rare), the 32 lanes sharing the
-// (floor(2r)+1)^3 candidate lattice points of the pixel.  This is the reference's scatter (RF.cpp:628-792) restricted
-// to W of those pixels.
-constexpr int kDampedPerThread = 8;
+// grid (ceil(words/256), nImg).  Every thread reads one word of the flag mask (32 pixels); the warp then walks the
+// flagged pixels one at a time (they are rare), the 32 lanes sharing the (floor(2r)+1)^3 candidate lattice points
+// of the pixel.  This is the reference's scatter (RF.cpp:628-792) restricted to W of those pixels.
 __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ DampedArgs a) {
     const Geometry& geo = a.geo;
     const int R = geo.R, Z = geo.Z;
     const int img = blockIdx.y;
     const int cols = R + 1, total = cols * (2 * R + 1);
+    const int wordsPerRow = (cols + 31) / 32, nWords = wordsPerRow * (2 * R + 1);
     const int lane = threadIdx.x & 31;
-    const int idx0 = blockIdx.x * (256 * kDampedPerThread) + threadIdx.x;
-    float dv[kDampedPerThread], dv2[kDampedPerThread];
-#pragma unroll
-    for (int e = 0; e < kDampedPerThread; ++e) {
-        const int idx = idx0 + 256 * e;
-        dv[e] = -1.f;
-        dv2[e] = 0.f;
-        if (idx < total) {
-            dv[e] = __ldg(a.damped + (size_t)img * total + idx);
-            if (a.damped2) dv2[e] = fmaxf(__ldg(a.damped2 + (size_t)img * total + idx), 0.f);
-        }
-    }
+    const int widx0 = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t word = 0;
+    if (widx0 < nWords) word = __ldg(a.mask + (size_t)img * nWords + widx0);
+    unsigned any = __ballot_sync(0xffffffffu, word != 0);
+    if (!any) return;
     const int p0 = a.imgPlane0[img];
     if (p0 < 0) return;
     const double r = geo.r, r2 = r * r;
@@ -686,20 +688,18 @@ __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ 
     }
     // |u| <= Z/2 + r + 1, so one conditional add wraps an index into [0, Z)
     auto wrap1 = [Z](int x) { return x < 0 ? x + Z : (x >= Z ? x - Z : x); };
-#pragma unroll 1
-    for (int e = 0; e < kDampedPerThread; ++e) {
-      float d = -1.f, d2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < kDampedPerThread; ++q)
-          if (q == e) { d = dv[q]; d2 = dv2[q]; }
-      const int idx = idx0 + 256 * e;
-      unsigned m = __ballot_sync(0xffffffffu, d > 0.f || (d >= 0.f && d2 > 0.f));
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float dd = __shfl_sync(0xffffffffu, d, src), dd2 = __shfl_sync(0xffffffffu, d2, src);
-        const int pidx = (idx - lane) + src;
-        const int row = pidx / cols, j = pidx - row * cols, ip = row - R;
+    while (any) {
+      const int srcW = __ffs(any) - 1;
+      any &= any - 1;
+      uint32_t w = __shfl_sync(0xffffffffu, word, srcW);
+      const int widx = (widx0 - lane) + srcW;
+      const int row = widx / wordsPerRow, ip = row - R, jBase = 32 * (widx - row * wordsPerRow);
+      while (w) {
+        const int j = jBase + __ffs(w) - 1;
+        w &= w - 1;
+        const size_t e = (size_t)img * total + (size_t)row * cols + j;
+        const float dd = __ldg(a.damped + e);
+        const float dd2 = a.damped2 ? __ldg(a.damped2 + e) : 0.f;
         for (int s = 0; s < a.nSym; ++s) {
             const PlaneD& pl = a.planesD[p0 + s];
             // position of the pixel in voxel units: e1/e2 carry pixel-per-voxel, so p = (j*e1 + ip*e2) * (Z/P)^2
