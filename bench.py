@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=192, help="particles per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk", type=int, default=1024, help="particles per preprocessing chunk inside the library (max_batch)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -255,7 +256,7 @@ def main():
         batches.append((img, make_particles(B, **cols)))
     torch.cuda.synchronize()
 
-    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=1024)
+    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=args.chunk)
     if world > 1:
         ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

@@ -90,7 +90,14 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
     const bool active = j <= sp.R;          // a warp = 32 consecutive columns of one row; no early exit (ballots below)
     const int img = blockIdx.z;
     const float2* f = a.fft + (size_t)img * sp.P * sp.Xh;
-    const CtfConsts* ctf = sp.useCtf ? a.ctfs + img : nullptr;
+    // the image's CTF constants are staged in shared memory once per CTA (19 doubles that every pixel needs)
+    __shared__ CtfConsts sCtf;
+    if (sp.useCtf) {
+        const int t = threadIdx.y * 32 + threadIdx.x;
+        if (t < (int)(sizeof(CtfConsts) / 8)) reinterpret_cast<double*>(&sCtf)[t] = reinterpret_cast<const double*>(a.ctfs + img)[t];
+        __syncthreads();
+    }
+    const CtfConsts* ctf = sp.useCtf ? &sCtf : nullptr;
     const float weight = a.ip[img].weight;
     // as float2: entry (i,j) = elements 2*(i*pitch+j) [pixel (i,j)] and +1 [pixel (i,j+1)]; a pixel is written to
     // its own entry and to the second half of the entry on its left: two adjacent 8-byte stores
