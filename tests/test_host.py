@@ -151,3 +151,18 @@ def test_cli_binary_reports_errors(tmp_path):
     assert r.returncode == 2 and "-i <md_file>" in r.stderr
     r = subprocess.run([exe, "-i", str(tmp_path / "nope.xmd"), "-v", "0"], capture_output=True, text=True)
     assert r.returncode == 1 and "XMIPP_ERROR" in r.stderr
+
+
+@pytest.mark.parametrize("geo", [dict(N=16), dict(N=25), dict(N=27, pad_proj=1.0, pad_vol=1.0), dict(N=32, pad_proj=1.0, pad_vol=2.0),
+                                 dict(N=32, pad_proj=2.0, pad_vol=1.5), dict(N=32, max_res=0.3), dict(N=24, r=2.4), dict(N=40)],
+                         ids=lambda g: "-".join("%s=%s" % kv for kv in g.items()))
+def test_gather_plan_is_consistent(geo):
+    """Host-side plan of the stick gather (no GPU): every voxel the gather owns is covered by exactly one stick of
+    each plane class, the pixel validity table equals a brute-force evaluation of the resolution cut-off
+    (RF.cpp:594-598), the fast-path radius really is all-valid, and every other reachable lattice point is an
+    edge item."""
+    from xmipp3_b200 import _host
+    res = _host.gather_plan_check(**geo)
+    assert res["units_x"] > 0 and res["units_y"] > 0 and res["units_z"] > 0
+    for k in ("uncovered", "double_covered", "bad_rim_entries", "bad_inner_pixels", "lost_points"):
+        assert res[k] == 0, (k, res)

@@ -26,6 +26,7 @@ def load():
         L.rfh_write_volume.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rfh_write_stack.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_long]
         L.rfh_parse_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int]
+        L.rfh_gather_plan_check.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -100,3 +101,12 @@ def parse_cli(argv):
     if L.rfh_parse_cli(len(argv) + 1, arr, out, 4096) < 0:
         raise _err()
     return dict(l.split("=", 1) for l in out.value.decode().strip().split("\n"))
+
+
+def gather_plan_check(N, pad_proj=2.0, pad_vol=2.0, max_res=0.5, r=1.9):
+    """Host-side plan of the stick gather for one geometry, checked for consistency (see host_abi.cpp)."""
+    out = (C.c_longlong * 9)()
+    if load().rfh_gather_plan_check(int(N), float(pad_proj), float(pad_vol), float(max_res), float(r), out) != 0:
+        raise _err()
+    keys = ("units_x", "units_y", "units_z", "edge_items", "uncovered", "double_covered", "bad_rim_entries", "bad_inner_pixels", "lost_points")
+    return dict(zip(keys, [int(v) for v in out]))
