@@ -247,3 +247,30 @@ def test_error_behaviour():
         r.reduce(0)                                  # no communicator yet
     assert e.value.code == _lib.ERR_STATE
     r.close()
+
+
+def test_fused_fft_chain_matches_cufft_chain(monkeypatch):
+    """The fused preprocessing chain (own shared-memory FFTs, rf_fft.cuh) against the general chain
+    (k_pad_images -> cuFFT R2C -> k_make_slices2) on the same particles: same slices, same accumulators."""
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    for N, pad in ((32, 2.0), (64, 2.0), (128, 1.0), (100, 1.28)):
+        d = synth.make_dataset(24, N, seed=17, ctf=True, shifts=True)
+        p = make_particles(24, **_cols(d, True))
+        kw = dict(use_ctf=True, sampling=d["sampling"], padding=(pad, pad))
+        monkeypatch.delenv("RFB200_FFT", raising=False)
+        a = Reconstructor(N, **kw)
+        a.insert(d["images"], p)
+        Sa, _ = a.debug_slice(3)
+        Va, Wa = a.accumulators()
+        monkeypatch.setenv("RFB200_FFT", "cufft")
+        b = Reconstructor(N, **kw)
+        b.insert(d["images"], p)
+        Sb, _ = b.debug_slice(3)
+        Vb, Wb = b.accumulators()
+        monkeypatch.delenv("RFB200_FFT", raising=False)
+        assert np.abs(Sa[..., :2] - Sb[..., :2]).max() <= 3e-6 * np.abs(Sb[..., :2]).max()
+        assert np.array_equal(Sa[..., 2], Sb[..., 2])
+        assert np.linalg.norm(Va - Vb) <= 3e-6 * np.linalg.norm(Vb)
+        assert np.linalg.norm(Wa - Wb) <= 3e-6 * np.linalg.norm(Wb)
+        a.close()
+        b.close()

@@ -20,6 +20,7 @@
 #include "rf_host.hpp"
 #include "rf_kernels.cuh"
 #include "rf_sticks.cuh"
+#include "rf_fft.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -158,6 +159,9 @@ struct rfb200_handle_s {
     PlaneS* dPlanesSStage = nullptr;
     int* dImgPlane0 = nullptr;
     int stickGrid = 0;
+    // ---- fused FFT chain (power-of-two padded sizes, integer shifts); cuFFT is the general path
+    bool fusedFft = false;
+    float2* dTwiddle = nullptr;
     cudaEvent_t swStart = nullptr, swStop = nullptr;
     bool swStarted = false;
     double* dSum = nullptr;         // 1024 partials + 1 result
@@ -270,6 +274,41 @@ int launch_sticks(rfb200_handle h, const StickArgs& a, int grid) {
         case 8: return launch_sticks_k<8>(h, a, grid);
     }
     return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
+}
+
+template <int P>
+int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& ca, int n) {
+    const Geometry& g = h->geo;
+    const int threads = kFftSeqs * P / 8;
+    const size_t smem = sizeof(float2) * (P + kFftSeqs * kFftBuf<P>);
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    {
+        StageTimer t(h, Stage::FFT2D, h->compute);
+        k_fft_rows<P><<<dim3((g.N + 2 * kFftSeqs - 1) / (2 * kFftSeqs), n), threads, smem, h->compute>>>(ra);
+        RF_CUDA(h, cudaGetLastError());
+    }
+    {
+        StageTimer t(h, Stage::SLICE, h->compute);
+        if (h->dDampedMask)
+            RF_CUDA(h, cudaMemsetAsync(h->dDampedMask, 0, sizeof(uint32_t) * (size_t)n * (2 * g.R + 1) * ((g.R + 1 + 31) / 32), h->compute));
+        k_fft_cols_slices<P><<<dim3((g.R + 1 + kFftSeqs - 1) / kFftSeqs, n), threads, smem, h->compute>>>(ca);
+        RF_CUDA(h, cudaGetLastError());
+    }
+    h->nKernelLaunches += 2;
+    return RFB200_OK;
+}
+int launch_fused_fft(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& ca, int n) {
+    switch (h->geo.P) {
+        case 64: return launch_fused_fft_p<64>(h, ra, ca, n);
+        case 128: return launch_fused_fft_p<128>(h, ra, ca, n);
+        case 256: return launch_fused_fft_p<256>(h, ra, ca, n);
+        case 512: return launch_fused_fft_p<512>(h, ra, ca, n);
+        case 1024: return launch_fused_fft_p<1024>(h, ra, ca, n);
+    }
+    return fail(h, RFB200_ERR_STATE, "fused FFT chain selected for an unsupported padded size");
 }
 
 // W += weights of the CTF-damped pixels; must run before W is read, reduced or copied
@@ -393,21 +432,19 @@ SliceParams make_slice_params(rfb200_handle h) {
 }
 
 // K1b' -> K2' (one launch per plane class) -> K2e' -> K2r for the n images whose half-plane FFTs sit in dFft
+Slice2Args make_slice_args(rfb200_handle h) {
+    const Geometry& g = h->geo;
+    Slice2Args a{};
+    a.sp = make_slice_params(h);
+    a.pitch = g.pitch; a.planeStride = g.planeStride;
+    a.fft = h->dFft; a.slices = h->dSlices2; a.col0 = h->dCol02; a.damped = h->dDamped; a.damped2 = h->dDamped2; a.dampedMask = h->dDampedMask;
+    a.ip = h->dImg; a.ctfs = h->dCtf; a.jmax = h->dJmax;
+    return a;
+}
+
 int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
     const Geometry& g = h->geo;
     int rc = RFB200_OK;
-    {
-        StageTimer t(h, Stage::SLICE, h->compute);
-        Slice2Args a{};
-        a.sp = make_slice_params(h);
-        a.pitch = g.pitch; a.planeStride = g.planeStride;
-        a.fft = h->dFft; a.slices = h->dSlices2; a.col0 = h->dCol02; a.damped = h->dDamped; a.damped2 = h->dDamped2; a.dampedMask = h->dDampedMask;
-        a.ip = h->dImg; a.ctfs = h->dCtf; a.jmax = h->dJmax;
-        dim3 grid((g.R + 1 + 31) / 32, (2 * g.R + 1 + 8 * kSliceRowsPerThread - 1) / (8 * kSliceRowsPerThread), n);
-        k_make_slices2<<<grid, dim3(32, 8), 0, h->compute>>>(a);
-        RF_CUDA(h, cudaGetLastError());
-        h->nKernelLaunches += 1;
-    }
     for (int p0 = 0; p0 < nPlanes; p0 += kMaxPlanes) {
         const int np = std::min(kMaxPlanes, nPlanes - p0);
         const float* soaChunk = slot->soaP + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
@@ -477,6 +514,15 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
     bool anySpline = false;
     int rc = upload_chunk_params(h, meta, n, &slot, &nPlanes, &anySpline);
     if (rc) return rc;
+    if (h->fusedFft && !anySpline) {
+        // K1r -> K1c: shift + pad + FFT + CTF + slices without the padded image and the half-plane transform in HBM
+        FftRowsArgs ra{};
+        ra.raw = dRaw; ra.ip = h->dImg; ra.twiddle = h->dTwiddle; ra.T = h->dFft; ra.N = g.N;
+        FftColsArgs ca{};
+        ca.s = make_slice_args(h); ca.twiddle = h->dTwiddle; ca.T = h->dFft; ca.N = g.N;
+        rc = launch_fused_fft(h, ra, ca, n);
+        if (rc) return rc;
+    } else {
     {
         StageTimer t(h, Stage::PAD, h->compute);
         if (anySpline) {
@@ -497,6 +543,15 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
         rc = get_plan2d(h, n, &plan);
         if (rc) return rc;
         RF_CUFFT(h, cufftExecR2C(plan, h->dPad, reinterpret_cast<cufftComplex*>(h->dFft)));
+    }
+    {
+        StageTimer t(h, Stage::SLICE, h->compute);
+        Slice2Args a = make_slice_args(h);
+        dim3 grid((g.R + 1 + 31) / 32, (2 * g.R + 1 + 8 * kSliceRowsPerThread - 1) / (8 * kSliceRowsPerThread), n);
+        k_make_slices2<<<grid, dim3(32, 8), 0, h->compute>>>(a);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+    }
     }
     rc = insert_planes_sticks(h, slot, n, nPlanes);
     if (rc) return rc;
@@ -538,7 +593,7 @@ void free_all(rfb200_handle h) {
     void* dev[] = {h->dBlobTable, h->dJmax, h->dEdge, h->dEdgeGroups, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
                    h->dPad, h->dCoef, h->dFft, h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dDampedMask, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
-                   h->dStickCounters, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0};
+                   h->dStickCounters, h->dTwiddle, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
         void* hp[] = {s.img, s.ctf, s.planesD, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0};
@@ -611,6 +666,20 @@ int do_create(rfb200_handle h) {
         h->nEdgeGroups = (int)starts.size() - 1;
         RF_CUDA(h, cudaMalloc(&h->dEdgeGroups, sizeof(int32_t) * starts.size()));
         RF_CUDA(h, cudaMemcpy(h->dEdgeGroups, starts.data(), sizeof(int32_t) * starts.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        const int Pp = g.P;
+        const char* e = getenv("RFB200_FFT");          // developer switch: "cufft" forces the general path
+        h->fusedFft = (Pp == 64 || Pp == 128 || Pp == 256 || Pp == 512 || Pp == 1024) && g.N <= Pp && !(e && std::string(e) == "cufft");
+        if (h->fusedFft) {
+            std::vector<float2> tw(Pp);
+            for (int k = 0; k < Pp; ++k) {
+                const double ang = -2.0 * host::kPi * (double)k / (double)Pp;
+                tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+            }
+            RF_CUDA(h, cudaMalloc(&h->dTwiddle, sizeof(float2) * Pp));
+            RF_CUDA(h, cudaMemcpy(h->dTwiddle, tw.data(), sizeof(float2) * Pp, cudaMemcpyHostToDevice));
+        }
     }
     RF_CUDA(h, cudaMalloc(&h->dSum, sizeof(double) * 1025));
     RF_CUDA(h, cudaMallocHost(&h->hSum, sizeof(double)));

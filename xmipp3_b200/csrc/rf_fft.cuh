@@ -1,0 +1,298 @@
+// rf_fft.cuh — fused preprocessing chain for power-of-two padded sizes (sm_100a):
+//
+//   K1r k_fft_rows<P>          raw N x N particle -> (integer shift, zero-pad, CenterFFT as one index map,
+//                              RF.cpp:388-402) -> P-point FFT of the N non-zero rows, two real rows per complex
+//                              transform -> intermediate T[img][kx][row] (kx = 0..P/2), 8 B x (P/2+1) x N per image
+//   K1c k_fft_cols_slices<P>   P-point FFT of every needed column (only N of its P inputs are non-zero), then, on
+//                              the transform still in shared memory, everything k_make_slices2 does: 1/P^2,
+//                              resolution cut-off, CTF weights, flags, pixel-pair slice entries (RF.cpp:405-407,
+//                              594-625)
+//
+// Compared with k_pad_images -> cuFFT R2C -> k_make_slices2 the padded image (4 B x P^2) and the half-plane
+// transform (8 B x P x (P/2+1)) never touch HBM, and the zero rows are never transformed: 0.26 MB read + 0.53 MB
+// intermediate (written and read once) + the slice write per particle instead of ~9 MB.  The transforms are our
+// own shared-memory Stockham FFTs (radix 8/4/2, 8 points per thread and stage, one padded buffer per sequence);
+// cuFFT stays the general path (any size, fractional shifts).
+#pragma once
+#include "rf_sticks.cuh"
+
+namespace rfb200 {
+
+__host__ __device__ constexpr int fft_phys(int i) { return i + (i >> 3); }   // padding: conflict-free strided stores
+template <int P> constexpr int kFftBuf = P + P / 8 + 2;   // float2 elements per sequence buffer (+2: sequences land in different banks)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void bf2(float2& a, float2& b) {
+    const float2 t = a;
+    a = make_float2(t.x + b.x, t.y + b.y);
+    b = make_float2(t.x - b.x, t.y - b.y);
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // * exp(-i pi/2)
+
+// DFT of size R on v[0..R), natural order output in x[0..R)
+template <int R>
+__device__ __forceinline__ void dft_small(float2* v, float2* x);
+template <>
+__device__ __forceinline__ void dft_small<2>(float2* v, float2* x) {
+    bf2(v[0], v[1]);
+    x[0] = v[0]; x[1] = v[1];
+}
+template <>
+__device__ __forceinline__ void dft_small<4>(float2* v, float2* x) {
+    bf2(v[0], v[2]); bf2(v[1], v[3]);
+    v[3] = mul_mi(v[3]);
+    bf2(v[0], v[1]); bf2(v[2], v[3]);
+    x[0] = v[0]; x[1] = v[2]; x[2] = v[1]; x[3] = v[3];
+}
+template <>
+__device__ __forceinline__ void dft_small<8>(float2* v, float2* x) {
+    const float s = 0.70710678118654752440f;
+    bf2(v[0], v[4]); bf2(v[1], v[5]); bf2(v[2], v[6]); bf2(v[3], v[7]);
+    v[5] = make_float2(s * (v[5].x + v[5].y), s * (v[5].y - v[5].x));      // * exp(-i pi/4)
+    v[6] = mul_mi(v[6]);
+    v[7] = make_float2(s * (v[7].y - v[7].x), -s * (v[7].x + v[7].y));     // * exp(-3i pi/4)
+    bf2(v[0], v[2]); bf2(v[1], v[3]); bf2(v[4], v[6]); bf2(v[5], v[7]);
+    v[3] = mul_mi(v[3]); v[7] = mul_mi(v[7]);
+    bf2(v[0], v[1]); bf2(v[2], v[3]); bf2(v[4], v[5]); bf2(v[6], v[7]);
+    x[0] = v[0]; x[1] = v[4]; x[2] = v[2]; x[3] = v[6]; x[4] = v[1]; x[5] = v[5]; x[6] = v[3]; x[7] = v[7];
+}
+
+// One Stockham stage of radix R over a sequence of P points held in the padded shared buffer `buf`; the P/8 threads
+// of the sequence (index t) each handle 8 points = 8/R butterflies.  W[k] = exp(-2 pi i k / P).  All threads of
+// the CTA call this together (two CTA barriers).
+template <int P, int R, int Ns>
+__device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ W, int t) {
+    constexpr int NB = 8 / R;               // butterflies per thread
+    float2 v[8];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int j = t * NB + q, k = j % Ns;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float2 a = buf[fft_phys(j + r * (P / R))];
+            if (Ns > 1 && r > 0) a = cmul(a, W[(r * k * (P / (Ns * R))) & (P - 1)]);
+            v[q * R + r] = a;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int j = t * NB + q, k = j % Ns;
+        float2 x[R];
+        dft_small<R>(v + q * R, x);
+        const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[fft_phys(j0 + r * Ns)] = x[r];
+    }
+    __syncthreads();
+}
+
+// forward FFT (e^{-i...}, unnormalised) of the P points in buf, natural order in and out
+template <int P>
+__device__ __forceinline__ void fft_block(float2* buf, const float2* __restrict__ W, int t);
+template <>
+__device__ __forceinline__ void fft_block<64>(float2* buf, const float2* __restrict__ W, int t) {
+    fft_stage<64, 8, 1>(buf, W, t);
+    fft_stage<64, 8, 8>(buf, W, t);
+}
+template <>
+__device__ __forceinline__ void fft_block<128>(float2* buf, const float2* __restrict__ W, int t) {
+    fft_stage<128, 8, 1>(buf, W, t);
+    fft_stage<128, 8, 8>(buf, W, t);
+    fft_stage<128, 2, 64>(buf, W, t);
+}
+template <>
+__device__ __forceinline__ void fft_block<256>(float2* buf, const float2* __restrict__ W, int t) {
+    fft_stage<256, 8, 1>(buf, W, t);
+    fft_stage<256, 8, 8>(buf, W, t);
+    fft_stage<256, 4, 64>(buf, W, t);
+}
+template <>
+__device__ __forceinline__ void fft_block<512>(float2* buf, const float2* __restrict__ W, int t) {
+    fft_stage<512, 8, 1>(buf, W, t);
+    fft_stage<512, 8, 8>(buf, W, t);
+    fft_stage<512, 8, 64>(buf, W, t);
+}
+template <>
+__device__ __forceinline__ void fft_block<1024>(float2* buf, const float2* __restrict__ W, int t) {
+    fft_stage<1024, 8, 1>(buf, W, t);
+    fft_stage<1024, 8, 8>(buf, W, t);
+    fft_stage<1024, 8, 64>(buf, W, t);
+    fft_stage<1024, 2, 512>(buf, W, t);
+}
+
+constexpr int kFftSeqs = 8;   // sequences transformed side by side by one CTA (P/8 threads each)
+
+// ================================================================== K1r
+struct FftRowsArgs {
+    const float* raw;            // nImg x N x N
+    const ImgParams* ip;
+    const float2* twiddle;       // P entries
+    float2* T;                   // nImg x (P/2+1) x N: T[img][kx][row]
+    int N;
+};
+
+// grid (ceil(N / 16), nImg), block kFftSeqs * P/8 threads: 16 image rows = 8 complex sequences
+template <int P>
+__global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_rows(const __grid_constant__ FftRowsArgs a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float2* W = reinterpret_cast<float2*>(smemRaw);
+    float2* bufs = W + P;
+    constexpr int TPS = P / 8, Xh = P / 2 + 1;
+    const int N = a.N, img = blockIdx.y;
+    const int tid = threadIdx.x, seq = tid / TPS, t = tid % TPS;
+    for (int i = tid; i < P; i += kFftSeqs * TPS) W[i] = __ldg(a.twiddle + i);
+    const ImgParams q = a.ip[img];
+    const float* src = a.raw + (size_t)img * N * N;
+    float2* buf = bufs + seq * kFftBuf<P>;
+    // rows 2*seq and 2*seq+1 of this CTA's 16 (destination rows before padding; the shift moves the source)
+    const int rowA = blockIdx.x * 2 * kFftSeqs + 2 * seq, rowB = rowA + 1;
+    const float* ra = rowA < N ? src + (size_t)d_wrap(rowA + q.my, N) * N : nullptr;
+    const float* rb = rowB < N ? src + (size_t)d_wrap(rowB + q.my, N) * N : nullptr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int x = t + TPS * e;                        // padded column
+        const int jj = (x + N / 2) & (P - 1);             // destination column before padding: x = (jj - N/2) mod P
+        float2 z = make_float2(0.f, 0.f);
+        if (jj < N) {
+            const int sj = d_wrap(jj + q.mx, N);
+            if (ra) z.x = __ldg(ra + sj);
+            if (rb) z.y = __ldg(rb + sj);
+        }
+        buf[fft_phys(x)] = z;
+    }
+    __syncthreads();
+    fft_block<P>(buf, W, t);
+    // untangle the two real transforms and write T[kx][row], 16 consecutive rows per kx
+    const int nOut = Xh * 2 * kFftSeqs;
+    for (int o = tid; o < nOut; o += kFftSeqs * TPS) {
+        const int r16 = o & (2 * kFftSeqs - 1), kx = o / (2 * kFftSeqs);
+        const int row = blockIdx.x * 2 * kFftSeqs + r16;
+        if (row >= N) continue;
+        const float2* b = bufs + (r16 >> 1) * kFftBuf<P>;
+        const float2 zk = b[fft_phys(kx)], zm = b[fft_phys((P - kx) & (P - 1))];
+        float2 out;
+        if (r16 & 1) out = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));      // B = (Z[k] - conj Z[P-k]) / 2i
+        else out = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));             // A = (Z[k] + conj Z[P-k]) / 2
+        a.T[((size_t)img * Xh + kx) * N + row] = out;
+    }
+}
+
+// ================================================================== K1c
+struct FftColsArgs {
+    Slice2Args s;                // slice outputs, CTF, cut-off (s.fft is unused)
+    const float2* twiddle;       // P entries
+    const float2* T;             // nImg x (P/2+1) x N
+    int N;
+};
+
+// value and weights of pixel (j, ip) from its transform value F (as d_pixel_contrib2)
+__device__ __forceinline__ float4 d_contrib_from_F(float2 F, bool valid, const SliceParams& sp, const CtfConsts* ctf, const CtfFloat& cf, float weight, int j, int ip) {
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!valid) return out;
+    float wc = 1.f, wm = 1.f;
+    if (sp.useCtf) d_ctf_weights(*ctf, cf, sp, j, ip, wc, wm);
+    const float s = weight * wm * wc * sp.invP2;
+    out.x = F.x * s;
+    out.y = F.y * s;
+    out.z = weight * wm;
+    out.w = (wm != 1.0f) ? 1.f : 0.f;
+    return out;
+}
+__device__ __forceinline__ bool d_pixel_valid(const int* __restrict__ jmax, const SliceParams& sp, int j, int ip) {
+    return ip >= sp.iLo && ip <= sp.iHi && j <= jmax[ip - sp.iLo];
+}
+
+// grid (ceil((R+1) / 8), nImg), block kFftSeqs * P/8 threads: 8 columns kx = 8*blockIdx.x .. +7
+template <int P>
+__global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float2* W = reinterpret_cast<float2*>(smemRaw);
+    float2* bufs = W + P;
+    __shared__ CtfConsts sCtf;
+    __shared__ CtfFloat sCtfF;
+    constexpr int TPS = P / 8, Xh = P / 2 + 1;
+    const SliceParams& sp = a.s.sp;
+    const int N = a.N, img = blockIdx.y;
+    const int tid = threadIdx.x, seq = tid / TPS, t = tid % TPS;
+    for (int i = tid; i < P; i += kFftSeqs * TPS) W[i] = __ldg(a.twiddle + i);
+    if (sp.useCtf && tid < (int)(sizeof(CtfConsts) / 8))
+        reinterpret_cast<double*>(&sCtf)[tid] = reinterpret_cast<const double*>(a.s.ctfs + img)[tid];
+    if (sp.useCtf && tid == 32) d_ctf_prepare(a.s.ctfs[img], sCtfF);
+    float2* buf = bufs + seq * kFftBuf<P>;
+    const int kx = blockIdx.x * kFftSeqs + seq;
+    const float2* col = (kx <= sp.R) ? a.T + ((size_t)img * Xh + kx) * N : nullptr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int y = t + TPS * e;                        // padded row
+        const int ii = (y + N / 2) & (P - 1);             // destination row before padding
+        float2 z = make_float2(0.f, 0.f);
+        if (col && ii < N) z = __ldg(col + ii);
+        buf[fft_phys(y)] = z;
+    }
+    __syncthreads();
+    fft_block<P>(buf, W, t);
+
+    // ---- the slice kernel's work on the transform in shared memory: thread <-> (row r = ip + R, column c), c fastest.
+    // Entry (i,j) = (pixel(i,j), pixel(i,j+1)): a lane gets its neighbour's pixel by shuffle and writes whole
+    // 16-byte entries; only the lanes at the edge of the CTA's 8 columns write the 8-byte halves of foreign entries.
+    const CtfConsts* ctf = sp.useCtf ? &sCtf : nullptr;
+    const float weight = a.s.ip[img].weight;
+    float4* S4 = a.s.slices + (size_t)img * a.s.planeStride;
+    float2* S2 = reinterpret_cast<float2*>(S4);
+    const size_t dOff = (size_t)img * (2 * sp.R + 1) * (sp.R + 1);
+    const int wordsPerRow = (sp.R + 1 + 31) / 32;
+    const int nElem = (2 * sp.R + 1) * kFftSeqs;
+    const int nIter = (nElem + kFftSeqs * TPS - 1) / (kFftSeqs * TPS);
+    for (int it = 0; it < nIter; ++it) {
+        const int o = tid + it * (kFftSeqs * TPS);
+        const int c = o & (kFftSeqs - 1), r = o / kFftSeqs;
+        const int j = blockIdx.x * kFftSeqs + c, ipx = r - sp.R;
+        const bool act = o < nElem && j <= sp.R;
+        float2 pv = make_float2(0.f, 0.f);       // the pixel's slice value (flag in the LSB of re)
+        bool flag = false;
+        float wDamped = 0.f, wUnmod = 0.f;
+        if (act) {
+            const float2* b = bufs + c * kFftBuf<P>;
+            const float2 F = b[fft_phys(ipx & (P - 1))];
+            float4 cc = d_contrib_from_F(F, d_pixel_valid(a.s.jmax, sp, j, ipx), sp, ctf, sCtfF, weight, j, ipx);
+            flag = cc.w != 0.f;
+            wDamped = cc.z;
+            wUnmod = (cc.z != 0.f || flag) ? weight : 0.f;
+            if (j > 0) {
+                pv = make_float2(d_set_flag(cc.x, flag), cc.y);
+            } else {
+                // column 0: original (0,ip) plus the mirror of original (0,-ip) (see k_make_slices2)
+                const float2 Fm = b[fft_phys((-ipx) & (P - 1))];
+                float4 m = d_contrib_from_F(Fm, d_pixel_valid(a.s.jmax, sp, 0, -ipx), sp, ctf, sCtfF, weight, 0, -ipx);
+                flag = flag || (m.w != 0.f);
+                pv = make_float2(d_set_flag(cc.x + m.x, flag), cc.y - m.y);
+                a.s.col0[(size_t)img * sp.side + (ipx + sp.Rp)] = make_float2(d_set_flag(cc.x, flag), cc.y);
+            }
+        }
+        // neighbours inside the group of 8 columns (same row)
+        float2 nxt, prv;
+        nxt.x = __shfl_down_sync(0xffffffffu, pv.x, 1, kFftSeqs); nxt.y = __shfl_down_sync(0xffffffffu, pv.y, 1, kFftSeqs);
+        prv.x = __shfl_up_sync(0xffffffffu, pv.x, 1, kFftSeqs);   prv.y = __shfl_up_sync(0xffffffffu, pv.y, 1, kFftSeqs);
+        if (!act) continue;
+        const bool last = (c == kFftSeqs - 1) || (j == sp.R);      // no lane of this CTA holds pixel j+1
+        const size_t o1 = (size_t)(ipx + sp.Rp) * a.s.pitch + (j + sp.Rp);
+        if (!last) S4[o1] = make_float4(pv.x, pv.y, nxt.x, nxt.y);
+        else S2[2 * o1] = pv;
+        if (c == 0 && j > 0) S2[2 * o1 - 1] = pv;                   // second half of the entry on the left (previous CTA's column)
+        if (j > 0) {
+            const size_t o2 = (size_t)(-ipx + sp.Rp) * a.s.pitch + (-j + sp.Rp);
+            if (c > 0) S4[o2] = make_float4(pv.x, -pv.y, prv.x, -prv.y);
+            else S2[2 * o2] = make_float2(pv.x, -pv.y);
+            if (last) S2[2 * o2 - 1] = make_float2(pv.x, -pv.y);    // entry (-j-1): its second pixel is this one
+        }
+        if (flag) {
+            if (a.s.damped) a.s.damped[dOff + (size_t)r * (sp.R + 1) + j] = wDamped;
+            if (a.s.damped2) a.s.damped2[dOff + (size_t)r * (sp.R + 1) + j] = wUnmod;
+            if (a.s.dampedMask)     // the mask is zeroed before the launch; a word spans four CTAs
+                atomicOr(a.s.dampedMask + ((size_t)img * (2 * sp.R + 1) + r) * wordsPerRow + (j >> 5), 1u << (j & 31));
+        }
+    }
+}
+
+}  // namespace rfb200

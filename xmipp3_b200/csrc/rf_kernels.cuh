@@ -188,8 +188,10 @@ __device__ __forceinline__ void d_ctf_rules(T v, T minCtf, int phaseFlipped, int
     if (fabs(wc) < minCtf) {                              // :616-622
         wm = fabs(wc);
         wc = (wc >= 0) ? T(1) : T(-1);
-    } else
-        wc = T(1) / wc;
+    } else {
+        if constexpr (sizeof(T) == 4) wc = __frcp_rn(wc);   // correctly rounded reciprocal, no slow path
+        else wc = T(1) / wc;
+    }
     if (phaseFlipped) wc = fabs(wc);                      // :623-624
     wCTF = (float)wc;
     wMod = (float)wm;
@@ -216,31 +218,51 @@ __device__ __noinline__ void d_ctf_weights_exact(const CtfConsts& c, const Slice
     d_ctf_rules<double>(v, sp.minCtf, sp.phaseFlipped, j, ip, wCTF, wMod);
 }
 
+// FP32 copies of the per-image constants that the per-pixel evaluation multiplies with (converted once per CTA)
+struct CtfFloat {
+    float KK, Kcos, Ksin, cos2az, sin2az;
+};
+__device__ __forceinline__ void d_ctf_prepare(const CtfConsts& c, CtfFloat& f) {
+    f.KK = (float)(c.K * c.K);
+    f.Kcos = (float)c.Kcos;
+    f.Ksin = (float)c.Ksin;
+    f.cos2az = (float)c.cos2az;
+    f.sin2az = (float)c.sin2az;
+}
+
 // wCTF / wModulator of half-plane pixel (j, ip) — RF.cpp:600-625.  Only the phase argument needs double
-// precision (it reaches hundreds of radians): it is formed from exact integer frequencies and range-reduced
-// in double; the astigmatism angle term, sin/cos and the minCTF rules run in FP32.
+// precision (it reaches hundreds of radians): it is formed from exact integer frequencies and reduced to
+// [-pi/4, pi/4] in double (quadrant kept as an integer); sin/cos are the classic single-precision minimax kernels
+// on that interval (~1 ulp); the astigmatism angle term and the minCTF rules run in FP32.
 // cos(2(atan2(Y,X) - az)) is expanded so that no atan2 is needed.
-__device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
+__device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const CtfFloat& f, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
     const int r2i = j * j + ip * ip;                      // exact: |freq|^2 in units of (1/(P*Ts))^2
     const double u2 = (double)r2i * sp.a2;
     double deltaf = 0.0;
     const float ax = fabsf((float)j) * sp.a, ay = fabsf((float)ip) * sp.a;
     if (!(ax < 1e-6f && ay < 1e-6f)) {                    // precomputeValues(X,Y): deltaf = 0 at the origin
-        const float inv = 1.0f / (float)r2i;
+        const float inv = __frcp_rn((float)r2i);
         const float c2 = (float)(j * j - ip * ip) * inv, s2 = (float)(2 * j * ip) * inv;
-        deltaf = c.defocus_average + c.defocus_deviation * (double)(c2 * (float)c.cos2az + s2 * (float)c.sin2az);
+        deltaf = c.defocus_average + c.defocus_deviation * (double)(c2 * f.cos2az + s2 * f.sin2az);
     }
     double arg = u2 * fma(c.K1, deltaf, c.K2 * u2);
     if (c.has_vpp) arg += -c.phase_shift * (1.0 - exp(-u2 / (2.0 * c.vpp_radius * c.vpp_radius)));
-    const double inv2pi = 0.15915494309189535, twopi_hi = 6.283185307179586, twopi_lo = 2.4492935982947064e-16;
-    const double kk = rint(arg * inv2pi);
-    double red = fma(-kk, twopi_hi, arg);
-    red = fma(-kk, twopi_lo, red);
-    float sn, cs;
-    sincosf((float)red, &sn, &cs);
+    const double two_over_pi = 0.63661977236758134, pio2_hi = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
+    const double kq = rint(arg * two_over_pi);
+    double red = fma(-kq, pio2_hi, arg);
+    red = fma(-kq, pio2_lo, red);
+    const int q = (int)kq;
+    const float x = (float)red, x2 = x * x;
+    const float sp_ = fmaf(x * x2, fmaf(x2, fmaf(x2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), x);
+    const float cp_ = fmaf(x2 * x2, fmaf(x2, fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                           fmaf(x2, -0.5f, 1.0f));
+    // quadrant: angle = red + q*pi/2
+    float sn = (q & 1) ? cp_ : sp_, cs = (q & 1) ? sp_ : cp_;
+    if (q & 2) sn = -sn;
+    if ((q + 1) & 2) cs = -cs;
     float E = 1.0f;
     if (c.has_envelope) E = (float)d_ctf_envelope(c, u2, deltaf);
-    const float v = (float)(c.K * c.K) * ((float)c.Kcos * cs - (float)c.Ksin * sn) * E;
+    const float v = f.KK * (f.Kcos * cs - f.Ksin * sn) * E;
     if (fabsf(fabsf(v) - sp.minCtfF) < 4e-6f) {
         d_ctf_weights_exact(c, sp, j, ip, wCTF, wMod);
         return;

@@ -50,14 +50,14 @@ __device__ __forceinline__ float d_rim_mult(int rt, int j) {
 // contribution of original half-plane pixel (j >= 0, ip): (x, y) = weight*wMod*wCTF*F/P^2, z = weight*wMod
 // (0 for a pixel outside the cut-off), w = 1 if the CTF damps the pixel (wMod != 1)
 __device__ __forceinline__ float4 d_pixel_contrib2(const float2* __restrict__ fft, const int* __restrict__ jmax,
-                                                   const SliceParams& sp, const CtfConsts* ctf, float weight, int j, int ip) {
+                                                   const SliceParams& sp, const CtfConsts* ctf, const CtfFloat& cf, float weight, int j, int ip) {
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ip < sp.iLo || ip > sp.iHi) return out;
     if (j > jmax[ip - sp.iLo]) return out;            // resolution cut-off, RF.cpp:597
     int row = ip < 0 ? ip + sp.P : ip;
     float2 F = __ldg(fft + (size_t)row * sp.Xh + j);
     float wc = 1.f, wm = 1.f;
-    if (sp.useCtf) d_ctf_weights(*ctf, sp, j, ip, wc, wm);
+    if (sp.useCtf) d_ctf_weights(*ctf, cf, sp, j, ip, wc, wm);
     float s = weight * wm * wc * sp.invP2;
     out.x = F.x * s;
     out.y = F.y * s;
@@ -92,9 +92,11 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
     const float2* f = a.fft + (size_t)img * sp.P * sp.Xh;
     // the image's CTF constants are staged in shared memory once per CTA (19 doubles that every pixel needs)
     __shared__ CtfConsts sCtf;
+    __shared__ CtfFloat sCtfF;
     if (sp.useCtf) {
         const int t = threadIdx.y * 32 + threadIdx.x;
         if (t < (int)(sizeof(CtfConsts) / 8)) reinterpret_cast<double*>(&sCtf)[t] = reinterpret_cast<const double*>(a.ctfs + img)[t];
+        if (t == 32) d_ctf_prepare(a.ctfs[img], sCtfF);
         __syncthreads();
     }
     const CtfConsts* ctf = sp.useCtf ? &sCtf : nullptr;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
         const int ipx = r - sp.R;
         bool flag = false;
         if (active) {
-            float4 c = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, j, ipx);
+            float4 c = d_pixel_contrib2(f, a.jmax, sp, ctf, sCtfF, weight, j, ipx);
             const size_t o1 = (size_t)(ipx + sp.Rp) * a.pitch + (j + sp.Rp);
             flag = c.w != 0.f;
             float unmod = (c.z != 0.f || flag) ? weight : 0.f;       // weight of a valid pixel without the CTF modulator
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
                 // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference inserts this
                 // column twice for x > 0 voxels.  The combined entry is flagged if either part is
                 // damped; the damped-weight pass then supplies the weights of both parts.
-                float4 m = d_pixel_contrib2(f, a.jmax, sp, ctf, weight, 0, -ipx);
+                float4 m = d_pixel_contrib2(f, a.jmax, sp, ctf, sCtfF, weight, 0, -ipx);
                 flag = flag || (m.w != 0.f);
                 const float2 v = make_float2(d_set_flag(c.x + m.x, flag), c.y - m.y);
                 S2[2 * o1] = v; S2[2 * o1 - 1] = v;
