@@ -100,3 +100,33 @@ def test_box256_d7_symmetry_property():
     ph = synth.phantom_volume(d["phantom"], N)
     assert np.corrcoef(vol.ravel(), ph.ravel())[0, 1] > 0.999
     r.close()
+
+
+def test_box512_config5_geometry(monkeypatch):
+    """Config 5 geometry (box 512, pad 2, Z = 1024: 6.5 GB of accumulators, 1024-point transforms): the fused
+    preprocessing chain against the cuFFT chain, determinism, and quality against the analytic phantom."""
+    from xmipp3_b200._lib import Reconstructor
+    n, box = 96, 512
+    d = synth.make_dataset(n, box, seed=41, ctf=True)
+    p, _ = _particles(d, True)
+    kw = dict(use_ctf=True, sampling=d["sampling"], max_batch=64)
+    a = Reconstructor(box, **kw)
+    a.insert(d["images"], p)
+    sa = a.weight_sum()
+    Va, Wa = a.accumulators()
+    vol = a.finalize()
+    a.close()
+    monkeypatch.setenv("RFB200_FFT", "cufft")
+    b = Reconstructor(box, **kw)
+    monkeypatch.delenv("RFB200_FFT", raising=False)
+    b.insert(d["images"], p)
+    sb = b.weight_sum()
+    Vb, Wb = b.accumulators()
+    b.close()
+    assert abs(sa - sb) <= 2e-6 * abs(sb)
+    assert np.linalg.norm(Va - Vb) <= 3e-6 * np.linalg.norm(Vb)
+    assert np.linalg.norm(Wa - Wb) <= 3e-6 * np.linalg.norm(Wb)
+    del Vb, Wb
+    assert np.isfinite(vol).all() and Wa.min() >= 0
+    ph = synth.phantom_volume(d["phantom"], box)
+    assert np.corrcoef(vol.ravel(), ph.ravel())[0, 1] > 0.98      # 96 views only
