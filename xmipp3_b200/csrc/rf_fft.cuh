@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_cols_slices(const __gri
     for (int i = tid; i < P; i += kFftSeqs * TPS) W[i] = __ldg(a.twiddle + i);
     if (sp.useCtf && tid < (int)(sizeof(CtfConsts) / 8))
         reinterpret_cast<double*>(&sCtf)[tid] = reinterpret_cast<const double*>(a.s.ctfs + img)[tid];
-    if (sp.useCtf && tid == 32) d_ctf_prepare(a.s.ctfs[img], sCtfF);
+    if (sp.useCtf && tid == 32) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
     float2* buf = bufs + seq * kFftBuf<P>;
     const int kx = blockIdx.x * kFftSeqs + seq;
     const float2* col = (kx <= sp.R) ? a.T + ((size_t)img * Xh + kx) * N : nullptr;

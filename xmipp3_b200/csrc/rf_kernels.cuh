@@ -218,50 +218,84 @@ __device__ __noinline__ void d_ctf_weights_exact(const CtfConsts& c, const Slice
     d_ctf_rules<double>(v, sp.minCtf, sp.phaseFlipped, j, ip, wCTF, wMod);
 }
 
-// FP32 copies of the per-image constants that the per-pixel evaluation multiplies with (converted once per CTA)
+// Per-image constants of the per-pixel evaluation, prepared once per CTA: FP32 copies of the amplitude terms and
+// the phase coefficients as 0.64 fixed-point TURNS.  With integer pixel frequencies (j, ip) the phase of the pure
+// CTF (no envelope / phase plate) is
+//   arg / 2pi = c1 * r2 + c2 * r2^2 + cA * (j^2 - ip^2) + cB * (2 j ip),   r2 = j^2 + ip^2,
+//   c1 = a2 K1 dAvg / 2pi,  c2 = a2^2 K2 / 2pi,  cA = a2 K1 dDev cos(2 az) / 2pi,  cB = a2 K1 dDev sin(2 az) / 2pi
+// (the astigmatism term cos(2(atan2(Y,X) - az)) * r2 is a polynomial in j, ip), and only its fractional part
+// matters: 64-bit integer multiply-adds wrap exactly like the angle does, so the range reduction is exact and the
+// per-pixel path needs neither FP64 nor a division.
 struct CtfFloat {
     float KK, Kcos, Ksin, cos2az, sin2az;
+    int fast;                       // 1: fixed-point phase path valid (no envelope, no phase plate)
+    long long fix1, fix2, fixA, fixB;
 };
-__device__ __forceinline__ void d_ctf_prepare(const CtfConsts& c, CtfFloat& f) {
+__device__ __forceinline__ long long d_turns_to_fix(double turns) {
+    const double fr = turns - rint(turns);                     // [-0.5, 0.5]
+    return (long long)((unsigned long long)llrint(fr * 9223372036854775808.0) << 1);   // * 2^64, modulo 2^64
+}
+__device__ __forceinline__ void d_ctf_prepare(const CtfConsts& c, const SliceParams& sp, CtfFloat& f) {
     f.KK = (float)(c.K * c.K);
     f.Kcos = (float)c.Kcos;
     f.Ksin = (float)c.Ksin;
     f.cos2az = (float)c.cos2az;
     f.sin2az = (float)c.sin2az;
+    const double i2pi = 0.15915494309189533577;
+    f.fix1 = d_turns_to_fix(sp.a2 * c.K1 * c.defocus_average * i2pi);
+    f.fix2 = d_turns_to_fix(sp.a2 * sp.a2 * c.K2 * i2pi);
+    f.fixA = d_turns_to_fix(sp.a2 * c.K1 * c.defocus_deviation * c.cos2az * i2pi);
+    f.fixB = d_turns_to_fix(sp.a2 * c.K1 * c.defocus_deviation * c.sin2az * i2pi);
+    // precomputeValues zeroes deltaf only where |X|,|Y| < 1e-6: with a >= 1e-6 that is the origin, where arg = 0 anyway
+    f.fast = (!c.has_vpp && !c.has_envelope && sp.a >= 1e-6f) ? 1 : 0;
 }
 
-// wCTF / wModulator of half-plane pixel (j, ip) — RF.cpp:600-625.  Only the phase argument needs double
-// precision (it reaches hundreds of radians): it is formed from exact integer frequencies and reduced to
-// [-pi/4, pi/4] in double (quadrant kept as an integer); sin/cos are the classic single-precision minimax kernels
-// on that interval (~1 ulp); the astigmatism angle term and the minCTF rules run in FP32.
-// cos(2(atan2(Y,X) - az)) is expanded so that no atan2 is needed.
-__device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const CtfFloat& f, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
-    const int r2i = j * j + ip * ip;                      // exact: |freq|^2 in units of (1/(P*Ts))^2
-    const double u2 = (double)r2i * sp.a2;
-    double deltaf = 0.0;
-    const float ax = fabsf((float)j) * sp.a, ay = fabsf((float)ip) * sp.a;
-    if (!(ax < 1e-6f && ay < 1e-6f)) {                    // precomputeValues(X,Y): deltaf = 0 at the origin
-        const float inv = __frcp_rn((float)r2i);
-        const float c2 = (float)(j * j - ip * ip) * inv, s2 = (float)(2 * j * ip) * inv;
-        deltaf = c.defocus_average + c.defocus_deviation * (double)(c2 * f.cos2az + s2 * f.sin2az);
-    }
-    double arg = u2 * fma(c.K1, deltaf, c.K2 * u2);
-    if (c.has_vpp) arg += -c.phase_shift * (1.0 - exp(-u2 / (2.0 * c.vpp_radius * c.vpp_radius)));
-    const double two_over_pi = 0.63661977236758134, pio2_hi = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
-    const double kq = rint(arg * two_over_pi);
-    double red = fma(-kq, pio2_hi, arg);
-    red = fma(-kq, pio2_lo, red);
-    const int q = (int)kq;
-    const float x = (float)red, x2 = x * x;
+// sin and cos of (q quarter turns + x), x in [-pi/4, pi/4]: the classic single-precision minimax kernels (~1 ulp)
+__device__ __forceinline__ void d_sincos_quadrant(float x, int q, float& sn, float& cs) {
+    const float x2 = x * x;
     const float sp_ = fmaf(x * x2, fmaf(x2, fmaf(x2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), x);
     const float cp_ = fmaf(x2 * x2, fmaf(x2, fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
                            fmaf(x2, -0.5f, 1.0f));
-    // quadrant: angle = red + q*pi/2
-    float sn = (q & 1) ? cp_ : sp_, cs = (q & 1) ? sp_ : cp_;
+    sn = (q & 1) ? cp_ : sp_;
+    cs = (q & 1) ? sp_ : cp_;
     if (q & 2) sn = -sn;
     if ((q + 1) & 2) cs = -cs;
-    float E = 1.0f;
-    if (c.has_envelope) E = (float)d_ctf_envelope(c, u2, deltaf);
+}
+
+// wCTF / wModulator of half-plane pixel (j, ip) — RF.cpp:600-625.  Fast path: exact fixed-point phase (see CtfFloat).
+// General path (envelope or phase plate): the phase argument is formed in double from exact integer frequencies and
+// reduced to [-pi/4, pi/4] in double.  sin/cos, the amplitude and the minCTF rules run in FP32.
+__device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const CtfFloat& f, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
+    float sn, cs, E = 1.0f;
+    if (f.fast) {
+        const int jj = j * j, ii = ip * ip;
+        typedef unsigned long long u64;                      // all products wrap modulo 2^64 = one turn
+        const u64 r2 = (u64)(jj + ii);
+        const u64 ph = ((u64)f.fix1 + (u64)f.fix2 * r2) * r2 + (u64)f.fixA * (u64)(long long)(jj - ii) + (u64)f.fixB * (u64)(long long)(2 * j * ip);
+        const unsigned long long rq = ph + (1ull << 61);                     // round to the nearest quarter turn
+        const int q = (int)(rq >> 62);
+        const int res = (int)((long long)(ph - ((rq >> 62) << 62)) >> 32);    // residual in 2^-32 turns, |res| <= 2^29
+        const float x = (float)res * 1.4629180792671596e-9f;                 // * 2 pi / 2^32
+        d_sincos_quadrant(x, q, sn, cs);
+    } else {
+        const int r2i = j * j + ip * ip;                      // exact: |freq|^2 in units of (1/(P*Ts))^2
+        const double u2 = (double)r2i * sp.a2;
+        double deltaf = 0.0;
+        const float ax = fabsf((float)j) * sp.a, ay = fabsf((float)ip) * sp.a;
+        if (!(ax < 1e-6f && ay < 1e-6f)) {                    // precomputeValues(X,Y): deltaf = 0 at the origin
+            const float inv = __frcp_rn((float)r2i);
+            const float c2 = (float)(j * j - ip * ip) * inv, s2 = (float)(2 * j * ip) * inv;
+            deltaf = c.defocus_average + c.defocus_deviation * (double)(c2 * f.cos2az + s2 * f.sin2az);
+        }
+        double arg = u2 * fma(c.K1, deltaf, c.K2 * u2);
+        if (c.has_vpp) arg += -c.phase_shift * (1.0 - exp(-u2 / (2.0 * c.vpp_radius * c.vpp_radius)));
+        const double two_over_pi = 0.63661977236758134, pio2_hi = 1.5707963267948966, pio2_lo = 6.123233995736766e-17;
+        const double kq = rint(arg * two_over_pi);
+        double red = fma(-kq, pio2_hi, arg);
+        red = fma(-kq, pio2_lo, red);
+        d_sincos_quadrant((float)red, (int)kq, sn, cs);
+        if (c.has_envelope) E = (float)d_ctf_envelope(c, u2, deltaf);
+    }
     const float v = f.KK * (f.Kcos * cs - f.Ksin * sn) * E;
     if (fabsf(fabsf(v) - sp.minCtfF) < 4e-6f) {
         d_ctf_weights_exact(c, sp, j, ip, wCTF, wMod);

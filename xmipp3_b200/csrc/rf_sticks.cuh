@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
     if (sp.useCtf) {
         const int t = threadIdx.y * 32 + threadIdx.x;
         if (t < (int)(sizeof(CtfConsts) / 8)) reinterpret_cast<double*>(&sCtf)[t] = reinterpret_cast<const double*>(a.ctfs + img)[t];
-        if (t == 32) d_ctf_prepare(a.ctfs[img], sCtfF);
+        if (t == 32) d_ctf_prepare(a.ctfs[img], sp, sCtfF);
         __syncthreads();
     }
     const CtfConsts* ctf = sp.useCtf ? &sCtf : nullptr;
