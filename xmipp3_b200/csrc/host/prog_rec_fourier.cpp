@@ -157,7 +157,8 @@ std::string ProgRecFourierB200::usage() {
         "  [--device <dev=0>]                 : GPU device to use\n"
         "  [--bufferSize <size=1024>]         : Number of projections handed to the GPU per call\n"
         "  [--fftOnGPU]                       : accepted for compatibility (the FFT always runs on the GPU)\n"
-        "  [--fast]                           : nearest-pixel insertion (not implemented on this path yet)\n"
+        "  [--fast]                           : accepted for compatibility; the exact blob insertion is used (it is\n"
+        "                                       the fast path here), so the result equals the one without --fast\n"
         "  [--prepare_fsc <fscfile>]          : Filename root for FSC files (<root>_1_recons.vol, <root>_2_recons.vol)\n"
         "  [-v <verbosity=1>]\n";
 }
@@ -287,7 +288,8 @@ void ProgRecFourierB200::particleFromRow(const MetaData& md, size_t i, bool hasC
 
 void ProgRecFourierB200::run() {
     show();
-    if (fast) throw ProgramError("--fast is not implemented on the B200 path yet");
+    if (fast)   // the reference's --fast trades accuracy (nearest pixel + final blob convolution) for speed; no need here
+        std::fprintf(stderr, "xmipp_reconstruct_fourier_b200: --fast accepted; using the exact blob insertion (same result as without --fast)\n");
     if (NiterWeight < 0) throw ProgramError("--iter must be >= 0");
 
     // ---- produceSideinfo (RF.cpp:184-287)
