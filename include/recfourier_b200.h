@@ -161,6 +161,11 @@ int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms);
 /* Sum of the weight accumulator (FP64 reduction on the device, 8-byte read-back): a cheap
  * per-step result that forces completion of everything inserted so far. */
 int rfb200_weight_sum(rfb200_handle h, double* sum);
+/* Split form for a pipelined host program: _begin enqueues the reduction behind everything inserted so far and
+ * returns at once, _end waits for it and returns the value.  A host loop "insert(k+1); end(k); begin(k+1)" overlaps
+ * the PCIe transfer of batch k+1 with the kernels of batch k.  One reduction may be outstanding per handle. */
+int rfb200_weight_sum_begin(rfb200_handle h);
+int rfb200_weight_sum_end(rfb200_handle h, double* sum);
 
 /* The CUDA streams the handle launches on (cudaStream_t), for host programs that want to
  * order their own work against it. */

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_nccl_unique_id", "rfb200_nccl_init", "rfb200_reduce_nccl", "rfb200_accumulator_ptrs",
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
-    "rfb200_debug_slice_dims", "rfb200_debug_get_slice",
+    "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
 ]
 
 
@@ -111,6 +111,8 @@ def load(build=True):
     L.rfb200_timer_start.argtypes = [H]
     L.rfb200_timer_stop.argtypes = [H, C.POINTER(C.c_double)]
     L.rfb200_weight_sum.argtypes = [H, C.POINTER(C.c_double)]
+    L.rfb200_weight_sum_begin.argtypes = [H]
+    L.rfb200_weight_sum_end.argtypes = [H, C.POINTER(C.c_double)]
     L.rfb200_get_streams.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.rfb200_debug_slice_dims.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rfb200_debug_get_slice.argtypes = [H, C.c_int32, C.c_void_p]
@@ -259,6 +261,14 @@ class Reconstructor:
     def weight_sum(self):
         s = C.c_double()
         self._check(self._L.rfb200_weight_sum(self._h, C.byref(s)))
+        return s.value
+
+    def weight_sum_begin(self):
+        self._check(self._L.rfb200_weight_sum_begin(self._h))
+
+    def weight_sum_end(self):
+        s = C.c_double()
+        self._check(self._L.rfb200_weight_sum_end(self._h, C.byref(s)))
         return s.value
 
     def streams(self):

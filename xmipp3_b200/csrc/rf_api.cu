@@ -166,6 +166,8 @@ struct rfb200_handle_s {
     bool swStarted = false;
     double* dSum = nullptr;         // 1024 partials + 1 result
     double* hSum = nullptr;         // pinned
+    cudaEvent_t evSum = nullptr;    // completion of the last rfb200_weight_sum_begin
+    bool sumPending = false;
 };
 
 namespace {
@@ -588,6 +590,7 @@ void free_all(rfb200_handle h) {
     if (h->swStop) cudaEventDestroy(h->swStop);
     if (h->dSum) cudaFree(h->dSum);
     if (h->hSum) cudaFreeHost(h->hSum);
+    if (h->evSum) cudaEventDestroy(h->evSum);
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dEdge, h->dEdgeGroups, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
@@ -683,6 +686,7 @@ int do_create(rfb200_handle h) {
     }
     RF_CUDA(h, cudaMalloc(&h->dSum, sizeof(double) * 1025));
     RF_CUDA(h, cudaMallocHost(&h->hSum, sizeof(double)));
+    RF_CUDA(h, cudaEventCreateWithFlags(&h->evSum, cudaEventDisableTiming));
     RF_CUDA(h, cudaEventCreate(&h->swStart));
     RF_CUDA(h, cudaEventCreate(&h->swStop));
     RF_CUDA(h, cudaMalloc(&h->dG, sizeof(float) * G.size()));
@@ -1077,8 +1081,8 @@ int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms) {
     return RFB200_OK;
 }
 
-int rfb200_weight_sum(rfb200_handle h, double* sum) {
-    if (!h || !sum) return RFB200_ERR_ARG;
+int rfb200_weight_sum_begin(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     if (int rcf = flush_deficit(h)) return rcf;
     k_weight_sum_partial<<<1024, 256, 0, h->compute>>>(h->dWb, h->nBlocked, h->dSum);
@@ -1087,9 +1091,25 @@ int rfb200_weight_sum(rfb200_handle h, double* sum) {
     RF_CUDA(h, cudaGetLastError());
     h->nKernelLaunches += 2;
     RF_CUDA(h, cudaMemcpyAsync(h->hSum, h->dSum + 1024, sizeof(double), cudaMemcpyDeviceToHost, h->compute));
-    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    RF_CUDA(h, cudaEventRecord(h->evSum, h->compute));
+    h->sumPending = true;
+    return RFB200_OK;
+}
+
+int rfb200_weight_sum_end(rfb200_handle h, double* sum) {
+    if (!h || !sum) return RFB200_ERR_ARG;
+    if (!h->sumPending) return fail(h, RFB200_ERR_STATE, "rfb200_weight_sum_begin has not been called");
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    RF_CUDA(h, cudaEventSynchronize(h->evSum));
+    h->sumPending = false;
     *sum = *h->hSum;
     return RFB200_OK;
+}
+
+int rfb200_weight_sum(rfb200_handle h, double* sum) {
+    int rc = rfb200_weight_sum_begin(h);
+    if (rc) return rc;
+    return rfb200_weight_sum_end(h, sum);
 }
 
 int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_stream) {
