@@ -167,6 +167,12 @@ int rfb200_weight_sum(rfb200_handle h, double* sum);
 int rfb200_weight_sum_begin(rfb200_handle h);
 int rfb200_weight_sum_end(rfb200_handle h, double* sum);
 
+/* Page-locked host memory for the image batches handed to rfb200_insert_batch: transfers from it run at full PCIe
+ * speed and asynchronously (cudaHostAlloc / cudaFreeHost; replaces pinMemory / unpinMemory of
+ * cuda_gpu_reconstruct_fourier.h:134-136).  Not tied to a handle. */
+int rfb200_host_alloc(void** ptr, size_t bytes);
+int rfb200_host_free(void* ptr);
+
 /* The CUDA streams the handle launches on (cudaStream_t), for host programs that want to
  * order their own work against it. */
 int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_stream);

@@ -34,6 +34,8 @@ struct Api {
     int (*halfset_push)(rfb200_handle) = nullptr;
     int (*halfset_merge)(rfb200_handle) = nullptr;
     int (*get_timings)(rfb200_handle, rfb200_timings*) = nullptr;
+    int (*host_alloc)(void**, size_t) = nullptr;
+    int (*host_free)(void*) = nullptr;
 };
 
 std::string selfDir() {
@@ -72,6 +74,8 @@ Api loadApi() {
     BIND(halfset_push, "rfb200_halfset_push")
     BIND(halfset_merge, "rfb200_halfset_merge")
     BIND(get_timings, "rfb200_get_timings")
+    BIND(host_alloc, "rfb200_host_alloc")
+    BIND(host_free, "rfb200_host_free")
 #undef BIND
     return a;
 }
@@ -148,7 +152,9 @@ std::string ProgRecFourierB200::usage() {
         "  [--padding <proj=2.0> <vol=2.0>]   : Padding used for projections and volume\n"
         "  [--max_resolution <p=0.5>]         : Max resolution (Nyquist=0.5)\n"
         "  [--weight]                         : Use weights stored in the image metadata\n"
-        "  [--thr <threads=1> <rows=1>]       : Number of host threads reading images (rows is accepted and ignored)\n"
+        "  [--thr <threads=all> <rows=1>]     : Number of host threads reading images; default (or \"all\"): the cores of\n"
+        "                                       the machine, at most 16, as in xmipp_cuda_reconstruct_fourier (rows is\n"
+        "                                       accepted and ignored)\n"
         "  [--blob <radius=1.9> <order=0> <alpha=15>] : Blob parameters\n"
         "  [--useCTF]                         : Use CTF information if present\n"
         "  [--sampling <Ts=1>]                : sampling rate of the input images in Angstroms/pixel\n"
@@ -201,7 +207,7 @@ void ProgRecFourierB200::readParams(int argc, const char* const* argv) {
     d = blob_order; num("--blob", 1, d); blob_order = (int)d;
     num("--blob", 2, blob_alpha);
     num("--max_resolution", 0, maxResolution);
-    d = numThreads; {
+    d = std::min(16u, std::max(1u, std::thread::hardware_concurrency())); {   // reconstruct_fourier_gpu.cpp:132-145: all cores
         auto v = a.values("--thr");
         if (!v.empty()) {
             if (v[0] == "all") d = std::max(1u, std::thread::hardware_concurrency());
@@ -347,21 +353,28 @@ void ProgRecFourierB200::run() {
     int rc = api.create(&cfg, &h);
     if (rc != RFB200_OK) throw ProgramError(std::string("GPU initialisation failed: ") + api.last_error(nullptr));
 
-    // ---- processImages (RF.cpp:835-1013): batches of bufferSize particles; numThreads loader threads fill
-    // batch k+1 while the GPU works on batch k (insert_batch returns once the batch has been uploaded)
+    // ---- processImages (RF.cpp:835-1013): batches of bufferSize particles in two page-locked buffers; numThreads
+    // loader threads fill batch k+1 (files -> pinned memory, metadata rows -> rfb200_particle) while batch k is being
+    // uploaded and inserted (insert_batch returns once the batch has been copied to the GPU)
     const size_t n = SF.size();
     const size_t B = (size_t)bufferSize;
-    std::vector<float> buf[2];
+    float* buf[2] = {nullptr, nullptr};
     std::vector<rfb200_particle> meta[2];
     for (int k = 0; k < 2; ++k) {
-        buf[k].resize(B * (size_t)N * N);
+        void* p = nullptr;
+        if (api.host_alloc(&p, B * (size_t)N * N * sizeof(float)) != RFB200_OK) {
+            if (buf[0]) api.host_free(buf[0]);
+            api.destroy(h);
+            throw ProgramError("cannot allocate the page-locked image buffers");
+        }
+        buf[k] = (float*)p;
         meta[k].resize(B);
     }
     auto t0 = std::chrono::steady_clock::now();
     std::string loadError;
+    std::mutex errM;
     auto loadBatch = [&](size_t first, size_t cnt, int slot) {
         std::atomic<size_t> next(0);
-        std::mutex errM;
         auto worker = [&] {
             for (;;) {
                 size_t k = next.fetch_add(1);
@@ -390,15 +403,22 @@ void ProgRecFourierB200::run() {
         const size_t FSCIndex = (n - 1) / 2;
         std::vector<float> vol((size_t)N * N * N);
         auto insertRange = [&](size_t begin, size_t end) {
+            if (begin >= end) return;
+            loadBatch(begin, std::min(B, end - begin), slot);
             for (size_t first = begin; first < end; first += B, slot ^= 1) {
-                size_t cnt = std::min(B, end - first);
-                loadBatch(first, cnt, slot);
+                const size_t cnt = std::min(B, end - first);
                 if (!loadError.empty()) throw ProgramError(loadError);
-                rc = api.insert_batch(h, buf[slot].data(), meta[slot].data(), (int32_t)cnt);
+                // prefetch the next batch into the other buffer while this one is uploaded and inserted
+                const size_t nextFirst = first + B;
+                std::thread prefetch;
+                if (nextFirst < end) prefetch = std::thread(loadBatch, nextFirst, std::min(B, end - nextFirst), slot ^ 1);
+                rc = api.insert_batch(h, buf[slot], meta[slot].data(), (int32_t)cnt);
+                if (prefetch.joinable()) prefetch.join();
                 if (rc != RFB200_OK) throw ProgramError(std::string("insert_batch failed: ") + api.last_error(h));
                 done += cnt;
                 if (verbose > 0) std::cout << "\r " << done << " / " << n << " images inserted" << std::flush;
             }
+            if (!loadError.empty()) throw ProgramError(loadError);
         };
         auto finish = [&](const std::string& name) {
             rc = api.finalize(h, vol.data());                                                   // RF.cpp:1056-1180
@@ -427,10 +447,14 @@ void ProgRecFourierB200::run() {
         }
     } catch (...) {
         api.destroy(h);
+        api.host_free(buf[0]);
+        api.host_free(buf[1]);
         closeImageCache();
         throw;
     }
     api.destroy(h);
+    api.host_free(buf[0]);
+    api.host_free(buf[1]);
     closeImageCache();
 }
 

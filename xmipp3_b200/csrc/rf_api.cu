@@ -1112,6 +1112,23 @@ int rfb200_weight_sum(rfb200_handle h, double* sum) {
     return rfb200_weight_sum_end(h, sum);
 }
 
+int rfb200_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return RFB200_ERR_ARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return RFB200_ERR_CUDA;
+    }
+    return RFB200_OK;
+}
+
+int rfb200_host_free(void* ptr) {
+    if (!ptr) return RFB200_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? RFB200_OK : RFB200_ERR_CUDA;
+}
+
 int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_stream) {
     if (!h) return RFB200_ERR_ARG;
     if (compute_stream) *compute_stream = (void*)h->compute;
