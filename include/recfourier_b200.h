@@ -167,6 +167,9 @@ int rfb200_weight_sum(rfb200_handle h, double* sum);
 int rfb200_weight_sum_begin(rfb200_handle h);
 int rfb200_weight_sum_end(rfb200_handle h, double* sum);
 
+/* Number of CUDA devices visible to the process (for host programs that start one process per GPU). */
+int rfb200_device_count(int32_t* n);
+
 /* Page-locked host memory for the image batches handed to rfb200_insert_batch: transfers from it run at full PCIe
  * speed and asynchronously (cudaHostAlloc / cudaFreeHost; replaces pinMemory / unpinMemory of
  * cuda_gpu_reconstruct_fourier.h:134-136).  Not tied to a handle. */

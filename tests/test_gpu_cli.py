@@ -100,3 +100,44 @@ def test_cli_errors(tmp_path):
     with pytest.raises(RuntimeError) as e:
         prog.run()
     assert "max_resolution" in str(e.value)
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_cli_two_gpus_prepare_fsc(tmp_path, oracle_mod):
+    """--gpus 2: the program forks one rank per GPU, each inserts a contiguous shard, one NCCL reduce per map;
+    full map and both half-set maps must equal the oracle's (and hence the single-GPU program's)."""
+    N, n = 32, 61
+    d, md = _dataset(tmp_path, N, n, True, True, ".stk", seed=11)
+    out = str(tmp_path / "full.vol")
+    root = str(tmp_path / "fsc")
+    prog = ProgRecFourier(useCTF=True, Ts=d["sampling"], fn_fsc=root, bufferSize=8, gpus=2)
+    prog.setIO(md, out)
+    log = prog.run(verbose=1)
+    assert "2 GPUs" in log
+    cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], shift_x=d["shift_x"], shift_y=d["shift_y"], **d["ctf"])
+    p = oracle_mod.make_particles(n, **cols)
+    split = (n - 1) // 2 + 1
+    for name, sl in ((root + "_1_recons.vol", slice(0, split)), (root + "_2_recons.vol", slice(split, n)), (out, slice(0, n))):
+        o = oracle_mod.Oracle(N, use_ctf=True, sampling=d["sampling"])
+        o.insert(d["images"][sl], p[sl], threads=1)
+        ref = o.finalize()
+        vol = io.read_volume(name)
+        assert synth.rel_l2(vol, ref) <= 1e-4, name
+        assert np.nanmin(synth.fsc(vol, ref)[1:]) >= 0.999, name
+
+
+def test_cli_gpus_all_single_box(tmp_path, oracle_mod):
+    """--gpus all on whatever the box has (1 GPU: runs in the launcher's own process)."""
+    N, n = 16, 20
+    d, md = _dataset(tmp_path, N, n, False, False, ".stk", seed=2)
+    out = str(tmp_path / "rec.vol")
+    prog = ProgRecFourier(gpus="all", bufferSize=4)
+    prog.setIO(md, out)
+    prog.run()
+    ref = _oracle(oracle_mod, d, N, False)
+    assert synth.rel_l2(io.read_volume(out), ref) <= 1e-4

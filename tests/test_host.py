@@ -139,7 +139,11 @@ def test_cli_parsing_defaults_and_errors():
     assert float(d["blob_radius"]) == 2.1 and d["blob_order"] == "2" and float(d["blob_alpha"]) == 10.4
     assert d["useCTF"] == "1" and float(d["sampling"]) == 1.34 and float(d["minCTF"]) == 0.05 and d["phaseFlipped"] == "1"
     assert d["do_weights"] == "1" and d["threads"] == "6" and d["iter"] == "0" and d["device"] == "3" and d["bufferSize"] == "256"
-    for bad in (["-o", "x.vol"], ["-i", "a.xmd", "--bogus"], ["-i", "a.xmd", "--padding", "two"]):
+    assert d["gpus"] == "1" and d["worldSize"] == "1"
+    assert _host.parse_cli(["-i", "a.xmd", "--gpus", "4"])["gpus"] == "4"
+    assert _host.parse_cli(["-i", "a.xmd", "--gpus", "all"])["gpus"] == "-1"
+    for bad in (["-o", "x.vol"], ["-i", "a.xmd", "--bogus"], ["-i", "a.xmd", "--padding", "two"], ["-i", "a.xmd", "--gpus", "0"],
+                ["-i", "a.xmd", "--gpus"]):
         with pytest.raises(_host.HostError):
             _host.parse_cli(bad)
 
@@ -151,6 +155,12 @@ def test_cli_binary_reports_errors(tmp_path):
     assert r.returncode == 2 and "-i <md_file>" in r.stderr
     r = subprocess.run([exe, "-i", str(tmp_path / "nope.xmd"), "-v", "0"], capture_output=True, text=True)
     assert r.returncode == 1 and "XMIPP_ERROR" in r.stderr
+    # --gpus 2 without a GPU: both ranks fail, the launcher reports it and leaves no rendezvous file behind
+    r = subprocess.run([exe, "-i", str(tmp_path / "nope.xmd"), "-v", "0", "--gpus", "2"], capture_output=True, text=True)
+    assert r.returncode == 1 and "a GPU rank failed" in r.stderr
+    # ranks started by an external launcher need the rendezvous file
+    r = subprocess.run([exe, "-i", "x.xmd"], capture_output=True, text=True, env=dict(os.environ, RFB200_WORLD_SIZE="2", RFB200_RANK="1"))
+    assert r.returncode == 2 and "RFB200_ID_FILE" in r.stderr
 
 
 @pytest.mark.parametrize("geo", [dict(N=16), dict(N=25), dict(N=27, pad_proj=1.0, pad_vol=1.0), dict(N=32, pad_proj=1.0, pad_vol=2.0),

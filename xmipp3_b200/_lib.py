@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
-    "rfb200_host_alloc", "rfb200_host_free",
+    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count",
 ]
 
 

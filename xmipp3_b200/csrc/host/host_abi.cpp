@@ -115,10 +115,10 @@ int rfh_parse_cli(int argc, const char* const* argv, char* out, int outLen) {
         snprintf(buf, sizeof buf,
                  "fn_sel=%s\nfn_out=%s\nfn_sym=%s\nfn_fsc=%s\ndo_weights=%d\npad_proj=%g\npad_vol=%g\nblob_radius=%g\nblob_order=%d\n"
                  "blob_alpha=%g\nmax_resolution=%g\nthreads=%d\niter=%d\nuseCTF=%d\nphaseFlipped=%d\nminCTF=%g\nsampling=%g\ndevice=%d\n"
-                 "bufferSize=%d\nfast=%d\n",
+                 "bufferSize=%d\nfast=%d\ngpus=%d\nrank=%d\nworldSize=%d\n",
                  p.fn_sel.c_str(), p.fn_out.c_str(), p.fn_sym.c_str(), p.fn_fsc.c_str(), (int)p.do_weights, p.padding_factor_proj,
                  p.padding_factor_vol, p.blob_radius, p.blob_order, p.blob_alpha, p.maxResolution, p.numThreads, p.NiterWeight,
-                 (int)p.useCTF, (int)p.phaseFlipped, p.minCTF, p.Ts, p.device, p.bufferSize, (int)p.fast);
+                 (int)p.useCTF, (int)p.phaseFlipped, p.minCTF, p.Ts, p.device, p.bufferSize, (int)p.fast, p.gpus, p.rank, p.worldSize);
         strncpy(out, buf, outLen - 1);
         out[outLen - 1] = 0;
         return 0;

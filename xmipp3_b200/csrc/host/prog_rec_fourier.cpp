@@ -3,6 +3,8 @@
 
 #include <dlfcn.h>
 #include <libgen.h>
+#include <signal.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -11,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <mutex>
 #include <thread>
@@ -36,6 +39,12 @@ struct Api {
     int (*get_timings)(rfb200_handle, rfb200_timings*) = nullptr;
     int (*host_alloc)(void**, size_t) = nullptr;
     int (*host_free)(void*) = nullptr;
+    int (*device_count)(int32_t*) = nullptr;
+    int (*nccl_unique_id)(void*) = nullptr;
+    int (*nccl_init)(rfb200_handle, const void*, int32_t, int32_t) = nullptr;
+    int (*reduce_nccl)(rfb200_handle, int32_t) = nullptr;
+    int (*sync)(rfb200_handle) = nullptr;
+    int (*reset)(rfb200_handle) = nullptr;
 };
 
 std::string selfDir() {
@@ -76,6 +85,12 @@ Api loadApi() {
     BIND(get_timings, "rfb200_get_timings")
     BIND(host_alloc, "rfb200_host_alloc")
     BIND(host_free, "rfb200_host_free")
+    BIND(device_count, "rfb200_device_count")
+    BIND(nccl_unique_id, "rfb200_nccl_unique_id")
+    BIND(nccl_init, "rfb200_nccl_init")
+    BIND(reduce_nccl, "rfb200_reduce_nccl")
+    BIND(sync, "rfb200_sync")
+    BIND(reset, "rfb200_reset")
 #undef BIND
     return a;
 }
@@ -162,6 +177,9 @@ std::string ProgRecFourierB200::usage() {
         "  [--minCTF <ctf=0.01>]              : Minimum value of the CTF that will be inverted\n"
         "  [--device <dev=0>]                 : GPU device to use\n"
         "  [--bufferSize <size=1024>]         : Number of projections handed to the GPU per call\n"
+        "  [--gpus <n=1>]                     : use n GPUs (devices dev .. dev+n-1, \"all\": every visible one): one process\n"
+        "                                       per GPU on a shard of the particles, one NCCL reduce before the\n"
+        "                                       normalisation (replaces mpirun xmipp_mpi_cuda_reconstruct_fourier)\n"
         "  [--fftOnGPU]                       : accepted for compatibility (the FFT always runs on the GPU)\n"
         "  [--fast]                           : accepted for compatibility; the exact blob insertion is used (it is\n"
         "                                       the fast path here), so the result equals the one without --fast\n"
@@ -174,7 +192,7 @@ void ProgRecFourierB200::readParams(int argc, const char* const* argv) {
     for (int i = 1; i < argc; ++i) a.v.push_back(argv[i]);
     static const char* known[] = {"-i", "-o", "--iter", "--sym", "--padding", "--prepare_fsc", "--max_resolution", "--weight",
                                   "--thr", "--blob", "--useCTF", "--sampling", "--phaseFlipped", "--minCTF", "--device",
-                                  "--bufferSize", "--fftOnGPU", "--fast", "-v", "-h", "--help"};
+                                  "--bufferSize", "--fftOnGPU", "--fast", "--gpus", "-v", "-h", "--help"};
     for (auto& t : a.v) {
         bool isOpt = t.size() > 1 && t[0] == '-' && !(isdigit((unsigned char)t[1]) || t[1] == '.');
         if (!isOpt) continue;
@@ -225,6 +243,24 @@ void ProgRecFourierB200::readParams(int argc, const char* const* argv) {
     d = bufferSize; num("--bufferSize", 0, d); bufferSize = std::max(1, (int)d);
     fast = a.find("--fast") != std::string::npos;
     d = verbose; num("-v", 0, d); verbose = (int)d;
+    {
+        auto v = a.values("--gpus");
+        if (a.find("--gpus") != std::string::npos) {
+            if (v.empty()) throw ProgramError("option --gpus needs a value");
+            gpus = v[0] == "all" ? -1 : (int)toDouble(v[0], "--gpus");
+            if (gpus == 0 || gpus < -1) throw ProgramError("--gpus must be a positive number or \"all\"");
+        }
+    }
+    // ranks started by an external launcher (one process per GPU, like the MPI program's workers)
+    if (const char* e = getenv("RFB200_WORLD_SIZE")) {
+        worldSize = atoi(e);
+        const char* r = getenv("RFB200_RANK");
+        const char* f = getenv("RFB200_ID_FILE");
+        rank = r ? atoi(r) : 0;
+        idFile = f ? f : "";
+        if (worldSize < 1 || rank < 0 || rank >= worldSize) throw ProgramError("bad RFB200_RANK / RFB200_WORLD_SIZE");
+        if (worldSize > 1 && idFile.empty()) throw ProgramError("RFB200_WORLD_SIZE > 1 needs RFB200_ID_FILE (rendezvous file of the NCCL id)");
+    }
 }
 
 void ProgRecFourierB200::show() const {
@@ -292,7 +328,101 @@ void ProgRecFourierB200::particleFromRow(const MetaData& md, size_t i, bool hasC
     }
 }
 
+// --gpus: one process per GPU.  The parent never touches CUDA (so forking is safe), forks the ranks, and waits;
+// a rank that fails takes the others down (they would otherwise wait for it inside NCCL).
+void ProgRecFourierB200::runRanks() {
+    int n = gpus;
+    if (n < 0) {    // "all": ask the CUDA library from a throw-away child
+        int fd[2];
+        if (pipe(fd) != 0) throw ProgramError("pipe() failed");
+        std::cout.flush();
+        pid_t pid = fork();
+        if (pid < 0) throw ProgramError("fork() failed");
+        if (pid == 0) {
+            int32_t c = 0;
+            try {
+                Api api = loadApi();
+                api.device_count(&c);
+            } catch (...) {
+                c = 0;
+            }
+            ssize_t w = write(fd[1], &c, sizeof c);
+            _exit(w == (ssize_t)sizeof c ? 0 : 1);
+        }
+        close(fd[1]);
+        int32_t c = 0;
+        if (read(fd[0], &c, sizeof c) != (ssize_t)sizeof c) c = 0;
+        close(fd[0]);
+        int st;
+        waitpid(pid, &st, 0);
+        if (c < 1) throw ProgramError("no CUDA device visible (there is no CPU fallback)");
+        n = c - device;
+        if (n < 1) throw ProgramError("--device is beyond the last visible GPU");
+    }
+    if (n == 1) {
+        gpus = 1;
+        run();
+        return;
+    }
+    char tmpl[] = "/tmp/rfb200_nccl_id_XXXXXX";
+    int tfd = mkstemp(tmpl);
+    if (tfd < 0) throw ProgramError("cannot create the rendezvous file in /tmp");
+    close(tfd);
+    unlink(tmpl);   // rank 0 creates it (atomically) once the id exists
+    std::cout.flush();
+    std::cerr.flush();
+    std::vector<pid_t> pids;
+    for (int r = 0; r < n; ++r) {
+        pid_t pid = fork();
+        if (pid < 0) {
+            for (pid_t p : pids) kill(p, SIGTERM);
+            throw ProgramError("fork() failed");
+        }
+        if (pid == 0) {
+            rank = r;
+            worldSize = n;
+            idFile = tmpl;
+            device += r;
+            gpus = 1;
+            if (r > 0) verbose = 0;
+            int code = tryRun();
+            std::cout.flush();
+            std::cerr.flush();
+            _exit(code);
+        }
+        pids.push_back(pid);
+    }
+    int failed = 0;
+    size_t left = pids.size();
+    while (left > 0) {
+        int st = 0;
+        pid_t p = wait(&st);
+        if (p < 0) break;
+        bool mine = false;
+        for (auto& q : pids)
+            if (q == p) {
+                q = -1;
+                mine = true;
+            }
+        if (!mine) continue;
+        --left;
+        const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + (WIFSIGNALED(st) ? WTERMSIG(st) : 0);
+        if (code != 0 && !failed) {
+            failed = code;
+            for (pid_t q : pids)
+                if (q > 0) kill(q, SIGTERM);
+        }
+    }
+    unlink(tmpl);
+    unlink((std::string(tmpl) + ".tmp").c_str());
+    if (failed) throw ProgramError("a GPU rank failed (exit code " + std::to_string(failed) + ")");
+}
+
 void ProgRecFourierB200::run() {
+    if (gpus != 1 && worldSize == 1) {
+        runRanks();
+        return;
+    }
     show();
     if (fast)   // the reference's --fast trades accuracy (nearest pixel + final blob convolution) for speed; no need here
         std::fprintf(stderr, "xmipp_reconstruct_fourier_b200: --fast accepted; using the exact blob insertion (same result as without --fast)\n");
@@ -352,6 +482,42 @@ void ProgRecFourierB200::run() {
     rfb200_handle h = nullptr;
     int rc = api.create(&cfg, &h);
     if (rc != RFB200_OK) throw ProgramError(std::string("GPU initialisation failed: ") + api.last_error(nullptr));
+    if (worldSize > 1) {
+        // rendezvous: rank 0 publishes the 128-byte ncclUniqueId in idFile (written aside, then renamed), the others
+        // wait for it (the MPI program broadcasts its job ranges the same way, mpi_reconstruct_fourier_gpu.cpp:150-200)
+        char id[128];
+        if (rank == 0) {
+            if (api.nccl_unique_id(id) != RFB200_OK) {
+                api.destroy(h);
+                throw ProgramError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)");
+            }
+            const std::string tmp = idFile + ".tmp";
+            std::ofstream f(tmp, std::ios::binary);
+            f.write(id, sizeof id);
+            f.close();
+            if (!f || rename(tmp.c_str(), idFile.c_str()) != 0) {
+                api.destroy(h);
+                throw ProgramError("cannot write the rendezvous file " + idFile);
+            }
+        } else {
+            auto tStart = std::chrono::steady_clock::now();
+            for (;;) {
+                std::ifstream f(idFile, std::ios::binary);
+                if (f && f.read(id, sizeof id) && f.gcount() == (std::streamsize)sizeof id) break;
+                if (std::chrono::steady_clock::now() - tStart > std::chrono::seconds(120)) {
+                    api.destroy(h);
+                    throw ProgramError("timed out waiting for the rendezvous file " + idFile);
+                }
+                std::this_thread::sleep_for(std::chrono::milliseconds(5));
+            }
+        }
+        rc = api.nccl_init(h, id, worldSize, rank);
+        if (rc != RFB200_OK) {
+            std::string msg = std::string("NCCL initialisation failed: ") + api.last_error(h);
+            api.destroy(h);
+            throw ProgramError(msg);
+        }
+    }
 
     // ---- processImages (RF.cpp:835-1013): batches of bufferSize particles in two page-locked buffers; numThreads
     // loader threads fill batch k+1 (files -> pinned memory, metadata rows -> rfb200_particle) while batch k is being
@@ -403,6 +569,11 @@ void ProgRecFourierB200::run() {
         const size_t FSCIndex = (n - 1) / 2;
         std::vector<float> vol((size_t)N * N * N);
         auto insertRange = [&](size_t begin, size_t end) {
+            if (worldSize > 1) {    // this rank's contiguous shard of [begin, end)
+                const size_t len = end - begin;
+                end = begin + len * (size_t)(rank + 1) / (size_t)worldSize;
+                begin = begin + len * (size_t)rank / (size_t)worldSize;
+            }
             if (begin >= end) return;
             loadBatch(begin, std::min(B, end - begin), slot);
             for (size_t first = begin; first < end; first += B, slot ^= 1) {
@@ -420,20 +591,31 @@ void ProgRecFourierB200::run() {
             }
             if (!loadError.empty()) throw ProgramError(loadError);
         };
+        // every rank's partial V and W are summed onto rank 0 over NVLink; the others are done with these particles
+        auto reduce = [&] {
+            if (worldSize == 1) return;
+            rc = api.reduce_nccl(h, 0);
+            if (rc != RFB200_OK) throw ProgramError(std::string("reduce failed: ") + api.last_error(h));
+            if (rank != 0 && api.reset(h) != RFB200_OK) throw ProgramError(std::string("reset failed: ") + api.last_error(h));
+        };
         auto finish = [&](const std::string& name) {
+            if (rank != 0) return;
             rc = api.finalize(h, vol.data());                                                   // RF.cpp:1056-1180
             if (rc != RFB200_OK) throw ProgramError(std::string("finalize failed: ") + api.last_error(h));
             writeVolume(name, vol.data(), N, N, N);                                             // RF.cpp:1179
         };
         if (saveFSC) {
             insertRange(0, FSCIndex + 1);
+            reduce();
             finish(fn_fsc + "_1_recons.vol");
-            if (api.halfset_push(h) != RFB200_OK) throw ProgramError(std::string("halfset_push failed: ") + api.last_error(h));
+            if (rank == 0 && api.halfset_push(h) != RFB200_OK) throw ProgramError(std::string("halfset_push failed: ") + api.last_error(h));
             insertRange(FSCIndex + 1, n);
+            reduce();
             finish(fn_fsc + "_2_recons.vol");
-            if (api.halfset_merge(h) != RFB200_OK) throw ProgramError(std::string("halfset_merge failed: ") + api.last_error(h));
+            if (rank == 0 && api.halfset_merge(h) != RFB200_OK) throw ProgramError(std::string("halfset_merge failed: ") + api.last_error(h));
         } else {
             insertRange(0, n);
+            reduce();
         }
         if (verbose > 0) std::cout << std::endl;
         finish(fn_out);
@@ -443,7 +625,8 @@ void ProgRecFourierB200::run() {
             if (api.get_timings(h, &t) == RFB200_OK)
                 std::cout << " GPU time (ms): h2d " << t.h2d_ms << ", pad " << t.preprocess_ms << ", fft " << t.fft2d_ms << ", slices "
                           << t.slice_ms << ", gather " << t.gather_ms << ", edge " << t.edge_ms << ", finalize " << t.finalize_ms << "\n";
-            std::cout << " " << n << " images in " << secs << " s (" << n / secs << " images/s including file I/O)" << std::endl;
+            std::cout << " " << n << " images in " << secs << " s (" << n / secs << " images/s including file I/O"
+                      << (worldSize > 1 ? ", " + std::to_string(worldSize) + " GPUs" : std::string()) << ")" << std::endl;
         }
     } catch (...) {
         api.destroy(h);

@@ -47,6 +47,13 @@ public:
     int bufferSize = 1024;              // --bufferSize: particles handed to the GPU per call
     bool fast = false;                  // --fast
     int verbose = 1;                    // -v
+    // multi-GPU (replaces mpirun + xmipp_mpi_cuda_reconstruct_fourier, parallel_adapt_cuda/mpi_reconstruct_fourier_gpu.cpp):
+    // --gpus N forks one process per GPU (devices device .. device+N-1); every process reconstructs a contiguous
+    // shard of the particles into private accumulators, one NCCL reduce onto rank 0 precedes the finalisation.
+    // An external launcher can instead export RFB200_RANK / RFB200_WORLD_SIZE / RFB200_ID_FILE (+ --device per rank).
+    int gpus = 1;                       // --gpus <n | all>
+    int rank = 0, worldSize = 1;        // set by --gpus or the environment
+    std::string idFile;                 // rendezvous file for the 128-byte ncclUniqueId
 
     static std::string usage();
     // parse argv (throws ProgramError on unknown / malformed options)
@@ -54,6 +61,8 @@ public:
     void show() const;
     void setIO(const std::string& fnIn, const std::string& fnOut) { fn_sel = fnIn; fn_out = fnOut; }
     void run();
+    // --gpus launcher: forks one rank per GPU (each runs run() on its shard) and waits for them
+    void runRanks();
     // like XmippProgram::tryRun: 0 on success, non-zero after printing the error
     int tryRun();
 

@@ -1112,6 +1112,18 @@ int rfb200_weight_sum(rfb200_handle h, double* sum) {
     return rfb200_weight_sum_end(h, sum);
 }
 
+int rfb200_device_count(int32_t* n) {
+    if (!n) return RFB200_ERR_ARG;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        *n = 0;
+        return RFB200_ERR_CUDA;
+    }
+    *n = c;
+    return RFB200_OK;
+}
+
 int rfb200_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return RFB200_ERR_ARG;
     *ptr = nullptr;

@@ -32,6 +32,7 @@ class ProgRecFourier:
         self.Ts = 1.0
         self.device = 0
         self.bufferSize = 1024
+        self.gpus = 1          # --gpus <n | "all">: one process per GPU, NCCL reduce onto rank 0
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise TypeError("unknown parameter " + k)
@@ -55,6 +56,8 @@ class ProgRecFourier:
             a += ["--useCTF", "--sampling", repr(float(self.Ts))]
         if self.phaseFlipped:
             a.append("--phaseFlipped")
+        if self.gpus != 1:
+            a += ["--gpus", str(self.gpus)]
         return a
 
     def run(self, verbose=0):
