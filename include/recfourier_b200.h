@@ -76,7 +76,10 @@ typedef struct {
     double min_ctf;           /* --minCTF <0.01>                                             */
     int32_t use_weights;      /* --weight                                                    */
     int32_t n_iter_weight;    /* --iter <1>: 0 = no weight correction, >= 1 passes           */
-    int32_t fast;             /* --fast (nearest-pixel insertion + final blob convolution)   */
+    int32_t fast;             /* --fast: nearest-pixel insertion in single precision + one final 3-D blob convolution
+                               * (reconstruct_fourier_gpu.cpp:71-72, 879-893; cuda_gpu_reconstruct_fourier.cpp:455-503).
+                               * Images are then padded to N*pad_vol, n_iter_weight is ignored (the --fast programs
+                               * have no --iter) and the accumulators are the (S+1)^3 temporary volume / weights.       */
     int32_t device;           /* CUDA device ordinal                                         */
     int32_t max_batch;        /* largest n passed to rfb200_insert_batch (0 = default 1024)  */
     int32_t reserved0;
@@ -138,6 +141,8 @@ int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_
  * V = Z*Z*X interleaved (re,im) float32, W = Z*Z*X float32.  On the x = 0 plane the values
  * are those AFTER forceWeightSymmetry / enforceHermitianSymmetry (RF.cpp:1188-1221). */
 int rfb200_export_accumulators(rfb200_handle h, float* V, float* W);
+/* With cfg.fast the call returns the temporary spaces instead (copyTempVolumes of the reference): V = (S+1)^3
+ * interleaved (re,im), W = (S+1)^3, [z][y][x] with the origin at S/2, S + 1 = rfb200_info.tile. */
 
 /* correctWeight + finishComputations (RF.cpp:1056-1180): weight normalisation, 3-D inverse
  * FFT, crop and gridding correction.  out: N*N*N float32 in HOST memory, [z][y][x].

@@ -14,9 +14,13 @@ _SO = os.path.join(_HERE, "liboracle_recfourier.so")
 _SRC = os.path.join(_HERE, "recfourier_oracle.cpp")
 
 
+_SRC_FAST = os.path.join(_HERE, "recfourier_fast_oracle.cpp")
+
+
 def build(force=False):
-    """Compile the C++ restatement with g++ (no CUDA, no external libraries)."""
-    deps = [_SRC, os.path.join(_HERE, "oracle_abi.h")]
+    """Compile the C++ restatements with g++ (no CUDA, no external libraries).  The --fast restatement is single
+    precision and decision-sensitive, so its translation unit is built without a*b+c contraction."""
+    deps = [_SRC, _SRC_FAST, os.path.join(_HERE, "oracle_abi.h")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps if os.path.exists(d))):
         return _SO
@@ -24,8 +28,13 @@ def build(force=False):
         if os.path.exists(_SO):
             return _SO
         raise RuntimeError("oracle source missing")
-    cmd = ["g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-fPIC", "-shared", "-pthread", "-o", _SO, _SRC]
-    subprocess.check_call(cmd, cwd=_HERE)
+    base = ["g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-fPIC", "-pthread"]
+    obj = [os.path.join(_HERE, "_oracle_main.o"), os.path.join(_HERE, "_oracle_fast.o")]
+    subprocess.check_call(base + ["-c", _SRC, "-o", obj[0]], cwd=_HERE)
+    subprocess.check_call(base + ["-ffp-contract=off", "-c", _SRC_FAST, "-o", obj[1]], cwd=_HERE)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", _SO] + obj, cwd=_HERE)
+    for o in obj:
+        os.remove(o)
     return _SO
 
 
@@ -96,12 +105,83 @@ def lib():
             getattr(L, f).argtypes = [C.c_double]
         L.orf_fft2_r2c.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orf_fft1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orf_finish_fourier.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_fast_create.restype = C.c_void_p
+        L.orf_fast_create.argtypes = [C.POINTER(Config)]
+        L.orf_fast_destroy.argtypes = [C.c_void_p]
+        L.orf_fast_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.orf_fast_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orf_fast_get_temp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_fast_finalize.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def _make_config(img_size, padding, max_resolution, blob, sym_matrices, use_ctf, sampling, min_ctf, phase_flipped,
+                 use_weights, n_iter_weight):
+    sm = np.zeros((0, 9)) if sym_matrices is None else np.ascontiguousarray(sym_matrices, dtype=np.float64).reshape(-1, 9)
+    cfg = Config()
+    cfg.img_size = int(img_size)
+    cfg.n_sym = sm.shape[0]
+    cfg.pad_proj, cfg.pad_vol = float(padding[0]), float(padding[1])
+    cfg.max_resolution = float(max_resolution)
+    cfg.blob_radius, cfg.blob_order, cfg.blob_alpha = float(blob[0]), int(blob[1]), float(blob[2])
+    cfg.use_ctf = int(bool(use_ctf))
+    cfg.sampling = float(sampling)
+    cfg.min_ctf = float(min_ctf)
+    cfg.phase_flipped = int(bool(phase_flipped))
+    cfg.use_weights = int(bool(use_weights))
+    cfg.n_iter_weight = int(n_iter_weight)
+    cfg.sym_matrices = sm.ctypes.data_as(C.POINTER(C.c_double)) if sm.size else None
+    return cfg, sm
+
+
+class FastOracle:
+    """CPU restatement of the --fast arithmetic (ProgRecFourierGPU with useFast: nearest-pixel insertion in single
+    precision + one final 3-D blob convolution); see recfourier_fast_oracle.cpp."""
+
+    def __init__(self, img_size, padding=(2.0, 2.0), max_resolution=0.5, blob=(1.9, 0, 15.0),
+                 sym_matrices=None, use_ctf=False, sampling=1.0, min_ctf=0.01, phase_flipped=False, use_weights=False):
+        self._L = lib()
+        self._cfg, self._sym = _make_config(img_size, padding, max_resolution, blob, sym_matrices, use_ctf, sampling,
+                                            min_ctf, phase_flipped, use_weights, 1)
+        self._h = self._L.orf_fast_create(C.byref(self._cfg))
+        if not self._h:
+            raise RuntimeError("orf_fast_create failed")
+        v = [C.c_int() for _ in range(4)]
+        self._L.orf_fast_dims(self._h, *[C.byref(x) for x in v])
+        self.S, self.sx, self.sy, self.Pv = [x.value for x in v]
+        self.N = int(img_size)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orf_fast_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def insert(self, images, particles):
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        particles = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+        assert images.shape == (len(particles), self.N, self.N)
+        self._L.orf_fast_insert(self._h, _ptr(images), _ptr(particles), len(particles))
+
+    def temp_spaces(self):
+        n = self.S + 1
+        V = np.empty((n, n, n), dtype=np.complex64)
+        W = np.empty((n, n, n), dtype=np.float32)
+        self._L.orf_fast_get_temp(self._h, _ptr(V), _ptr(W))
+        return V, W
+
+    def finalize(self):
+        out = np.empty((self.N,) * 3, dtype=np.float64)
+        self._L.orf_fast_finalize(self._h, _ptr(out))
+        return out
 
 
 class Oracle:

@@ -38,6 +38,18 @@ void orf_insert(void* h, const float* imgs, const orf_particle* meta, int n, int
 void orf_get_accumulators(void* h, double* V, double* W);
 void orf_add_accumulators(void* h, const double* V, const double* W);
 void orf_finalize(void* h, double* out);
+/* tail of finishComputations on a given Z*Z*(Z/2+1) Fourier volume (interleaved re,im): c2r, CenterFFT, crop, correction */
+void orf_finish_fourier(void* h, const double* Vri, double* out);
+
+/* ---- --fast (recfourier_fast_oracle.cpp): nearest-pixel insertion + final blob convolution, single precision,
+ * restating ProgRecFourierGPU with useFast (reconstruction_adapt_cuda/reconstruct_fourier_gpu.cpp and the device
+ * functions of reconstruction_cuda/cuda_gpu_reconstruct_fourier.cpp:391-503, 655-760). */
+void* orf_fast_create(const orf_config* cfg);
+void orf_fast_destroy(void* h);
+void orf_fast_dims(void* h, int* S, int* sx, int* sy, int* Pv);
+void orf_fast_insert(void* h, const float* imgs, const orf_particle* meta, int n);
+void orf_fast_get_temp(void* h, float* Vri, float* W);     /* (S+1)^3 interleaved complex / real, [z][y][x] */
+void orf_fast_finalize(void* h, double* out);
 void orf_tables(void* h, double* blobTableSqrt, double* fourierBlobTable, double* iDeltaSqrt, double* iDeltaFourier);
 void orf_preprocess(void* h, const float* img, const orf_particle* p, double* F, double* Ainv);
 void orf_apply_shift(void* h, const float* img, double sx, double sy, double* out);

@@ -772,6 +772,12 @@ struct Oracle {
             else if (1.0 / w[k] > kAccuracy) v[k] *= corr2D_3D * w[k];
             else v[k] = 0;
         }
+        finish_fourier(v, out);
+    }
+
+    // tail of finishComputations (RF.cpp:1145-1179): inverse transform, CenterFFT, crop, gridding correction.
+    // Also the tail of the --fast programs (reconstruct_fourier_gpu.cpp:894-931), which is the same code.
+    void finish_fourier(std::vector<cd>& v, double* out) const {
         // inverse c2r, unnormalised — :1145 (complex along z, y; c2r along x using Re of x=0, x=Z/2)
         std::vector<double> vol((size_t)Z * Z * Z);
         c2r_3d(v, vol);
@@ -884,6 +890,12 @@ void orf_add_accumulators(void* h, const double* V, const double* W) {
     for (size_t k = 0; k < o->V.size(); ++k) { o->V[k] += cd(V[2 * k], V[2 * k + 1]); o->W[k] += W[k]; }
 }
 void orf_finalize(void* h, double* out) { static_cast<Oracle*>(h)->finalize(out); }
+void orf_finish_fourier(void* h, const double* Vri, double* out) {
+    Oracle* o = static_cast<Oracle*>(h);
+    std::vector<cd> v((size_t)o->Z * o->Z * o->X);
+    for (size_t k = 0; k < v.size(); ++k) v[k] = cd(Vri[2 * k], Vri[2 * k + 1]);
+    o->finish_fourier(v, out);
+}
 void orf_tables(void* h, double* blobTableSqrt, double* fourierBlobTable, double* iDeltaSqrt, double* iDeltaFourier) {
     auto* o = static_cast<Oracle*>(h);
     std::memcpy(blobTableSqrt, o->blobTableSqrt.data(), kTable * sizeof(double));

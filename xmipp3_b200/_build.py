@@ -15,7 +15,7 @@ LIB_HOST = os.path.join(_HERE, "librecfourier_host.so")
 CLI_BIN = os.path.join(_HERE, "xmipp_reconstruct_fourier_b200")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _newer(target, sources):

@@ -165,6 +165,7 @@ class Reconstructor:
         self._check(self._L.rfb200_get_info(self._h, C.byref(info)))
         self.info = info
         self.N, self.P, self.Z = info.N, info.P, info.Z
+        self.fast = bool(fast)
 
     def _check(self, rc):
         if rc != OK:
@@ -229,6 +230,12 @@ class Reconstructor:
 
     # -- results
     def accumulators(self):
+        if self.fast:       # --fast: the (S+1)^3 temporary volume and weights, S + 1 = info.tile
+            n = self.info.tile
+            V = np.empty((n, n, n), dtype=np.complex64)
+            W = np.empty((n, n, n), dtype=np.float32)
+            self._check(self._L.rfb200_export_accumulators(self._h, V.ctypes.data_as(C.c_void_p), W.ctypes.data_as(C.c_void_p)))
+            return V, W
         Z, X = self.Z, self.Z // 2 + 1
         V = np.empty((Z, Z, X), dtype=np.complex64)
         W = np.empty((Z, Z, X), dtype=np.float32)

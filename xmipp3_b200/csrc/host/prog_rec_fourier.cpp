@@ -181,8 +181,9 @@ std::string ProgRecFourierB200::usage() {
         "                                       per GPU on a shard of the particles, one NCCL reduce before the\n"
         "                                       normalisation (replaces mpirun xmipp_mpi_cuda_reconstruct_fourier)\n"
         "  [--fftOnGPU]                       : accepted for compatibility (the FFT always runs on the GPU)\n"
-        "  [--fast]                           : accepted for compatibility; the exact blob insertion is used (it is\n"
-        "                                       the fast path here), so the result equals the one without --fast\n"
+        "  [--fast]                           : Do the blobing at the end of the computation (nearest-pixel insertion,\n"
+        "                                       one final blob convolution). Gives slightly different results;\n"
+        "                                       --iter and --padding <proj> are then ignored like in the reference\n"
         "  [--prepare_fsc <fscfile>]          : Filename root for FSC files (<root>_1_recons.vol, <root>_2_recons.vol)\n"
         "  [-v <verbosity=1>]\n";
 }
@@ -424,8 +425,6 @@ void ProgRecFourierB200::run() {
         return;
     }
     show();
-    if (fast)   // the reference's --fast trades accuracy (nearest pixel + final blob convolution) for speed; no need here
-        std::fprintf(stderr, "xmipp_reconstruct_fourier_b200: --fast accepted; using the exact blob insertion (same result as without --fast)\n");
     if (NiterWeight < 0) throw ProgramError("--iter must be >= 0");
 
     // ---- produceSideinfo (RF.cpp:184-287)
@@ -476,7 +475,7 @@ void ProgRecFourierB200::run() {
     cfg.min_ctf = minCTF;
     cfg.use_weights = do_weights ? 1 : 0;
     cfg.n_iter_weight = NiterWeight;
-    cfg.fast = 0;
+    cfg.fast = fast ? 1 : 0;       // reconstruct_fourier_gpu.cpp:87
     cfg.device = device;
     cfg.max_batch = bufferSize;
     rfb200_handle h = nullptr;

@@ -21,6 +21,7 @@
 #include "rf_kernels.cuh"
 #include "rf_sticks.cuh"
 #include "rf_fft.cuh"
+#include "rf_fast.cuh"
 
 #if __has_include(<nccl.h>)
 #include <nccl.h>
@@ -50,6 +51,7 @@ struct ParamSlot {      // pinned host staging for one chunk's parameters
     PlaneS* planesS = nullptr;
     float* soaP = nullptr;
     int* imgPlane0 = nullptr;
+    FastSpace* fast = nullptr;     // --fast: traverse spaces of the chunk
     cudaEvent_t done = nullptr;
     bool used = false;
 };
@@ -164,6 +166,15 @@ struct rfb200_handle_s {
     float2* dTwiddle = nullptr;
     cudaEvent_t swStart = nullptr, swStop = nullptr;
     bool swStarted = false;
+    // ---- --fast (rf_fast.cuh): dVb / dWb are then the (S+1)^3 temporary volume and weights
+    bool fast = false;
+    FastGeo fgeo{};
+    float4* dFastPix = nullptr;     // per image sy x sx folded pixels
+    FastSpace* dFastSpaces = nullptr;
+    float2* dFastVh = nullptr;      // finalisation: mirrored half space, then its blob convolution
+    float2* dFastVc = nullptr;
+    float* dFastWh = nullptr;
+    float* dFastWc = nullptr;
     double* dSum = nullptr;         // 1024 partials + 1 result
     double* hSum = nullptr;         // pinned
     cudaEvent_t evSum = nullptr;    // completion of the last rfb200_weight_sum_begin
@@ -336,6 +347,33 @@ int get_plan2d(rfb200_handle h, int batch, cufftHandle* out) {
     return RFB200_OK;
 }
 
+// weight and shift parameters of one metadata row (RF.cpp:362-381)
+ImgParams make_img_params(const rfb200_config& cfg, const rfb200_particle& p, bool& anySpline) {
+    ImgParams q{};
+    double w = cfg.use_weights ? p.weight : 1.0;     // RF.cpp:374-381
+    q.weight = (float)w;
+    q.skip = (w == 0.0) ? 1 : 0;                        // RF.cpp:483-484
+    // readApplyGeo(only_apply_shifts): out(x) = in(x - shift).  Integer shifts are an exact circular
+    // shift; if either component is fractional the image goes through cubic B-spline interpolation.
+    double rx = std::nearbyint(p.shift_x), ry = std::nearbyint(p.shift_y);
+    bool integer = std::fabs(p.shift_x - rx) < 1e-9 && std::fabs(p.shift_y - ry) < 1e-9;
+    if (integer) {
+        q.mx = (int)(-rx);
+        q.my = (int)(-ry);
+        q.ux = q.uy = 0.f;
+        q.spline = 0;
+    } else {
+        double fx = std::floor(-p.shift_x), fy = std::floor(-p.shift_y);
+        q.mx = (int)fx;
+        q.my = (int)fy;
+        q.ux = (float)(-p.shift_x - fx);
+        q.uy = (float)(-p.shift_y - fy);
+        q.spline = 1;
+        anySpline = true;
+    }
+    return q;
+}
+
 // fill one chunk's parameter slot on the host (double precision) and upload it
 int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, ParamSlot** slotOut, int* nPlanesOut, bool* anySplineOut) {
     bool anySpline = false;
@@ -347,28 +385,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
     int np = 0;
     for (int i = 0; i < n; ++i) {
         const rfb200_particle& p = meta[i];
-        ImgParams q{};
-        double w = h->cfg.use_weights ? p.weight : 1.0;     // RF.cpp:374-381
-        q.weight = (float)w;
-        q.skip = (w == 0.0) ? 1 : 0;                        // RF.cpp:483-484
-        // readApplyGeo(only_apply_shifts): out(x) = in(x - shift).  Integer shifts are an exact circular
-        // shift; if either component is fractional the image goes through cubic B-spline interpolation.
-        double rx = std::nearbyint(p.shift_x), ry = std::nearbyint(p.shift_y);
-        bool integer = std::fabs(p.shift_x - rx) < 1e-9 && std::fabs(p.shift_y - ry) < 1e-9;
-        if (integer) {
-            q.mx = (int)(-rx);
-            q.my = (int)(-ry);
-            q.ux = q.uy = 0.f;
-            q.spline = 0;
-        } else {
-            double fx = std::floor(-p.shift_x), fy = std::floor(-p.shift_y);
-            q.mx = (int)fx;
-            q.my = (int)fy;
-            q.ux = (float)(-p.shift_x - fx);
-            q.uy = (float)(-p.shift_y - fy);
-            q.spline = 1;
-            anySpline = true;
-        }
+        ImgParams q = make_img_params(h->cfg, p, anySpline);
         s.img[i] = q;
         if (s.imgPlane0) s.imgPlane0[i] = q.skip ? -1 : np;
         if (h->cfg.use_ctf)
@@ -509,7 +526,96 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
 }
 
 // K1a -> cuFFT -> K1b -> K2 (+K2e) for n images whose raw data sit at dRaw (device)
+// shift + pad (K1a) and the batched R2C of one chunk into dFft
+int pad_and_fft(rfb200_handle h, const float* dRaw, int n, bool anySpline) {
+    const Geometry& g = h->geo;
+    {
+        StageTimer t(h, Stage::PAD, h->compute);
+        if (anySpline) {
+            if (!h->dCoef) RF_CUDA(h, cudaMalloc(&h->dCoef, sizeof(float) * (size_t)h->chunkImages * g.N * g.N));
+            dim3 pg((g.N + 127) / 128, n);
+            k_bspline_prefilter<<<pg, 128, 0, h->compute>>>(dRaw, h->dCoef, h->dImg, g.N, 0);
+            k_bspline_prefilter<<<pg, 128, 0, h->compute>>>(dRaw, h->dCoef, h->dImg, g.N, 1);
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 2;
+        }
+        dim3 grid((g.N * g.N + 255) / 256, n);
+        k_pad_images<<<grid, 256, 0, h->compute>>>(dRaw, h->dCoef, h->dPad, h->dImg, g.N, g.P);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+    }
+    {
+        StageTimer t(h, Stage::FFT2D, h->compute);
+        cufftHandle plan;
+        int rc = get_plan2d(h, n, &plan);
+        if (rc) return rc;
+        RF_CUFFT(h, cufftExecR2C(plan, h->dPad, reinterpret_cast<cufftComplex*>(h->dFft)));
+    }
+    return RFB200_OK;
+}
+
+// --fast: K1a -> cuFFT R2C -> K1f (crop, re-centre, CTF, weights folded) -> K2f (nearest-pixel insertion)
+int process_chunk_fast(rfb200_handle h, const float* dRaw, const rfb200_particle* meta, int n) {
+    const FastGeo& fg = h->fgeo;
+    ParamSlot& s = h->slots[h->slotIdx];
+    h->slotIdx ^= 1;
+    if (s.used) RF_CUDA(h, cudaEventSynchronize(s.done));
+    bool anySpline = false;
+    int np = 0;
+    for (int i = 0; i < n; ++i) {
+        const rfb200_particle& p = meta[i];
+        ImgParams q = make_img_params(h->cfg, p, anySpline);
+        if (h->cfg.use_weights && (float)p.weight == 0.f) q.skip = 1;     // G:351-353 compares the float weight
+        s.img[i] = q;
+        if (h->cfg.use_ctf)
+            s.ctf[i] = host::make_ctf(p.kV, p.defocusU, p.defocusV, p.defocus_angle, p.Cs, p.Ca, p.espr, p.ispr, p.alpha, p.DeltaF,
+                                      p.DeltaR, p.Q0, p.K, p.envR0, p.envR1, p.envR2, p.phase_shift, p.vpp_radius);
+        if (q.skip) continue;
+        for (int sIdx = 0; sIdx < h->nSymTot; ++sIdx)
+            host::make_fast_space(fg, &h->sym[9 * sIdx], p.rot, p.tilt, p.psi, i, q.weight, s.fast[np++]);
+    }
+    int rc = fetch_params(h, h->dImg, s.img, sizeof(ImgParams) * n);
+    if (!rc && h->cfg.use_ctf) rc = fetch_params(h, h->dCtf, s.ctf, sizeof(CtfConsts) * n);
+    if (!rc && np) rc = fetch_params(h, h->dFastSpaces, s.fast, sizeof(FastSpace) * np);
+    if (rc) return rc;
+    s.used = true;
+    rc = pad_and_fft(h, dRaw, n, anySpline);
+    if (rc) return rc;
+    {
+        StageTimer t(h, Stage::SLICE, h->compute);
+        FastPrepArgs a{};
+        a.g = fg; a.fft = h->dFft; a.pix = h->dFastPix; a.ip = h->dImg; a.ctfs = h->dCtf;
+        a.useCtf = h->cfg.use_ctf; a.phaseFlipped = h->cfg.phase_flipped;
+        a.iTs = h->cfg.use_ctf ? 1.0 / h->cfg.sampling : 1.0;
+        a.minCtf = h->cfg.min_ctf;
+        a.maxRes2 = (float)(h->cfg.max_resolution * h->cfg.max_resolution);
+        dim3 grid((fg.sx * fg.sy + 255) / 256, n);
+        k_fast_prepare<<<grid, 256, 0, h->compute>>>(a);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+    }
+    if (np) {
+        StageTimer t(h, Stage::GATHER, h->compute);
+        for (int p0 = 0; p0 < np; p0 += 65535) {
+            const int cnt = std::min(65535, np - p0);
+            FastInsertArgs a{};
+            a.g = fg; a.spaces = h->dFastSpaces + p0; a.pix = h->dFastPix; a.V = h->dVb; a.W = h->dWb;
+            dim3 grid((fg.S + 1 + 31) / 32, (fg.S + 1 + 7) / 8, cnt);
+            k_fast_insert<<<grid, dim3(32, 8), 0, h->compute>>>(a);
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 1;
+            h->nGatherLaunches += 1;
+        }
+    }
+    RF_CUDA(h, cudaEventRecord(s.done, h->compute));
+    h->nImages += n;
+    h->nPlanes += np;
+    h->lastChunkImages = n;
+    return RFB200_OK;
+}
+
 int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* meta, int n) {
+    if (h->fast) return process_chunk_fast(h, dRaw, meta, n);
     const Geometry& g = h->geo;
     ParamSlot* slot = nullptr;
     int nPlanes = 0;
@@ -525,27 +631,8 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
         rc = launch_fused_fft(h, ra, ca, n);
         if (rc) return rc;
     } else {
-    {
-        StageTimer t(h, Stage::PAD, h->compute);
-        if (anySpline) {
-            if (!h->dCoef) RF_CUDA(h, cudaMalloc(&h->dCoef, sizeof(float) * (size_t)h->chunkImages * g.N * g.N));
-            dim3 pg((g.N + 127) / 128, n);
-            k_bspline_prefilter<<<pg, 128, 0, h->compute>>>(dRaw, h->dCoef, h->dImg, g.N, 0);
-            k_bspline_prefilter<<<pg, 128, 0, h->compute>>>(dRaw, h->dCoef, h->dImg, g.N, 1);
-            RF_CUDA(h, cudaGetLastError());
-            h->nKernelLaunches += 2;
-        }
-        dim3 grid((g.N * g.N + 255) / 256, n);
-        k_pad_images<<<grid, 256, 0, h->compute>>>(dRaw, h->dCoef, h->dPad, h->dImg, g.N, g.P);
-        RF_CUDA(h, cudaGetLastError());
-    }
-    {
-        StageTimer t(h, Stage::FFT2D, h->compute);
-        cufftHandle plan;
-        rc = get_plan2d(h, n, &plan);
-        if (rc) return rc;
-        RF_CUFFT(h, cufftExecR2C(plan, h->dPad, reinterpret_cast<cufftComplex*>(h->dFft)));
-    }
+    rc = pad_and_fft(h, dRaw, n, anySpline);
+    if (rc) return rc;
     {
         StageTimer t(h, Stage::SLICE, h->compute);
         Slice2Args a = make_slice_args(h);
@@ -574,7 +661,6 @@ int validate(const rfb200_config* c, std::string& why) {
     if (c->blob_order != 0 && c->blob_order != 2) { why = "blob order must be 0 or 2 (kaiser_Fourier_value, blobs.cpp:146)"; return RFB200_ERR_ARG; }
     if (c->n_sym < 0 || (c->n_sym > 0 && !c->sym_matrices)) { why = "symmetry matrices missing"; return RFB200_ERR_ARG; }
     if (c->n_iter_weight < 0) { why = "n_iter_weight must be >= 0"; return RFB200_ERR_ARG; }
-    if (c->fast) { why = "--fast is not implemented on this path yet"; return RFB200_ERR_UNSUPPORTED; }
     if (c->use_ctf && !(c->sampling > 0.0)) { why = "sampling must be positive with use_ctf"; return RFB200_ERR_ARG; }
     return RFB200_OK;
 }
@@ -596,10 +682,11 @@ void free_all(rfb200_handle h) {
     void* dev[] = {h->dBlobTable, h->dJmax, h->dEdge, h->dEdgeGroups, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
                    h->dPad, h->dCoef, h->dFft, h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dDampedMask, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
-                   h->dStickCounters, h->dTwiddle, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0};
+                   h->dStickCounters, h->dTwiddle, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0,
+                   h->dFastPix, h->dFastSpaces, h->dFastVh, h->dFastVc, h->dFastWh, h->dFastWc};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
-        void* hp[] = {s.img, s.ctf, s.planesD, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0};
+        void* hp[] = {s.img, s.ctf, s.planesD, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0, s.fast};
         for (void* p : hp) if (p) cudaFreeHost(p);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -613,6 +700,107 @@ void free_all(rfb200_handle h) {
     if (h->compute) cudaStreamDestroy(h->compute);
     if (h->copy) cudaStreamDestroy(h->copy);
     delete h;
+}
+
+// --fast handle: images are padded to N*pad_vol (both --fast programs do, G:229, 384-394), the accumulators are the
+// (S+1)^3 temporary volume and weights (G:838-843), finalisation buffers are allocated on first use
+int do_create_fast(rfb200_handle h) {
+    const rfb200_config& c = h->cfg;
+    h->fast = true;
+    h->fgeo = host::make_fast_geo(c.img_size, c.pad_vol, c.max_resolution);
+    const FastGeo& fg = h->fgeo;
+    if (fg.S < 2 || fg.S > fg.Pv) return fail(h, RFB200_ERR_ARG, "--fast: resolution sphere does not fit the padded volume");
+    h->tables = host::build_tables(c.img_size, c.pad_proj, c.pad_vol, c.blob_radius, c.blob_order, c.blob_alpha);
+    Geometry& g = h->geo;
+    g = Geometry{};
+    g.N = c.img_size; g.P = fg.Pv; g.Z = fg.Pv; g.X = fg.Pv / 2 + 1;
+    double meanF2 = 0;
+    std::vector<float> G = host::build_gridding_table(c.img_size, c.pad_proj, c.pad_vol, h->tables, 1, &meanF2);
+    std::vector<float> blobF(kBlobTable);
+    for (int i = 0; i < kBlobTable; ++i) blobF[i] = (float)h->tables.blobSqrt[i];
+    int maxBatch = c.max_batch > 0 ? c.max_batch : 1024;
+    h->chunkImages = std::min(maxBatch, 1024);
+    RF_CUDA(h, cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    RF_CUDA(h, cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        RF_CUDA(h, cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming));
+        RF_CUDA(h, cudaEventCreateWithFlags(&h->evRawFree[i], cudaEventDisableTiming));
+    }
+    RF_CUDA(h, cudaMalloc(&h->dBlobTable, sizeof(float) * kBlobTable));
+    RF_CUDA(h, cudaMemcpy(h->dBlobTable, blobF.data(), sizeof(float) * kBlobTable, cudaMemcpyHostToDevice));
+    RF_CUDA(h, cudaMalloc(&h->dSum, sizeof(double) * 1025));
+    RF_CUDA(h, cudaMallocHost(&h->hSum, sizeof(double)));
+    RF_CUDA(h, cudaEventCreateWithFlags(&h->evSum, cudaEventDisableTiming));
+    RF_CUDA(h, cudaEventCreate(&h->swStart));
+    RF_CUDA(h, cudaEventCreate(&h->swStop));
+    RF_CUDA(h, cudaMalloc(&h->dG, sizeof(float) * G.size()));
+    RF_CUDA(h, cudaMemcpy(h->dG, G.data(), sizeof(float) * G.size(), cudaMemcpyHostToDevice));
+    h->nBlocked = (int64_t)(fg.S + 1) * (fg.S + 1) * (fg.S + 1);
+    RF_CUDA(h, cudaMalloc(&h->dVb, sizeof(float2) * h->nBlocked));
+    RF_CUDA(h, cudaMalloc(&h->dWb, sizeof(float) * h->nBlocked));
+    RF_CUDA(h, cudaMemset(h->dVb, 0, sizeof(float2) * h->nBlocked));
+    RF_CUDA(h, cudaMemset(h->dWb, 0, sizeof(float) * h->nBlocked));
+    const size_t CH = h->chunkImages;
+    const size_t nRaw = CH * g.N * g.N, nPad = CH * (size_t)g.P * g.P, nFft = CH * (size_t)g.P * (g.P / 2 + 1);
+    for (int i = 0; i < 2; ++i) RF_CUDA(h, cudaMalloc(&h->dRaw[i], sizeof(float) * nRaw));
+    RF_CUDA(h, cudaMalloc(&h->dPad, sizeof(float) * nPad));
+    RF_CUDA(h, cudaMemset(h->dPad, 0, sizeof(float) * nPad));
+    RF_CUDA(h, cudaMalloc(&h->dFft, sizeof(float2) * nFft));
+    RF_CUDA(h, cudaMalloc(&h->dFastPix, sizeof(float4) * CH * fg.sx * fg.sy));
+    const size_t maxSpaces = CH * h->nSymTot;
+    RF_CUDA(h, cudaMalloc(&h->dFastSpaces, sizeof(FastSpace) * maxSpaces + 16));
+    RF_CUDA(h, cudaMalloc(&h->dImg, sizeof(ImgParams) * CH));
+    RF_CUDA(h, cudaMalloc(&h->dCtf, sizeof(CtfConsts) * CH));
+    for (auto& s : h->slots) {
+        RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
+        RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));
+        RF_CUDA(h, cudaMallocHost(&s.fast, sizeof(FastSpace) * maxSpaces + 16));
+        RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    RF_CUDA(h, cudaDeviceSynchronize());
+    return RFB200_OK;
+}
+
+// --fast: mirrorAndCrop -> applyBlob -> forceHermitianSymmetry + processWeights + convertToExpectedSpace (G:879-893),
+// then the common inverse FFT, crop and gridding correction
+int finalize_fast(rfb200_handle h, float* out) {
+    const FastGeo& fg = h->fgeo;
+    const Geometry& g = h->geo;
+    const rfb200_config& c = h->cfg;
+    const size_t nH = (size_t)(fg.S + 1) * (fg.S + 1) * (fg.X + 1);
+    const size_t nHalf = (size_t)g.Z * g.Z * g.X, nVol = (size_t)g.Z * g.Z * g.Z, nOut = (size_t)g.N * g.N * g.N;
+    if (!h->havePlan3d) {
+        RF_CUFFT(h, cufftPlan3d(&h->plan3d, g.Z, g.Z, g.Z, CUFFT_C2R));
+        RF_CUFFT(h, cufftSetStream(h->plan3d, h->compute));
+        h->havePlan3d = true;
+    }
+    if (!h->dFastVh) {
+        RF_CUDA(h, cudaMalloc(&h->dFastVh, sizeof(float2) * nH));
+        RF_CUDA(h, cudaMalloc(&h->dFastVc, sizeof(float2) * nH));
+        RF_CUDA(h, cudaMalloc(&h->dFastWh, sizeof(float) * nH));
+        RF_CUDA(h, cudaMalloc(&h->dFastWc, sizeof(float) * nH));
+    }
+    if (!h->dNorm) RF_CUDA(h, cudaMalloc(&h->dNorm, sizeof(float2) * nHalf));
+    if (!h->dVol) RF_CUDA(h, cudaMalloc(&h->dVol, sizeof(float) * nVol));
+    if (!h->dOut) RF_CUDA(h, cudaMalloc(&h->dOut, sizeof(float) * nOut));
+    {
+        StageTimer t(h, Stage::FINALIZE, h->compute);
+        const unsigned gh = (unsigned)((nH + 255) / 256);
+        k_fast_mirror_crop<<<gh, 256, 0, h->compute>>>(fg, h->dVb, h->dWb, h->dFastVh, h->dFastWh);
+        k_fast_blob<<<gh, 256, 0, h->compute>>>(fg, h->dBlobTable, (float)c.blob_radius, (float)h->tables.iDeltaSqrt, h->dFastVh, h->dFastWh,
+                                                 h->dFastVc, h->dFastWc);
+        const float corr = (float)(std::pow(c.pad_proj, 2.0) / (c.img_size * std::pow(c.pad_vol, 3.0)));   // G:753-754
+        k_fast_to_fourier<<<(unsigned)((nHalf + 255) / 256), 256, 0, h->compute>>>(fg, h->dFastVc, h->dFastWc, corr, h->dNorm);
+        RF_CUDA(h, cudaGetLastError());
+        RF_CUFFT(h, cufftExecC2R(h->plan3d, reinterpret_cast<cufftComplex*>(h->dNorm), h->dVol));
+        k_crop_correct<<<(unsigned)((nOut + 255) / 256), 256, 0, h->compute>>>(h->dVol, h->dG, h->dOut, g.N, g.Z);
+        RF_CUDA(h, cudaGetLastError());
+        RF_CUDA(h, cudaMemcpyAsync(out, h->dOut, sizeof(float) * nOut, cudaMemcpyDeviceToHost, h->compute));
+    }
+    h->nKernelLaunches += 4;
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    resolve_timings(h);
+    return RFB200_OK;
 }
 
 int do_create(rfb200_handle h) {
@@ -631,6 +819,7 @@ int do_create(rfb200_handle h) {
     h->sym.assign((size_t)9 * h->nSymTot, 0.0);
     h->sym[0] = h->sym[4] = h->sym[8] = 1.0;
     if (c.n_sym) std::memcpy(&h->sym[9], c.sym_matrices, sizeof(double) * 9 * c.n_sym);
+    if (c.fast) return do_create_fast(h);
     h->tables = host::build_tables(c.img_size, c.pad_proj, c.pad_vol, c.blob_radius, c.blob_order, c.blob_alpha);
     int P = (int)(c.img_size * c.pad_proj);
     int R = 0;
@@ -820,6 +1009,10 @@ int rfb200_get_info(rfb200_handle h, rfb200_info* info) {
     info->chunk_images = h->chunkImages;
     info->n_tiles_active = h->nUnits[0] + h->nUnits[1] + h->nUnits[2];   // work units (sticks) of the gather
     info->n_edge_items = h->nEdge;
+    if (h->fast) {          // --fast: Z = padded size, tile = S + 1 (edge of the temporary volume), no blocked layout
+        info->tiles_x = info->tiles_y = info->tiles_z = 1;
+        info->tile = h->fgeo.S + 1;
+    }
     return RFB200_OK;
 }
 
@@ -953,6 +1146,13 @@ int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_
 int rfb200_export_accumulators(rfb200_handle h, float* V, float* W) {
     if (!h || !V || !W) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->fast) {
+        // --fast: the (S+1)^3 temporary volume and weights [z][y][x], as the reference copies them back (copyTempVolumes)
+        RF_CUDA(h, cudaMemcpyAsync(V, h->dVb, sizeof(float2) * h->nBlocked, cudaMemcpyDeviceToHost, h->compute));
+        RF_CUDA(h, cudaMemcpyAsync(W, h->dWb, sizeof(float) * h->nBlocked, cudaMemcpyDeviceToHost, h->compute));
+        RF_CUDA(h, cudaStreamSynchronize(h->compute));
+        return RFB200_OK;
+    }
     const Geometry& g = h->geo;
     size_t total = (size_t)g.Z * g.Z * g.X;
     if (int rcf = flush_deficit(h)) return rcf;
@@ -974,6 +1174,7 @@ int rfb200_export_accumulators(rfb200_handle h, float* V, float* W) {
 int rfb200_finalize(rfb200_handle h, float* out) {
     if (!h || !out) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->fast) return finalize_fast(h, out);
     const Geometry& g = h->geo;
     const rfb200_config& c = h->cfg;
     size_t nHalf = (size_t)g.Z * g.Z * g.X, nVol = (size_t)g.Z * g.Z * g.Z, nOut = (size_t)g.N * g.N * g.N;
@@ -1150,6 +1351,7 @@ int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_strea
 
 int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radius) {
     if (!h) return RFB200_ERR_ARG;
+    if (h->fast) return fail(h, RFB200_ERR_UNSUPPORTED, "no slices in --fast mode");
     if (side) *side = h->geo.side;
     if (apron_radius) *apron_radius = h->geo.Rp;
     return RFB200_OK;
@@ -1157,6 +1359,7 @@ int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radiu
 
 int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
     if (!h || !out4 || idx < 0 || idx >= h->lastChunkImages) return RFB200_ERR_ARG;
+    if (h->fast) return fail(h, RFB200_ERR_UNSUPPORTED, "no slices in --fast mode");
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
     // format v2: plane A holds (re, im); the third channel is rebuilt from the validity table (multiplicity of the

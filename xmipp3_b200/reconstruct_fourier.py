@@ -32,6 +32,7 @@ class ProgRecFourier:
         self.Ts = 1.0
         self.device = 0
         self.bufferSize = 1024
+        self.fast = False      # --fast: nearest-pixel insertion + final blob convolution
         self.gpus = 1          # --gpus <n | "all">: one process per GPU, NCCL reduce onto rank 0
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -56,6 +57,8 @@ class ProgRecFourier:
             a += ["--useCTF", "--sampling", repr(float(self.Ts))]
         if self.phaseFlipped:
             a.append("--phaseFlipped")
+        if self.fast:
+            a.append("--fast")
         if self.gpus != 1:
             a += ["--gpus", str(self.gpus)]
         return a
@@ -78,7 +81,7 @@ class ProgRecFourier:
         r = Reconstructor(nx, padding=(self.padding_factor_proj, self.padding_factor_vol), max_resolution=self.maxResolution,
                           blob=self.blob, sym_matrices=sym, use_ctf=has_ctf, sampling=self.Ts, min_ctf=self.minCTF,
                           phase_flipped=self.phaseFlipped, use_weights=self.do_weights, n_iter_weight=self.NiterWeight,
-                          device=self.device, max_batch=self.bufferSize)
+                          fast=self.fast, device=self.device, max_batch=self.bufferSize)
         r.insert(imgs, p)
         vol = r.finalize()
         r.close()
