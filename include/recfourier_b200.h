@@ -189,6 +189,10 @@ int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_strea
 /* Full-plane slice of image `idx` of the last chunk: (2*Rp+1)^2 float4 (re, im, m, 0). */
 int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radius);
 int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4);
+/* cfg.fast only: the Pv x Pv x (Pv/2+1) transform (interleaved re, im; Pv = rfb200_info.Z) that finalisation hands to
+ * the inverse FFT, i.e. the temporary spaces after mirrorAndCrop, applyBlob, forceHermitianSymmetry, processWeights and
+ * convertToExpectedSpace (reconstruct_fourier_gpu.cpp:879-893). */
+int rfb200_debug_fast_fourier(rfb200_handle h, float* out);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,8 @@ def lib():
         L.orf_fast_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orf_fast_get_temp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orf_fast_finalize.argtypes = [C.c_void_p, C.c_void_p]
+        L.orf_fast_set_temp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_fast_fourier.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -177,6 +179,20 @@ class FastOracle:
         W = np.empty((n, n, n), dtype=np.float32)
         self._L.orf_fast_get_temp(self._h, _ptr(V), _ptr(W))
         return V, W
+
+    def set_temp_spaces(self, V, W):
+        """Replace the temporary spaces (e.g. by the ones a GPU run produced) before finalize()."""
+        n = self.S + 1
+        V = np.ascontiguousarray(V, dtype=np.complex64)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        assert V.shape == (n, n, n) and W.shape == (n, n, n)
+        self._L.orf_fast_set_temp(self._h, _ptr(V), _ptr(W))
+
+    def fourier(self):
+        """The Fourier volume handed to the inverse transform (after blob convolution, symmetrisation and weights)."""
+        out = np.empty((self.Pv, self.Pv, self.Pv // 2 + 1), dtype=np.complex128)
+        self._L.orf_fast_fourier(self._h, _ptr(out))
+        return out
 
     def finalize(self):
         out = np.empty((self.N,) * 3, dtype=np.float64)

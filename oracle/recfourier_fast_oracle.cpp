@@ -386,6 +386,12 @@ struct FastOracle {
     }
 
     void finalize(double* out) const {
+        std::vector<double> VF = fourier();
+        orf_finish_fourier(fin, VF.data(), out);                                             // G:894-931
+    }
+
+    // everything of finishComputations before the inverse transform: the Pv x Pv x (Pv/2+1) volume (interleaved re, im)
+    std::vector<double> fourier() const {
         const int X = S / 2;                                                                  // G:698
         std::vector<float> W = mirrorAndCrop(tempWeights, X, [](float v) { return v; });
         std::vector<cf> V = mirrorAndCrop(tempVolume, X, [](cf v) { return std::conj(v); });
@@ -422,7 +428,7 @@ struct FastOracle {
                     VF[2 * o] += V[z * oz + y * oy + x].real();
                     VF[2 * o + 1] += V[z * oz + y * oy + x].imag();
                 }
-        orf_finish_fourier(fin, VF.data(), out);                                             // G:894-931
+        return VF;
     }
 };
 
@@ -443,6 +449,15 @@ void orf_fast_get_temp(void* h, float* Vri, float* W) {
     FastOracle* o = static_cast<FastOracle*>(h);
     std::memcpy(Vri, o->tempVolume.data(), sizeof(cf) * o->tempVolume.size());
     std::memcpy(W, o->tempWeights.data(), sizeof(float) * o->tempWeights.size());
+}
+void orf_fast_set_temp(void* h, const float* Vri, const float* W) {
+    FastOracle* o = static_cast<FastOracle*>(h);
+    std::memcpy(o->tempVolume.data(), Vri, sizeof(cf) * o->tempVolume.size());
+    std::memcpy(o->tempWeights.data(), W, sizeof(float) * o->tempWeights.size());
+}
+void orf_fast_fourier(void* h, double* VFri) {
+    std::vector<double> v = static_cast<FastOracle*>(h)->fourier();
+    std::memcpy(VFri, v.data(), sizeof(double) * v.size());
 }
 void orf_fast_finalize(void* h, double* out) { static_cast<FastOracle*>(h)->finalize(out); }
 

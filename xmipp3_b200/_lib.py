@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
-    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count",
+    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count", "rfb200_debug_fast_fourier",
 ]
 
 
@@ -117,6 +117,7 @@ def load(build=True):
     L.rfb200_get_streams.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.rfb200_debug_slice_dims.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rfb200_debug_get_slice.argtypes = [H, C.c_int32, C.c_void_p]
+    L.rfb200_debug_fast_fourier.argtypes = [H, C.c_void_p]
     _lib = L
     return L
 
@@ -241,6 +242,12 @@ class Reconstructor:
         W = np.empty((Z, Z, X), dtype=np.float32)
         self._check(self._L.rfb200_export_accumulators(self._h, V.ctypes.data_as(C.c_void_p), W.ctypes.data_as(C.c_void_p)))
         return V, W
+
+    def fast_fourier(self):
+        """cfg.fast diagnostics: the transform handed to the inverse FFT."""
+        out = np.empty((self.Z, self.Z, self.Z // 2 + 1), dtype=np.complex64)
+        self._check(self._L.rfb200_debug_fast_fourier(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def finalize(self):
         out = np.empty((self.N,) * 3, dtype=np.float32)

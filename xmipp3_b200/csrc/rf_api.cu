@@ -763,7 +763,7 @@ int do_create_fast(rfb200_handle h) {
 
 // --fast: mirrorAndCrop -> applyBlob -> forceHermitianSymmetry + processWeights + convertToExpectedSpace (G:879-893),
 // then the common inverse FFT, crop and gridding correction
-int finalize_fast(rfb200_handle h, float* out) {
+int finalize_fast(rfb200_handle h, float* out, float* fourierOut = nullptr) {
     const FastGeo& fg = h->fgeo;
     const Geometry& g = h->geo;
     const rfb200_config& c = h->cfg;
@@ -792,6 +792,11 @@ int finalize_fast(rfb200_handle h, float* out) {
         const float corr = (float)(std::pow(c.pad_proj, 2.0) / (c.img_size * std::pow(c.pad_vol, 3.0)));   // G:753-754
         k_fast_to_fourier<<<(unsigned)((nHalf + 255) / 256), 256, 0, h->compute>>>(fg, h->dFastVc, h->dFastWc, corr, h->dNorm);
         RF_CUDA(h, cudaGetLastError());
+        if (fourierOut) {       // diagnostics: the transform handed to the inverse FFT
+            RF_CUDA(h, cudaMemcpyAsync(fourierOut, h->dNorm, sizeof(float2) * nHalf, cudaMemcpyDeviceToHost, h->compute));
+            RF_CUDA(h, cudaStreamSynchronize(h->compute));
+            return RFB200_OK;
+        }
         RF_CUFFT(h, cufftExecC2R(h->plan3d, reinterpret_cast<cufftComplex*>(h->dNorm), h->dVol));
         k_crop_correct<<<(unsigned)((nOut + 255) / 256), 256, 0, h->compute>>>(h->dVol, h->dG, h->dOut, g.N, g.Z);
         RF_CUDA(h, cudaGetLastError());
@@ -1347,6 +1352,14 @@ int rfb200_get_streams(rfb200_handle h, void** compute_stream, void** copy_strea
     if (compute_stream) *compute_stream = (void*)h->compute;
     if (copy_stream) *copy_stream = (void*)h->copy;
     return RFB200_OK;
+}
+
+int rfb200_debug_fast_fourier(rfb200_handle h, float* out) {
+    if (!h || !out) return RFB200_ERR_ARG;
+    if (!h->fast) return fail(h, RFB200_ERR_STATE, "handle was not created with cfg.fast");
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    std::vector<float> dummy(1);
+    return finalize_fast(h, dummy.data(), out);
 }
 
 int rfb200_debug_slice_dims(rfb200_handle h, int32_t* side, int32_t* apron_radius) {

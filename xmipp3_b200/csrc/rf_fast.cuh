@@ -380,7 +380,27 @@ __device__ __forceinline__ float2 d_fast_value(const FastGeo& g, const float2* _
     return make_float2(0.f, 0.f);
 }
 
-// convertToExpectedSpace G:664-681 as a gather: out is the Pv x Pv x (Pv/2+1) transform handed to the inverse FFT
+// convertToExpectedSpace G:664-681 as a gather: sum of the (up to four) half-space voxels that land on target (zt, yt, xt)
+__device__ __forceinline__ float2 d_fast_target(const FastGeo& g, const float2* __restrict__ Vc, const float* __restrict__ Wc, float corr,
+                                                int zt, int yt, int xt) {
+    const int Z = g.Pv, half = g.S / 2;
+    float2 acc = make_float2(0.f, 0.f);
+    // sources of target index c: s < half with Z - half + s == c, and s >= half with s - half == c (ascending s)
+    int ys[2], zs[2], ny = 0, nz = 0;
+    { int s = yt - (Z - half); if (s >= 0 && s < half) ys[ny++] = s; s = yt + half; if (s <= g.S) ys[ny++] = s; }
+    { int s = zt - (Z - half); if (s >= 0 && s < half) zs[nz++] = s; s = zt + half; if (s <= g.S) zs[nz++] = s; }
+    for (int a = 0; a < nz; ++a)
+        for (int b = 0; b < ny; ++b) {
+            const float2 v = d_fast_value(g, Vc, Wc, corr, zs[a], ys[b], xt);
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+    return acc;
+}
+
+// out is the Pv x Pv x (Pv/2+1) transform handed to the inverse FFT.  The x = 0 plane is Hermitian by construction
+// (forceHermitianSymmetry); the x = Pv/2 plane (reached when S == Pv) is not, and FFTW's c2r only sees its Hermitian part,
+// so that part is what is stored (cuFFT's result for a non-Hermitian plane is unspecified).
 __global__ void __launch_bounds__(256) k_fast_to_fourier(FastGeo g, const float2* __restrict__ Vc, const float* __restrict__ Wc, float corr,
                                                          float2* __restrict__ out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,16 +411,12 @@ __global__ void __launch_bounds__(256) k_fast_to_fourier(FastGeo g, const float2
     const int yt = (int)(t % Z), zt = (int)(t / Z);
     float2 acc = make_float2(0.f, 0.f);
     if (xt <= half) {
-        // sources of target index c: s < half with Z - half + s == c, and s >= half with s - half == c (ascending s)
-        int ys[2], zs[2], ny = 0, nz = 0;
-        { int s = yt - (Z - half); if (s >= 0 && s < half) ys[ny++] = s; s = yt + half; if (s <= g.S) ys[ny++] = s; }
-        { int s = zt - (Z - half); if (s >= 0 && s < half) zs[nz++] = s; s = zt + half; if (s <= g.S) zs[nz++] = s; }
-        for (int a = 0; a < nz; ++a)
-            for (int b = 0; b < ny; ++b) {
-                const float2 v = d_fast_value(g, Vc, Wc, corr, zs[a], ys[b], xt);
-                acc.x += v.x;
-                acc.y += v.y;
-            }
+        acc = d_fast_target(g, Vc, Wc, corr, zt, yt, xt);
+        if (2 * xt == Z) {
+            const float2 m = d_fast_target(g, Vc, Wc, corr, (Z - zt) % Z, (Z - yt) % Z, xt);
+            acc.x = 0.5f * (acc.x + m.x);
+            acc.y = 0.5f * (acc.y - m.y);
+        }
     }
     out[idx] = acc;
 }
