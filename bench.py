@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=1024, help="particles per preprocessing chunk inside the library (max_batch)")
+    ap.add_argument("--fast", action="store_true", help="measure the --fast arithmetic (nearest-pixel insertion + final blob "
+                    "convolution) instead of the exact blob insertion; not the headline configuration")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -256,7 +258,7 @@ def main():
         batches.append((img, make_particles(B, **cols)))
     torch.cuda.synchronize()
 
-    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=args.chunk)
+    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=args.chunk, fast=args.fast)
     if world > 1:
         ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -332,6 +334,17 @@ def main():
                "source": prof.get("source", "no ncu summary in profiles/gather_ncu.json"),
                "note": "ncu l1tex__data_pipe_lsu_wavefronts / smsp__issue_active of the same kernel (cold, serialised)"}
     stage_ms = {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}
+    if args.fast:
+        # k_fast_insert: one launch per chunk; per lattice column crossing the half-disc of a plane one 16-byte folded pixel
+        # is read and V (8 B) + W (4 B) are read-modified-written
+        S = 2 * box
+        hits = 0.5 * np.pi * (S / 2.0) ** 2
+        alg_bytes = imgs_per_launch * hits * (16 + 24)
+        roofline = {"kernel": "k_fast_insert", "bound": "hbm", "achieved": alg_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": alg_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": g_ms, "particles_per_launch": imgs_per_launch,
+                    "note": "scatter of one nearest pixel per lattice column and plane with FP32 atomics (L2 atomic throughput bound)"}
+        fp32 = l1_pipe = None
 
     # ---------------- end to end through the C ABI with pinned host buffers
     e2e = None
@@ -410,7 +423,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections with CTF, padding 2, C1, blob 1.9/0/15, max_resolution 0.5" % (box, box),
+            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections with CTF, padding 2, C1, blob 1.9/0/15, max_resolution 0.5%s" % (box, box, ", --fast arithmetic" if args.fast else ""),
                        "box": box, "padding": 2, "sym": "c1", "ctf": True, "particles_per_step_per_gpu": B,
                        "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
                        "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
