@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=1024, help="particles per preprocessing chunk inside the library (max_batch)")
+    ap.add_argument("--sym", default="c1", help="point group (e.g. d7 = BASELINE config 4: 14 insertions per image); "
+                    "not the headline configuration")
     ap.add_argument("--fast", action="store_true", help="measure the --fast arithmetic (nearest-pixel insertion + final blob "
                     "convolution) instead of the exact blob insertion; not the headline configuration")
     args = ap.parse_args()
@@ -258,7 +260,13 @@ def main():
         batches.append((img, make_particles(B, **cols)))
     torch.cuda.synchronize()
 
-    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=args.chunk, fast=args.fast)
+    sym_mats = None
+    n_ops = 1
+    if args.sym.lower() != "c1":
+        from xmipp3_b200 import geometry
+        sym_mats = geometry.point_group_matrices(args.sym)
+        n_ops = len(sym_mats) + 1
+    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=args.chunk, fast=args.fast, sym_matrices=sym_mats)
     if world > 1:
         ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -305,7 +313,7 @@ def main():
     g_ms = tm["gather_ms"] / g_launches
     imgs_per_launch = K * B / g_launches
     alg_bytes = imgs_per_launch * wm["k2_bytes_per_particle"] + wm["k2_bytes_per_launch_fixed"]
-    alg_flops = imgs_per_launch * wm["k2_flops_per_particle"]
+    alg_flops = imgs_per_launch * wm["k2_flops_per_particle"] * n_ops
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -423,8 +431,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections with CTF, padding 2, C1, blob 1.9/0/15, max_resolution 0.5%s" % (box, box, ", --fast arithmetic" if args.fast else ""),
-                       "box": box, "padding": 2, "sym": "c1", "ctf": True, "particles_per_step_per_gpu": B,
+            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections with CTF, padding 2, %s, blob 1.9/0/15, max_resolution 0.5%s" % (box, box, args.sym.upper(), ", --fast arithmetic" if args.fast else ""),
+                       "box": box, "padding": 2, "sym": args.sym.lower(), "insertions_per_particle": n_ops, "ctf": True, "particles_per_step_per_gpu": B,
                        "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
                        "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
                        "stage_ms_per_step": stage_ms},
