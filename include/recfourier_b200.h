@@ -194,6 +194,26 @@ int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4);
  * convertToExpectedSpace (reconstruct_fourier_gpu.cpp:879-893). */
 int rfb200_debug_fast_fourier(rfb200_handle h, float* out);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Central-slice projector: the producer of the particle sets this path consumes (xmipp_phantom_project,
+ * reconstruction/project.cpp:992).  Replaces FourierProjector (data/fourier_projection.h:91-175:
+ * FourierProjector(V, paddFactor, maxFreq, BSplineDegree), project(rot, tilt, psi, ctf), projection()) and its CUDA twin
+ * CudaFourierProjector (reconstruction_cuda/cuda_fourier_projection.h:183-216).
+ *   volume   N^3 float32 in HOST memory, [z][y][x], centred like setXmippOrigin (voxel N/2 is the origin)
+ *   degree   0 NEAREST, 1 LINEAR, 3 BSPLINE3 (xmipp_transformation)
+ *   angles   n x (rot, tilt, psi) in degrees
+ *   ctf      optional n x N x (N/2+1) float32 multipliers of the half-plane transform (the `ctf` image of project()), or NULL
+ *   images   n x N x N float32
+ * Same status codes as above; no CPU fallback. */
+typedef struct rfb200_projector_s* rfb200_projector;
+int rfb200_projector_create(const float* volume, int32_t N, double padding, double max_freq, int32_t degree, int32_t device,
+                            rfb200_projector* out);
+int rfb200_projector_project(rfb200_projector p, const double* angles, const float* ctf, int32_t n, float* images);
+/* same with `d_ctf` (or NULL) and `d_images` in DEVICE memory of the projector's device */
+int rfb200_projector_project_device(rfb200_projector p, const double* angles, const float* d_ctf, int32_t n, float* d_images);
+const char* rfb200_projector_last_error(rfb200_projector p);
+void rfb200_projector_destroy(rfb200_projector p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,10 @@ def lib():
         L.orf_fft2_r2c.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orf_fft1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orf_finish_fourier.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_projector_create.restype = C.c_void_p
+        L.orf_projector_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]
+        L.orf_projector_destroy.argtypes = [C.c_void_p]
+        L.orf_projector_project.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.orf_fast_create.restype = C.c_void_p
         L.orf_fast_create.argtypes = [C.POINTER(Config)]
         L.orf_fast_destroy.argtypes = [C.c_void_p]
@@ -140,6 +144,37 @@ def _make_config(img_size, padding, max_resolution, blob, sym_matrices, use_ctf,
     cfg.n_iter_weight = int(n_iter_weight)
     cfg.sym_matrices = sm.ctypes.data_as(C.POINTER(C.c_double)) if sm.size else None
     return cfg, sm
+
+
+class ProjectorOracle:
+    """CPU restatement of FourierProjector (data/fourier_projection.cpp): padded 3-D transform of a volume, central
+    slices by NEAREST (0) / LINEAR (1) / BSPLINE3 (3) interpolation, inverse 2-D transform."""
+
+    def __init__(self, volume, padding=2.0, max_freq=0.5, degree=3):
+        self._L = lib()
+        v = np.ascontiguousarray(volume, dtype=np.float32)
+        assert v.ndim == 3 and v.shape[0] == v.shape[1] == v.shape[2]
+        self.N = v.shape[0]
+        self._h = self._L.orf_projector_create(_ptr(v), self.N, float(padding), float(max_freq), int(degree))
+        if not self._h:
+            raise RuntimeError("orf_projector_create failed")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orf_projector_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def project(self, rot, tilt, psi, ctf=None):
+        out = np.empty((self.N, self.N), dtype=np.float64)
+        c = None
+        if ctf is not None:
+            c = np.ascontiguousarray(ctf, dtype=np.float64)
+            assert c.shape == (self.N, self.N // 2 + 1)
+        self._L.orf_projector_project(self._h, float(rot), float(tilt), float(psi), _ptr(c) if c is not None else None, _ptr(out))
+        return out
 
 
 class FastOracle:

@@ -41,6 +41,12 @@ void orf_finalize(void* h, double* out);
 /* tail of finishComputations on a given Z*Z*(Z/2+1) Fourier volume (interleaved re,im): c2r, CenterFFT, crop, correction */
 void orf_finish_fourier(void* h, const double* Vri, double* out);
 
+/* ---- FourierProjector (data/fourier_projection.cpp:91-333): degree 0 NEAREST, 1 LINEAR, 3 BSPLINE3;
+ * vol N^3 float [z][y][x] about the Xmipp origin; ctf N*(N/2+1) doubles or NULL; out N*N doubles */
+void* orf_projector_create(const float* vol, int N, double padding, double max_freq, int degree);
+void orf_projector_destroy(void* h);
+void orf_projector_project(void* h, double rot, double tilt, double psi, const double* ctf, double* out);
+
 /* ---- --fast (recfourier_fast_oracle.cpp): nearest-pixel insertion + final blob convolution, single precision,
  * restating ProgRecFourierGPU with useFast (reconstruction_adapt_cuda/reconstruct_fourier_gpu.cpp and the device
  * functions of reconstruction_cuda/cuda_gpu_reconstruct_fourier.cpp:391-503, 655-760). */

@@ -861,6 +861,195 @@ struct Oracle {
     }
 };
 
+
+// =============================================================================
+// FourierProjector (libraries/data/fourier_projection.cpp = "FP"): central-slice projector used by
+// xmipp_phantom_project (reconstruction/project.cpp:992) to make the particle sets this path consumes.
+//   produceSideInfo FP:265-308, produceSideInfoProjection FP:310-333, project FP:91-262
+// xmippCore pieces as used there (source absent, semantics from their call sites and headers): window() about the
+// Xmipp origin, completeFourierTransform (forward, 1/size), ShiftFFT (multiply by exp(-2 pi i k.shift/size)),
+// CenterFFT(forward) (cyclic shift by size/2), produceSplineCoefficients (bilib ChangeBasisVolume, cubic, mirror-off-
+// bounds: the same half-sample mirror FP:189-215 applies when it reads the coefficients), interpolatedElement3D
+// (trilinear, 0 outside), inverseFourierTransform (c2r, unnormalised).
+// =============================================================================
+struct ProjectorOracle {
+    int N, P, degree;            // volume size, padded size, 0 NEAREST / 1 LINEAR / 3 BSPLINE3
+    double maxFrequency;
+    int start, dim;              // logical index of coefficient 0 and edge length of the (windowed) coefficient cube
+    std::vector<cd> C;           // VfourierRealCoefs + i VfourierImagCoefs, [z][y][x]
+    std::vector<double> phA, phB;
+
+    static void prefilter_line(cd* c, int n, long stride) {
+        // cubic B-spline direct transform, mirror-off-bounds (half-sample symmetric) extension
+        if (n == 1) return;
+        const double z = std::sqrt(3.0) - 2.0, lambda = (1.0 - z) * (1.0 - 1.0 / z);
+        for (int k = 0; k < n; ++k) c[k * stride] *= lambda;
+        // causal initialisation: c+[0] = s[0] + z * sum_{m>=0} z^m s~[m], s~ the half-sample mirrored, 2n-periodic signal
+        cd sum = 0;
+        double zm = 1.0;
+        for (int m = 0; m < 64 * 1 + 2 * n && std::fabs(zm) > 1e-300; ++m) {
+            int q = m % (2 * n);
+            int idx = q < n ? q : 2 * n - 1 - q;
+            sum += zm * c[idx * stride];
+            zm *= z;
+            if (m >= 80 && m >= 2 * n) break;
+        }
+        c[0] = c[0] + z * sum;
+        for (int k = 1; k < n; ++k) c[k * stride] += z * c[(k - 1) * stride];
+        c[(n - 1) * stride] = (z / (z - 1.0)) * c[(n - 1) * stride];
+        for (int k = n - 2; k >= 0; --k) c[k * stride] = z * (c[(k + 1) * stride] - c[k * stride]);
+    }
+
+    ProjectorOracle(const float* vol, int N_, double padding, double maxFreq, int degree_)
+        : N(N_), P((int)(padding * N_)), degree(degree_), maxFrequency(maxFreq) {
+        const int hP = P / 2, firstN = -(N / 2);
+        std::vector<cd> V((size_t)P * P * P, cd(0, 0));
+        for (int k = 0; k < N; ++k)                                             // window FP:270-272
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j)
+                    V[((size_t)(k + firstN + hP) * P + (i + firstN + hP)) * P + (j + firstN + hP)] = vol[((size_t)k * N + i) * N + j];
+        Fft f(P);
+        std::vector<cd> a(P), b(P);
+        for (int z = 0; z < P; ++z)
+            for (int y = 0; y < P; ++y) f.run(&V[((size_t)z * P + y) * P], 1, -1, a.data(), b.data());
+        for (int z = 0; z < P; ++z)
+            for (int x = 0; x < P; ++x) f.run(&V[(size_t)z * P * P + x], P, -1, a.data(), b.data());
+        for (int y = 0; y < P; ++y)
+            for (int x = 0; x < P; ++x) f.run(&V[(size_t)y * P + x], (long)P * P, -1, a.data(), b.data());
+        // 1/size of the forward transform, ShiftFFT by FIRST_XMIPP_INDEX(P) = -P/2 (FP:278), K = P^3/N^2 (FP:283-285)
+        const double xx = -2.0 * kPi * (double)(-hP) / (double)P;
+        const double scale = 1.0 / ((double)N * (double)N);                    // (1/P^3) * K
+        std::vector<cd> ph(P);
+        for (int k = 0; k < P; ++k) ph[k] = cd(std::cos(k * xx), std::sin(k * xx));
+        std::vector<cd> Cfull((size_t)P * P * P);
+        for (int z = 0; z < P; ++z)
+            for (int y = 0; y < P; ++y)
+                for (int x = 0; x < P; ++x) {
+                    cd v = V[((size_t)z * P + y) * P + x] * ph[z] * ph[y] * ph[x] * scale;
+                    // CenterFFT(forward): element k moves to (k + P/2) mod P (FP:279)
+                    Cfull[((size_t)((z + hP) % P) * P + (y + hP) % P) * P + (x + hP) % P] = v;
+                }
+        V.clear();
+        V.shrink_to_fit();
+        start = -hP;
+        dim = P;
+        if (degree == 3) {                                                      // FP:288-308
+            for (int z = 0; z < P; ++z)
+                for (int y = 0; y < P; ++y) prefilter_line(&Cfull[((size_t)z * P + y) * P], P, 1);
+            for (int z = 0; z < P; ++z)
+                for (int x = 0; x < P; ++x) prefilter_line(&Cfull[(size_t)z * P * P + x], P, P);
+            for (int y = 0; y < P; ++y)
+                for (int x = 0; x < P; ++x) prefilter_line(&Cfull[(size_t)y * P + x], P, (long)P * P);
+            int idxMax = (int)(maxFrequency * P + 10);
+            idxMax = std::min(P - 1 - hP, idxMax);
+            int idxMin = std::max(-idxMax, -hP);
+            dim = idxMax - idxMin + 1;
+            start = idxMin;
+            C.resize((size_t)dim * dim * dim);
+            for (int z = 0; z < dim; ++z)
+                for (int y = 0; y < dim; ++y)
+                    for (int x = 0; x < dim; ++x)
+                        C[((size_t)z * dim + y) * dim + x] = Cfull[((size_t)(z + idxMin + hP) * P + (y + idxMin + hP)) * P + (x + idxMin + hP)];
+        } else {
+            C.swap(Cfull);
+        }
+        // produceSideInfoProjection FP:310-333
+        const int Xh = N / 2 + 1;
+        phA.resize((size_t)N * Xh);
+        phB.resize((size_t)N * Xh);
+        const double shift = (double)(N / 2);                                   // -FIRST_XMIPP_INDEX(N)
+        const double xxs = -2 * kPi * shift / N;
+        for (int i = 0; i < N; ++i) {
+            double phasey = (double)i * xxs;
+            for (int j = 0; j < Xh; ++j) {
+                double dotp = (double)j * xxs + phasey;
+                phB[(size_t)i * Xh + j] = std::sin(dotp);
+                phA[(size_t)i * Xh + j] = std::cos(dotp);
+            }
+        }
+    }
+
+    inline cd at(int k, int i, int j) const {      // logical indices; 0 outside
+        k -= start; i -= start; j -= start;
+        if (k < 0 || i < 0 || j < 0 || k >= dim || i >= dim || j >= dim) return cd(0, 0);
+        return C[((size_t)k * dim + i) * dim + j];
+    }
+    static inline double bspline03(double x) {
+        double a = std::fabs(x);
+        if (a < 1.0) return a * a * (a - 2.0) * 0.5 + 2.0 / 3.0;
+        if (a < 2.0) { a -= 2.0; return a * a * a / -6.0; }
+        return 0.0;
+    }
+
+    // FP:91-262; ctf: N x (N/2+1) or nullptr; out: N x N
+    void project(double rot, double tilt, double psi, const double* ctf, double* out) const {
+        const int Xh = N / 2 + 1;
+        M3 E = euler_matrix(rot, tilt, psi);
+        std::vector<cd> PF((size_t)N * Xh, cd(0, 0));
+        const double maxFreq2 = maxFrequency * maxFrequency;
+        for (int i = 0; i < N; ++i) {
+            double freqy = idx2digfreq(i, N), freqy2 = freqy * freqy;
+            double fYX = E.m[3] * freqy, fYY = E.m[4] * freqy, fYZ = E.m[5] * freqy;
+            for (int j = 0; j < Xh; ++j) {
+                double freqx = idx2digfreq(j, N);
+                if (freqy2 + freqx * freqx > maxFreq2) continue;
+                double fX = fYX + E.m[0] * freqx, fY = fYY + E.m[1] * freqx, fZ = fYZ + E.m[2] * freqx;
+                double c, d;
+                if (degree == 0) {
+                    cd v = at((int)std::round(fZ * P), (int)std::round(fY * P), (int)std::round(fX * P));   // outside: 0 (the reference reads out of bounds there)
+                    c = v.real(); d = v.imag();
+                } else if (degree == 1) {
+                    double z = fZ * P, y = fY * P, x = fX * P;
+                    int x0 = (int)std::floor(x), y0 = (int)std::floor(y), z0 = (int)std::floor(z);
+                    double fx = x - x0, fy = y - y0, fz = z - z0;
+                    cd d000 = at(z0, y0, x0), d001 = at(z0, y0, x0 + 1), d010 = at(z0, y0 + 1, x0), d011 = at(z0, y0 + 1, x0 + 1);
+                    cd d100 = at(z0 + 1, y0, x0), d101 = at(z0 + 1, y0, x0 + 1), d110 = at(z0 + 1, y0 + 1, x0), d111 = at(z0 + 1, y0 + 1, x0 + 1);
+                    auto lin = [](double a, cd l, cd h) { return l + (h - l) * a; };      // LIN_INTERP
+                    cd dx00 = lin(fx, d000, d001), dx01 = lin(fx, d100, d101), dx10 = lin(fx, d010, d011), dx11 = lin(fx, d110, d111);
+                    cd dxy0 = lin(fy, dx00, dx10), dxy1 = lin(fy, dx01, dx11);
+                    cd v = lin(fz, dxy0, dxy1);
+                    c = v.real(); d = v.imag();
+                } else {
+                    double z = fZ * P - start, y = fY * P - start, x = fX * P - start;
+                    int l1 = (int)std::ceil(x - 2), m1 = (int)std::ceil(y - 2), n1 = (int)std::ceil(z - 2);
+                    cd acc = 0;
+                    for (int nn = n1; nn <= n1 + 3; ++nn) {
+                        int en = nn < 0 ? -nn - 1 : (nn >= dim ? 2 * dim - nn - 1 : nn);
+                        cd yx = 0;
+                        for (int m = m1; m <= m1 + 3; ++m) {
+                            int em = m < 0 ? -m - 1 : (m >= dim ? 2 * dim - m - 1 : m);
+                            cd xs = 0;
+                            for (int l = l1; l <= l1 + 3; ++l) {
+                                int el = l < 0 ? -l - 1 : (l >= dim ? 2 * dim - l - 1 : l);
+                                xs += C[((size_t)en * dim + em) * dim + el] * bspline03(x - (double)l);
+                            }
+                            yx += xs * bspline03(y - (double)m);
+                        }
+                        acc += yx * bspline03(z - (double)nn);
+                    }
+                    c = acc.real(); d = acc.imag();
+                }
+                double a = phA[(size_t)i * Xh + j], b = phB[(size_t)i * Xh + j];
+                if (ctf) { a *= ctf[(size_t)i * Xh + j]; b *= ctf[(size_t)i * Xh + j]; }
+                PF[(size_t)i * Xh + j] = cd(a * c - b * d, a * d + b * c);
+            }
+        }
+        // inverseFourierTransform: complex along y for every stored column, then c2r along x (unnormalised)
+        Fft f(N);
+        std::vector<cd> ta(N), tb(N);
+        for (int j = 0; j < Xh; ++j) f.run(&PF[j], Xh, +1, ta.data(), tb.data());
+        for (int i = 0; i < N; ++i) {
+            const cd* row = &PF[(size_t)i * Xh];
+            ta[0] = cd(row[0].real(), 0);
+            for (int x = 1; x < Xh; ++x) ta[x] = row[x];
+            if (N % 2 == 0) ta[N / 2] = cd(row[N / 2].real(), 0);
+            for (int x = Xh; x < N; ++x) ta[x] = std::conj(row[N - x]);
+            f.rec(N, 1, ta.data(), tb.data(), +1);
+            for (int x = 0; x < N; ++x) out[(size_t)i * N + x] = tb[x].real();
+        }
+    }
+};
+
 }  // namespace
 
 // =============================================================================
@@ -890,6 +1079,14 @@ void orf_add_accumulators(void* h, const double* V, const double* W) {
     for (size_t k = 0; k < o->V.size(); ++k) { o->V[k] += cd(V[2 * k], V[2 * k + 1]); o->W[k] += W[k]; }
 }
 void orf_finalize(void* h, double* out) { static_cast<Oracle*>(h)->finalize(out); }
+void* orf_projector_create(const float* vol, int N, double padding, double max_freq, int degree) {
+    if (degree != 0 && degree != 1 && degree != 3) return nullptr;
+    try { return new ProjectorOracle(vol, N, padding, max_freq, degree); } catch (...) { return nullptr; }
+}
+void orf_projector_destroy(void* h) { delete static_cast<ProjectorOracle*>(h); }
+void orf_projector_project(void* h, double rot, double tilt, double psi, const double* ctf, double* out) {
+    static_cast<ProjectorOracle*>(h)->project(rot, tilt, psi, ctf, out);
+}
 void orf_finish_fourier(void* h, const double* Vri, double* out) {
     Oracle* o = static_cast<Oracle*>(h);
     std::vector<cd> v((size_t)o->Z * o->Z * o->X);

@@ -23,6 +23,8 @@ EXPORTED_SYMBOLS = [
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
     "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count", "rfb200_debug_fast_fourier",
+    "rfb200_projector_create", "rfb200_projector_project", "rfb200_projector_project_device", "rfb200_projector_last_error",
+    "rfb200_projector_destroy",
 ]
 
 
@@ -118,6 +120,13 @@ def load(build=True):
     L.rfb200_debug_slice_dims.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rfb200_debug_get_slice.argtypes = [H, C.c_int32, C.c_void_p]
     L.rfb200_debug_fast_fourier.argtypes = [H, C.c_void_p]
+    L.rfb200_projector_create.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.POINTER(H)]
+    L.rfb200_projector_project.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.rfb200_projector_project_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.rfb200_projector_last_error.argtypes = [H]
+    L.rfb200_projector_last_error.restype = C.c_char_p
+    L.rfb200_projector_destroy.argtypes = [H]
+    L.rfb200_projector_destroy.restype = None
     _lib = L
     return L
 
@@ -297,3 +306,61 @@ class Reconstructor:
         out = np.empty((side.value, side.value, 4), dtype=np.float32)
         self._check(self._L.rfb200_debug_get_slice(self._h, int(idx), out.ctypes.data_as(C.c_void_p)))
         return out, rp.value
+
+
+class FourierProjector:
+    """GPU central-slice projector with the interface of the reference's FourierProjector
+    (data/fourier_projection.h:91-175): FourierProjector(V, paddFactor, maxFreq, degree) then project(...)."""
+
+    NEAREST, LINEAR, BSPLINE3 = 0, 1, 3
+
+    def __init__(self, volume, padding=2.0, max_freq=0.5, degree=3, device=0):
+        self._L = load()
+        v = np.ascontiguousarray(volume, dtype=np.float32)
+        if v.ndim != 3 or not (v.shape[0] == v.shape[1] == v.shape[2]):
+            raise ValueError("volume must be a cube")
+        self.N = v.shape[0]
+        self._h = C.c_void_p()
+        rc = self._L.rfb200_projector_create(v.ctypes.data_as(C.c_void_p), self.N, float(padding), float(max_freq), int(degree),
+                                             int(device), C.byref(self._h))
+        if rc != OK:
+            self._h = None
+            raise RecFourierError(rc, "rfb200_projector_create failed" + (" (no CUDA device; there is no CPU fallback)" if rc == ERR_CUDA else ""))
+
+    def _check(self, rc):
+        if rc != OK:
+            raise RecFourierError(rc, (self._L.rfb200_projector_last_error(self._h) or b"").decode())
+
+    def project(self, rot, tilt, psi, ctf=None):
+        """rot, tilt, psi: scalars or arrays (degrees); ctf: optional [n, N, N/2+1] multipliers.  Returns [n, N, N] float32."""
+        ang = np.ascontiguousarray(np.stack(np.broadcast_arrays(np.atleast_1d(rot), np.atleast_1d(tilt), np.atleast_1d(psi)), axis=1),
+                                   dtype=np.float64)
+        n = ang.shape[0]
+        out = np.empty((n, self.N, self.N), dtype=np.float32)
+        c = None
+        if ctf is not None:
+            c = np.ascontiguousarray(ctf, dtype=np.float32)
+            assert c.shape == (n, self.N, self.N // 2 + 1), c.shape
+        self._check(self._L.rfb200_projector_project(self._h, ang.ctypes.data_as(C.c_void_p),
+                                                     c.ctypes.data_as(C.c_void_p) if c is not None else None, n,
+                                                     out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def project_device_ptr(self, rot, tilt, psi, d_images, d_ctf=None):
+        """Same, writing n*N*N float32 at the raw device address d_images (e.g. a torch tensor's data_ptr())."""
+        ang = np.ascontiguousarray(np.stack(np.broadcast_arrays(np.atleast_1d(rot), np.atleast_1d(tilt), np.atleast_1d(psi)), axis=1),
+                                   dtype=np.float64)
+        self._check(self._L.rfb200_projector_project_device(self._h, ang.ctypes.data_as(C.c_void_p),
+                                                            C.c_void_p(int(d_ctf)) if d_ctf else None, ang.shape[0],
+                                                            C.c_void_p(int(d_images))))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rfb200_projector_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1394,3 +1394,5 @@ int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
 }
 
 }  // extern "C"
+
+#include "rf_projector.cuh"
