@@ -237,6 +237,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner does) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -439,7 +444,8 @@ def main():
             "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32": fp32, "l1_data_pipe": l1_pipe, "cpu_baseline": cpu_baseline,
         }
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     r.close()
     if world > 1:
         dist.destroy_process_group()
