@@ -100,4 +100,6 @@ def test_gpu_project_then_reconstruct_round_trip():
     r.close()
     assert np.corrcoef(rec.ravel(), vol.ravel())[0, 1] >= 0.99
     f = synth.fsc(rec, vol)
-    assert np.nanmin(f[1:N // 2 - 2]) >= 0.95
+    # the Gaussian phantom has no power near Nyquist (the last shells compare interpolation error with nothing); measured:
+    # >= 0.9995 in the first 14 shells, 0.988 at shell 21, falling to 0.14 at the last one
+    assert np.nanmin(f[1:N // 2 - 10]) >= 0.97

@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(256) k_fast_insert(const __grid_constant__ Fas
     imgY = min(max(imgY, 0), g.sy - 1);
     const float4 p = __ldg(a.pix + (size_t)sp.img * g.sx * g.sy + (size_t)imgY * g.sx + imgX);
     const size_t i3 = ((size_t)z * (g.S + 1) + y) * (g.S + 1) + x;
-    atomicAdd(&a.V[i3].x, p.x);
-    atomicAdd(&a.V[i3].y, p.y);
-    atomicAdd(&a.W[i3], p.z);
+    // fire-and-forget reductions: one 8-byte vector RED for V, one for W (the reference issues three atomicAdd, D:499-502)
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(a.V + i3), "f"(p.x), "f"(p.y) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a.W + i3), "f"(p.z) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ K3f
