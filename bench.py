@@ -374,8 +374,9 @@ def main():
         r.weight_sum()
         if world > 1:
             r.reduce(0)          # warm-up of the communicator (connection set-up happens on the first collective)
+        vol_pinned = torch.empty((box, box, box), dtype=torch.float32, pin_memory=True) if rank == 0 else None
         if rank == 0:
-            r.finalize()         # creates the 3-D FFT plan and the finalisation buffers
+            r.finalize_into(vol_pinned.data_ptr())      # creates the 3-D FFT plan and the finalisation buffers
         r.reset()
         barrier()
         t0 = time.perf_counter()
@@ -402,7 +403,10 @@ def main():
             r.reduce(0)
             r.sync()
         t_red = time.perf_counter()
-        vol = r.finalize() if rank == 0 else None
+        vol = None
+        if rank == 0:           # the caller owns the output buffer (page-locked here, like the input batches)
+            r.finalize_into(vol_pinned.data_ptr())
+            vol = vol_pinned.numpy()
         if world > 1:
             dist.barrier()
         t1 = time.perf_counter()

@@ -263,6 +263,11 @@ class Reconstructor:
         self._check(self._L.rfb200_finalize(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def finalize_into(self, host_ptr):
+        """finalize() into caller-owned host memory of N^3 float32 (e.g. page-locked: the 4 N^3-byte read-back then runs
+        at full PCIe speed instead of being staged through a bounce buffer)."""
+        self._check(self._L.rfb200_finalize(self._h, C.c_void_p(int(host_ptr))))
+
     def timings(self):
         t = Timings()
         self._check(self._L.rfb200_get_timings(self._h, C.byref(t)))

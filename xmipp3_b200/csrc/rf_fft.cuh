@@ -121,7 +121,15 @@ __device__ __forceinline__ void fft_block<1024>(float2* buf, const float2* __res
     fft_stage<1024, 2, 512>(buf, W, t);
 }
 
-constexpr int kFftSeqs = 8;   // sequences transformed side by side by one CTA (P/8 threads each)
+#ifndef RF_FFT_SEQS
+#define RF_FFT_SEQS 8
+#endif
+constexpr int kFftSeqs = RF_FFT_SEQS;   // sequences transformed side by side by one CTA (P/8 threads each)
+#ifdef RF_FFT_COLS_MAXREG
+#define RF_FFT_COLS_BOUNDS(P) __maxnreg__(RF_FFT_COLS_MAXREG)
+#else
+#define RF_FFT_COLS_BOUNDS(P) __launch_bounds__(kFftSeqs* P / 8)
+#endif
 
 // ================================================================== K1r
 struct FftRowsArgs {
@@ -205,7 +213,7 @@ __device__ __forceinline__ bool d_pixel_valid(const int* __restrict__ jmax, cons
 
 // grid (ceil((R+1) / 8), nImg), block kFftSeqs * P/8 threads: 8 columns kx = 8*blockIdx.x .. +7
 template <int P>
-__global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
+__global__ void RF_FFT_COLS_BOUNDS(P) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float2* W = reinterpret_cast<float2*>(smemRaw);
     float2* bufs = W + P;
