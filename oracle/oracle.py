@@ -92,8 +92,16 @@ def lib():
         L.orf_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orf_apply_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         L.orf_ctf_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orf_bspline_coeffs_2d.argtypes = [C.c_void_p, C.c_int]
+        L.orf_bspline_interp_2d.restype = C.c_double
+        L.orf_bspline_interp_2d.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.orf_ctf_value.restype = C.c_double
         L.orf_ctf_value.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orf_ctf_argument.restype = C.c_double
+        L.orf_ctf_argument.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orf_ctf_K1.restype = C.c_double
+        L.orf_ctf_K1.argtypes = [C.c_void_p]
+        L.orf_ctf_grid.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.orf_euler.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.orf_idx2digfreq.restype = C.c_double
         L.orf_idx2digfreq.argtypes = [C.c_int, C.c_int]
@@ -327,6 +335,31 @@ class Oracle:
 def ctf_value(particle, X, Y):
     particle = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
     return lib().orf_ctf_value(_ptr(particle), float(X), float(Y))
+
+
+def bspline_coeffs_2d(a):
+    c = np.array(a, dtype=np.float64, order="C")
+    assert c.ndim == 2 and c.shape[0] == c.shape[1]
+    lib().orf_bspline_coeffs_2d(_ptr(c), c.shape[0])
+    return c
+
+
+def bspline_interp_2d(c, x, y):
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    return lib().orf_bspline_interp_2d(_ptr(c), c.shape[0], float(x), float(y))
+
+
+def ctf_grid(particle, n, Tm, what="value"):
+    """CTF values ("value") or sine arguments ("argument") on the n x n FFT grid at sampling Tm."""
+    particle = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+    out = np.empty((n, n))
+    lib().orf_ctf_grid(_ptr(particle), int(n), float(Tm), 1 if what == "argument" else 0, _ptr(out))
+    return out
+
+
+def ctf_K1(particle):
+    particle = np.ascontiguousarray(particle, dtype=PARTICLE_DTYPE).reshape(1)
+    return lib().orf_ctf_K1(_ptr(particle))
 
 
 def euler(rot, tilt, psi):

@@ -62,7 +62,12 @@ void orf_tables(void* h, double* blobTableSqrt, double* fourierBlobTable, double
 void orf_preprocess(void* h, const float* img, const orf_particle* p, double* F, double* Ainv);
 void orf_apply_shift(void* h, const float* img, double sx, double sy, double* out);
 void orf_ctf_weights(void* h, const orf_particle* p, int i, int j, double* wCTF, double* wMod);
+void orf_bspline_coeffs_2d(double* a, int n);                        /* produceSplineCoefficients(BSPLINE3), in place */
+double orf_bspline_interp_2d(const double* c, int n, double x, double y);   /* interpolatedElementBSpline2D, physical coords */
 double orf_ctf_value(const orf_particle* p, double X, double Y);
+double orf_ctf_argument(const orf_particle* p, double X, double Y);   /* getValueArgument */
+double orf_ctf_K1(const orf_particle* p);                            /* pi * lambda (produceSideInfo) */
+void orf_ctf_grid(const orf_particle* p, int n, double Tm, int what, double* out);   /* n x n values (0) / arguments (1) */
 void orf_euler(double rot, double tilt, double psi, double* m9);
 double orf_idx2digfreq(int idx, int size);
 double orf_kaiser_value(double r, double a, double alpha, int m);

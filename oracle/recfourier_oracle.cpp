@@ -274,6 +274,18 @@ struct Ctf {
         defocus_average = -(p.defocusU + p.defocusV) * 0.5;
         defocus_deviation = -(p.defocusU - p.defocusV) * 0.5;
     }
+    // getValueArgument() after precomputeValues(X,Y) (ctf.h: the phase of the CTF sine)
+    double argument(double X, double Y) const {
+        double ang = std::atan2(Y, X);
+        double u2 = X * X + Y * Y, u4 = u2 * u2;
+        double deltaf;
+        if (std::fabs(X) < kEqualAccuracy && std::fabs(Y) < kEqualAccuracy) deltaf = 0;
+        else deltaf = defocus_average + defocus_deviation * std::cos(2 * (ang - rad_azimuth));
+        double VPP = 0.0;
+        if (std::round(VPP_radius * 1000) != 0)
+            VPP = -phase_shift * (1 - std::exp(-u2 / (2 * VPP_radius * VPP_radius)));
+        return VPP + K1 * deltaf * u2 + K2 * u4;
+    }
     // getValuePureNoKAt() after precomputeValues(X,Y): K * getValuePureAt()
     double value(double X, double Y) const {
         double ang = std::atan2(Y, X);
@@ -387,39 +399,48 @@ struct Oracle {
         Ainv = transpose(A);                                          // :412
     }
 
-    // cubic B-spline helpers for fractional shifts (xmippCore applyGeometry, BSPLINE3, wrap)
+    // cubic B-spline helpers for fractional shifts (xmippCore applyGeometry with BSPLINE3 and wrap).  Conventions pinned by
+    // the reference's known answer TransformationTest.rotate (test_transformation_main.cpp:76-95, reproduced to 1e-7 in
+    // tests/test_oracle_kat.py): produceSplineCoefficients = bilib direct transform with MIRROR-OFF-BOUNDS (half-sample
+    // symmetric) extension, interpolatedElementBSpline2D reflects out-of-range neighbours (l < 0 -> -l-1,
+    // l >= n -> 2n-l-1), and applyGeometry wraps the source COORDINATE into [-0.5, n-0.5) (realWRAP) before interpolating.
     static void bspline_prefilter_1d(double* c, int n, long stride) {
-        // Unser's causal/anticausal recursive filter, pole z1 = sqrt(3)-2, mirror boundaries
         const double z1 = std::sqrt(3.0) - 2.0, lambda = (1.0 - z1) * (1.0 - 1.0 / z1);
         if (n == 1) return;
         for (int k = 0; k < n; ++k) c[k * stride] *= lambda;
-        // causal init (mirror, full sum with tolerance)
-        double tol = 2.220446049250313e-16;   // DBL_EPSILON, as xmippCore's produceSplineCoefficients
-        int horizon = (int)std::ceil(std::log(tol) / std::log(std::fabs(z1)));
-        double sum;
-        if (horizon < n) {
-            double zn = z1;
-            sum = c[0];
-            for (int k = 1; k < horizon; ++k) { sum += zn * c[k * stride]; zn *= z1; }
-        } else {
-            double zn = z1, iz = 1.0 / z1, z2n = std::pow(z1, (double)(n - 1));
-            sum = c[0] + z2n * c[(n - 1) * stride];
-            z2n *= z2n * iz;
-            for (int k = 1; k <= n - 2; ++k) { sum += (zn + z2n) * c[k * stride]; zn *= z1; z2n *= iz; }
-            sum /= (1.0 - zn * zn);
+        // causal initialisation: c+[0] = s[0] + z1 * sum_{m>=0} z1^m s~[m], s~ the half-sample mirrored (2n-periodic) signal
+        double sum = 0, zm = 1.0;
+        const int horizon = std::max(80, 2 * n);
+        for (int m = 0; m < horizon; ++m) {
+            int q = m % (2 * n);
+            int idx = q < n ? q : 2 * n - 1 - q;
+            sum += zm * c[idx * stride];
+            zm *= z1;
+            if (m >= 80) break;
         }
-        c[0] = sum;
+        c[0] = c[0] + z1 * sum;
         for (int k = 1; k < n; ++k) c[k * stride] += z1 * c[(k - 1) * stride];
-        c[(n - 1) * stride] = (z1 / (z1 * z1 - 1.0)) * (z1 * c[(n - 2) * stride] + c[(n - 1) * stride]);
+        c[(n - 1) * stride] = (z1 / (z1 - 1.0)) * c[(n - 1) * stride];
         for (int k = n - 2; k >= 0; --k) c[k * stride] = z1 * (c[(k + 1) * stride] - c[k * stride]);
     }
-    static inline void bspline3_weights(double t, double w[4]) {
-        // t in [0,1): weights for samples floor-1 .. floor+2
-        double t2 = t * t, t3 = t2 * t;
-        w[0] = (1.0 - 3.0 * t + 3.0 * t2 - t3) / 6.0;
-        w[1] = (4.0 - 6.0 * t2 + 3.0 * t3) / 6.0;
-        w[2] = (1.0 + 3.0 * t + 3.0 * t2 - 3.0 * t3) / 6.0;
-        w[3] = t3 / 6.0;
+    static inline int reflect(int l, int n) { return l < 0 ? -l - 1 : (l >= n ? 2 * n - l - 1 : l); }
+    // interpolatedElementBSpline2D at physical (x, y) of an n x n coefficient array
+    static double bspline_interp_2d(const double* c, int n, double x, double y) {
+        int l1 = (int)std::ceil(x - 2), m1 = (int)std::ceil(y - 2);
+        double columns = 0;
+        for (int m = m1; m <= m1 + 3; ++m) {
+            const double* row = c + (size_t)reflect(m, n) * n;
+            double rows = 0;
+            for (int l = l1; l <= l1 + 3; ++l) rows += row[reflect(l, n)] * ProjectorBspline03(x - (double)l);
+            columns += rows * ProjectorBspline03(y - (double)m);
+        }
+        return columns;
+    }
+    static inline double ProjectorBspline03(double x) {      // BSPLINE03
+        double a = std::fabs(x);
+        if (a < 1.0) return a * a * (a - 2.0) * 0.5 + 2.0 / 3.0;
+        if (a < 2.0) { a -= 2.0; return a * a * a / -6.0; }
+        return 0.0;
     }
     void apply_shift(const float* img, double sx, double sy, std::vector<double>& out) const {
         double rx = std::round(sx), ry = std::round(sy);
@@ -431,30 +452,18 @@ struct Oracle {
                     out[(size_t)i * N + j] = img[(size_t)wrap(i - isy, N) * N + wrap(j - isx, N)];
             return;
         }
-        // out(x) = in(x - shift), cubic B-spline interpolation with wrap
+        // out(x) = in(x - shift): coefficients, then per pixel the wrapped source coordinate and the reflected neighbours
         std::vector<double> c((size_t)N * N);
         for (size_t k = 0; k < c.size(); ++k) c[k] = img[k];
         for (int i = 0; i < N; ++i) bspline_prefilter_1d(&c[(size_t)i * N], N, 1);
         for (int j = 0; j < N; ++j) bspline_prefilter_1d(&c[j], N, N);
+        auto wrapc = [&](double v) {       // realWRAP(v, -0.5, N - 0.5) applied when v leaves [0, N-1] (applyGeometry)
+            if (v < -kEqualAccuracy || v > (N - 1) + kEqualAccuracy) v -= std::floor((v + 0.5) / N) * N;
+            return v;
+        };
         for (int i = 0; i < N; ++i) {
-            double y = i - sy;
-            int fy = (int)std::floor(y);
-            double wy[4];
-            bspline3_weights(y - fy, wy);
-            for (int j = 0; j < N; ++j) {
-                double x = j - sx;
-                int fx = (int)std::floor(x);
-                double wx[4];
-                bspline3_weights(x - fx, wx);
-                double acc = 0;
-                for (int a = 0; a < 4; ++a) {
-                    const double* row = &c[(size_t)wrap(fy - 1 + a, N) * N];
-                    double r = 0;
-                    for (int b = 0; b < 4; ++b) r += wx[b] * row[wrap(fx - 1 + b, N)];
-                    acc += wy[a] * r;
-                }
-                out[(size_t)i * N + j] = acc;
-            }
+            const double y = wrapc(i - sy);
+            for (int j = 0; j < N; ++j) out[(size_t)i * N + j] = bspline_interp_2d(c.data(), N, wrapc(j - sx), y);
         }
     }
 
@@ -1120,7 +1129,28 @@ void orf_ctf_weights(void* h, const orf_particle* p, int i, int j, double* wCTF,
     Ctf c(*p);
     o->ctf_weights(c, i, j, idx2digfreq(j, o->P), idx2digfreq(i, o->P), *wCTF, *wMod);
 }
+// spline primitives for the known-answer test: in-place coefficients of an n x n array, interpolation at physical (x, y)
+void orf_bspline_coeffs_2d(double* a, int n) {
+    for (int i = 0; i < n; ++i) Oracle::bspline_prefilter_1d(a + (size_t)i * n, n, 1);
+    for (int j = 0; j < n; ++j) Oracle::bspline_prefilter_1d(a + j, n, n);
+}
+double orf_bspline_interp_2d(const double* c, int n, double x, double y) { return Oracle::bspline_interp_2d(c, n, x, y); }
 double orf_ctf_value(const orf_particle* p, double X, double Y) { Ctf c(*p); return c.value(X, Y); }
+double orf_ctf_argument(const orf_particle* p, double X, double Y) { Ctf c(*p); return c.argument(X, Y); }
+double orf_ctf_K1(const orf_particle* p) { Ctf c(*p); return c.K1; }
+// values (what = 0) or arguments (what = 1) on the n x n FFT grid of digital frequencies scaled by 1/Tm: the loop of
+// errorBetween2CTFs / errorMaxFreqCTFs2D (data/ctf.cpp:150-165, 262-275)
+void orf_ctf_grid(const orf_particle* p, int n, double Tm, int what, double* out) {
+    Ctf c(*p);
+    const double iTm = 1.0 / Tm;
+    for (int i = 0; i < n; ++i) {
+        double fy = idx2digfreq(i, n) * iTm;
+        for (int j = 0; j < n; ++j) {
+            double fx = idx2digfreq(j, n) * iTm;
+            out[(size_t)i * n + j] = what ? c.argument(fx, fy) : c.value(fx, fy);
+        }
+    }
+}
 
 // --- known-answer-test entry points ---
 void orf_euler(double rot, double tilt, double psi, double* m9) { M3 a = euler_matrix(rot, tilt, psi); std::memcpy(m9, a.m, sizeof(a.m)); }

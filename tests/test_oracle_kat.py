@@ -193,3 +193,102 @@ def test_oracle_multithread_same_scheme(oracle_mod):
     W1 = o1.accumulators()[1]
     W2 = o2.accumulators()[1]
     assert np.linalg.norm(W1 - W2) / np.linalg.norm(W1) < 5e-2
+
+
+# ---- CTF: the reference's own known answers (test_ctf_main.cpp) over data/ctf.cpp:107-300, restated here on top of the
+# oracle's CTF value / argument (the functions the reconstruction path evaluates per pixel, RF.cpp:600-606)
+def _ctf_particle(O, md):
+    return O.make_particles(1, **{k: v for k, v in md.items() if k != "sampling"})
+
+
+def test_ctf_known_answer_error_between_two_ctfs(oracle_mod):
+    O = oracle_mod
+    k = GOLD["ctf"]["errorBetween2CTFs"]
+    Tm, X = k["md1"]["sampling"], k["Xdim"]
+    c1 = O.ctf_grid(_ctf_particle(O, k["md1"]), X, Tm)          # getValuePureWithoutDampingAt: no envelope columns, K = 1
+    c2 = O.ctf_grid(_ctf_particle(O, k["md2"]), X, Tm)
+    f = np.fft.fftfreq(X) / Tm
+    f[X // 2] = 0.5 / Tm                                        # FFT_IDX2DIGFREQ(n/2) = +0.5
+    mod = np.hypot(f[None, :], f[:, None])
+    keep = ~((mod < k["minFreq"] / Tm) | (mod > k["maxFreq"] / Tm))     # ctf.cpp:157-158
+    err = np.abs(c2 - c1)[keep].sum()
+    assert np.float32(err) == pytest.approx(np.float32(k["expected"]), rel=5e-7)     # EXPECT_FLOAT_EQ
+
+
+def test_ctf_known_answer_max_freq(oracle_mod):
+    O = oracle_mod
+    k = GOLD["ctf"]["errorMaxFreqCTFs"]
+    md = k["md"]
+    K1 = O.ctf_K1(_ctf_particle(O, md))
+    res = 1.0 / np.sqrt(k["phaseRad"] / (K1 * abs(md["defocusU"] - md["defocusV"])))      # ctf.cpp:210
+    assert np.float32(res) == pytest.approx(np.float32(k["expected"]), rel=5e-7)
+
+
+def test_ctf_known_answer_max_freq_2d(oracle_mod):
+    O = oracle_mod
+    k = GOLD["ctf"]["errorMaxFreqCTFs2D"]
+    Tm, X = k["md1"]["sampling"], k["Xdim"]
+    a = O.ctf_grid(_ctf_particle(O, k["md1"]), X, Tm, "argument")
+    b = O.ctf_grid(_ctf_particle(O, k["md2"]), X, Tm, "argument")
+    counter = int((np.abs(b - a) < k["phaseRad"]).sum())                 # ctf.cpp:272-275
+    total = np.pi * X * X / 4.0
+    max_freq = 1.0 / (2.0 * Tm)
+    res_1 = max_freq if counter > total else counter * max_freq / total  # ctf.cpp:294-299
+    assert 1.0 / res_1 == pytest.approx(k["expected"], abs=k["tolerance"])
+
+
+# ---- cubic B-spline interpolation (readApplyGeo's fractional shifts): the reference's known answer for rotate()
+def test_bspline_rotate_known_answer(oracle_mod):
+    """applyGeometry restated around the oracle's spline primitives: Ainv = inverse of rotation2DMatrix(ang) =
+    [[cos, -sin], [sin, cos]], output pixel (i, j) looks up (xp, yp) = Ainv (j - cen, i - cen), skipped when it leaves
+    [-cen, n - cen - 1] (DONT_WRAP), interpolated at physical (xp + cen, yp + cen)."""
+    O = oracle_mod
+    k = GOLD["bspline_rotate"]
+    a = np.array(k["input"], dtype=np.float64)
+    n = a.shape[0]
+    c = O.bspline_coeffs_2d(a)
+    ang = np.radians(k["angle"])
+    cs, sn = np.cos(ang), np.sin(ang)
+    cen = n // 2
+    out = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            x, y = j - cen, i - cen
+            xp, yp = x * cs - y * sn, x * sn + y * cs
+            if min(xp, yp) < -cen - 1e-6 or max(xp, yp) > n - cen - 1 + 1e-6:
+                continue
+            out[i, j] = O.bspline_interp_2d(c, xp + cen, yp + cen)
+    assert np.abs(out - np.array(k["output"])).max() <= k["tolerance"]
+
+
+def test_shift_wraps_like_translate_known_answer(oracle_mod):
+    """translate(BSPLINE3, ..., (0, 1, 0)) with wrap moves row i to row wrap(i + 1); a fractional shift of a constant image
+    leaves it constant (the half-sample mirror keeps constants), and integer and 'almost integer' shifts agree."""
+    O = oracle_mod
+    o = O.Oracle(8)
+    rng = np.random.default_rng(0)
+    img = rng.standard_normal((8, 8)).astype(np.float32)
+    out = o.apply_shift(img, 0.0, GOLD["translate_wrap"]["shift_y"])
+    assert np.array_equal(out, np.roll(img, 1, axis=0).astype(np.float64))
+    near = o.apply_shift(img, 1e-7, 1.0 + 1e-7)                    # goes through the spline path
+    assert np.abs(near - out).max() <= 1e-5
+    const = o.apply_shift(np.full((8, 8), 2.5, np.float32), 0.37, -1.62)
+    assert np.abs(const - 2.5).max() <= 1e-12
+
+
+def test_euler_elements_known_answer(oracle_mod):
+    k = GOLD["euler_elements"]
+    step = k["step"]
+    for z in range(12):
+        for y in range(12):
+            for x in range(12):
+                rot, tilt, psi = np.radians([x * step, y * step, z * step])
+                m = oracle_mod.euler(x * step, y * step, z * step)
+                want = {(0, 0): np.cos(psi) * np.cos(tilt) * np.cos(rot) - np.sin(psi) * np.sin(rot),
+                        (0, 1): np.cos(psi) * np.cos(tilt) * np.sin(rot) + np.sin(psi) * np.cos(rot),
+                        (0, 2): -np.cos(psi) * np.sin(tilt),
+                        (1, 1): -np.sin(psi) * np.cos(tilt) * np.sin(rot) + np.cos(psi) * np.cos(rot),
+                        (1, 2): np.sin(psi) * np.sin(tilt),
+                        (2, 2): np.cos(tilt)}
+                for (a, b), v in want.items():
+                    assert abs(m[a, b] - v) <= k["tolerance"]

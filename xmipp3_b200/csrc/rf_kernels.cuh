@@ -39,37 +39,30 @@ __device__ __forceinline__ bool d_main_owns(const Geometry& geo, int ux, int uy)
 }
 
 // ================================================================== K1a
-// Cubic B-spline prefilter (Unser's recursive filter, pole sqrt(3)-2, mirror boundaries) for the images
-// whose shift is fractional: xmippCore's readApplyGeo interpolates with BSPLINE3.
-// One thread filters one line; `stride` selects rows (1) or columns (N).  Recursion state in double.
+// Cubic B-spline coefficients for the images whose shift is fractional: xmippCore's readApplyGeo interpolates with
+// BSPLINE3.  produceSplineCoefficients = bilib direct transform with the MIRROR-OFF-BOUNDS (half-sample
+// symmetric) extension; convention pinned by the reference's rotate() known answer (test_transformation_main.cpp:76-95,
+// tests/test_oracle_kat.py).  One thread filters one line; `stride` selects rows (1) or columns (N).  Recursion in double.
 __device__ __forceinline__ void d_bspline_line(float* c, int n, long stride) {
     if (n == 1) return;
     const double z1 = -0.26794919243112270647, lambda = 6.0;   // sqrt(3)-2, (1-z1)(1-1/z1)
-    const int horizon = 28;                                     // ceil(log(DBL_EPSILON)/log|z1|)
-    double sum;
-    if (horizon < n) {
-        double zn = z1;
-        sum = lambda * c[0];
-        for (int k = 1; k < horizon; ++k) { sum += zn * lambda * c[k * stride]; zn *= z1; }
-    } else {
-        double zn = z1, iz = 1.0 / z1, z2n = pow(z1, (double)(n - 1));
-        sum = lambda * c[0] + z2n * lambda * c[(n - 1) * stride];
-        z2n *= z2n * iz;
-        for (int k = 1; k <= n - 2; ++k) { sum += (zn + z2n) * lambda * c[k * stride]; zn *= z1; z2n *= iz; }
-        sum /= (1.0 - zn * zn);
+    // causal initialisation: c+[0] = s[0] + z1 * sum_{m>=0} z1^m s~[m] over the mirrored, 2n-periodic signal (z1^80 ~ 1e-46)
+    double sum = 0.0, zm = 1.0;
+    for (int m = 0; m <= 80; ++m) {
+        const int q = m % (2 * n);
+        const int idx = q < n ? q : 2 * n - 1 - q;
+        sum += zm * lambda * (double)c[idx * stride];
+        zm *= z1;
     }
     // causal pass; the running value is kept in double, the line holds float
-    double prev = sum;
+    double prev = lambda * (double)c[0] + z1 * sum;
     c[0] = (float)prev;
-    double last2 = prev;
     for (int k = 1; k < n; ++k) {
-        double v = lambda * c[k * stride] + z1 * prev;
-        last2 = prev;
-        prev = v;
-        c[k * stride] = (float)v;
+        prev = lambda * (double)c[k * stride] + z1 * prev;
+        c[k * stride] = (float)prev;
     }
     // anticausal pass
-    double nxt = (z1 / (z1 * z1 - 1.0)) * (z1 * last2 + prev);
+    double nxt = (z1 / (z1 - 1.0)) * prev;
     c[(n - 1) * stride] = (float)nxt;
     for (int k = n - 2; k >= 0; --k) {
         nxt = z1 * (nxt - (double)c[k * stride]);
@@ -117,17 +110,31 @@ __global__ void __launch_bounds__(256) k_pad_images(const float* __restrict__ ra
         int si = d_wrap(i + q.my, N), sj = d_wrap(j + q.mx, N);
         v = __ldg(raw + (size_t)img * N * N + (size_t)si * N + sj);
     } else {
+        // applyGeometry: the source coordinate (j + mx) + ux is wrapped into [-0.5, N - 0.5) (realWRAP), then
+        // interpolatedElementBSpline2D reflects out-of-range neighbours (l < 0 -> -l-1, l >= N -> 2N-l-1)
         float wx[4], wy[4];
         d_bspline3_weights(q.ux, wx);
         d_bspline3_weights(q.uy, wy);
+        int bj = j + q.mx, bi = i + q.my;                       // floor of the source coordinate
+        {
+            const float xs = (float)bj + q.ux, ys = (float)bi + q.uy;
+            if (xs < -1e-6f || xs > (float)(N - 1) + 1e-6f) bj -= (int)floorf((xs + 0.5f) / (float)N) * N;
+            if (ys < -1e-6f || ys > (float)(N - 1) + 1e-6f) bi -= (int)floorf((ys + 0.5f) / (float)N) * N;
+        }
         const float* c = coef + (size_t)img * N * N;
         v = 0.f;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const float* row = c + (size_t)d_wrap(i + q.my - 1 + a, N) * N;
+            int ri = bi - 1 + a;
+            ri = ri < 0 ? -ri - 1 : (ri >= N ? 2 * N - ri - 1 : ri);
+            const float* row = c + (size_t)ri * N;
             float r = 0.f;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) r = fmaf(wx[b], __ldg(row + d_wrap(j + q.mx - 1 + b, N)), r);
+            for (int b = 0; b < 4; ++b) {
+                int rj = bj - 1 + b;
+                rj = rj < 0 ? -rj - 1 : (rj >= N ? 2 * N - rj - 1 : rj);
+                r = fmaf(wx[b], __ldg(row + rj), r);
+            }
             v = fmaf(wy[a], r, v);
         }
     }
