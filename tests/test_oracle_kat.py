@@ -292,3 +292,38 @@ def test_euler_elements_known_answer(oracle_mod):
                         (2, 2): np.cos(tilt)}
                 for (a, b), v in want.items():
                     assert abs(m[a, b] - v) <= k["tolerance"]
+
+
+def test_readapplygeo_golden_images(oracle_mod):
+    """The reference's fixture pair for Image::readApplyGeo (test_image_main.cpp:80-98: test2.spi rotated by anglePsi = 45
+    with BSPLINE3, wrap off and on; tests/golden/readapplygeo_test2.npz).  applyGeometry restated around the oracle's spline
+    primitives — the same primitives apply_shift uses for fractional shifts, with the same coordinate wrap — must give the
+    reference's output images (stored as float32)."""
+    O = oracle_mod
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "readapplygeo_test2.npz"))
+    a = g["input"].astype(np.float64)
+    n = a.shape[0]
+    c = O.bspline_coeffs_2d(a)
+    cs = sn = np.sqrt(0.5)                      # rotation2DMatrix(45); Ainv = [[cos, -sin], [sin, cos]]
+    cen = n // 2
+    lo, hi = -cen, n - cen - 1
+    jj, ii = np.meshgrid(np.arange(n) - cen, np.arange(n) - cen)
+    xp, yp = jj * cs - ii * sn, jj * sn + ii * cs
+    inside = (xp >= lo - 1e-6) & (xp <= hi + 1e-6) & (yp >= lo - 1e-6) & (yp <= hi + 1e-6)
+
+    def wrapc(v):                               # realWRAP(v, lo - 0.5, hi + 0.5) for the coordinates that left [lo, hi]
+        out = v.copy()
+        m = (v < lo - 1e-6) | (v > hi + 1e-6)
+        out[m] = v[m] - np.floor((v[m] - (lo - 0.5)) / n) * n
+        return out
+
+    xw, yw = wrapc(xp), wrapc(yp)
+    got_false = np.zeros((n, n))
+    got_true = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if inside[i, j]:
+                got_false[i, j] = O.bspline_interp_2d(c, xp[i, j] - lo, yp[i, j] - lo)
+            got_true[i, j] = O.bspline_interp_2d(c, xw[i, j] - lo, yw[i, j] - lo)
+    assert np.abs(got_false - g["wrap_false"]).max() <= 2e-6
+    assert np.abs(got_true - g["wrap_true"]).max() <= 2e-6
