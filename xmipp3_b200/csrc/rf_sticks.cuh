@@ -375,7 +375,8 @@ __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const Stick
 template <int K, int CLS>
 __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArgs a) {
     const Geometry& geo = a.geo;
-    __shared__ float tbl[kBlobTable];          // static: its shared address is a compile-time constant
+    __shared__ __align__(16) float tbl[kBlobTable];   // static: its shared address is a compile-time constant
+    __shared__ __align__(8) unsigned long long tblBar;    // mbarrier of the table's bulk copy
     __shared__ int sAdj;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -383,11 +384,38 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
     float2* accV = reinterpret_cast<float2*>(smem) + (size_t)warp * kAccN;
     float* accW = reinterpret_cast<float*>(smem + sizeof(float2) * kStickWarps * kAccN) + (size_t)warp * kAccN;
 
-    for (int i = tid; i < kBlobTable; i += kStickThreads) tbl[i] = __ldg(a.blobTable + i);
+    // The blob table is the one tile-shaped operand every warp of the CTA reuses: one TMA bulk copy (cp.async.bulk,
+    // 40 000 B, completion on an mbarrier) brings it in while the warps zero their accumulators.  (The image windows are
+    // not staged: they are per-lane 4 x 4 windows at data-dependent positions, and re-reading a staged tile would cost the
+    // same L1 wavefronts that bound this kernel.)
+    static_assert((kBlobTable * sizeof(float)) % 16 == 0, "bulk copies move multiples of 16 bytes");
+    const uint32_t barAddr = (uint32_t)__cvta_generic_to_shared(&tblBar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = kBlobTable * sizeof(float);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(tbl)), "l"(a.blobTable), "r"(bytes), "r"(barAddr)
+                     : "memory");
+    }
     for (int i = lane; i < kAccN; i += 32) {
         accV[i] = make_float2(0.f, 0.f);
         accW[i] = 0.f;
     }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TBL_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra TBL_DONE;\n\t"
+        "bra TBL_WAIT;\n\t"
+        "TBL_DONE:\n\t"
+        "}" ::"r"(barAddr)
+        : "memory");
     // Shared byte address of tbl[0] minus (bits(2^23) << 2), modulo 2^32.  Routed through shared memory so that
     // the compiler treats it as an opaque value: the lookup address is then one LEA.
     if (tid == 0) sAdj = (int)((uint32_t)__cvta_generic_to_shared(tbl) - (0x4B000000u << 2));
