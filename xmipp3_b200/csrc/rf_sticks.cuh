@@ -530,6 +530,9 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
                         plain = plain && inb && !special;
                     }
                 }
+                // which of a column's two lanes owns an accumulator depends on the parity of the column's first depth in
+                // THIS plane, so consecutive tasks may touch the same shared address from different lanes: order them
+                __syncwarp();
                 if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
                 else touched |= d_task_run<K, true>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
             }
