@@ -347,7 +347,23 @@ def main():
                "source": prof.get("source", "no ncu summary in profiles/gather_ncu.json"),
                "note": "ncu l1tex__data_pipe_lsu_wavefronts / smsp__issue_active of the same kernel (cold, serialised)"}
     stage_ms = {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}
+    # roofline fraction of every kernel of the step against the measured HBM peak, from the stage timers (CUDA events on
+    # the compute stream) and the algorithmic bytes of DESIGN.md section 5 (fused chain: power-of-two padded sizes)
+    P = wm["P"]
+    side = 2 * (P // 2) + 11                       # slice edge incl. apron (Geometry::side at pad 2, r 1.9)
+    k_bytes = {"k_fft_rows (K1r)": (box * box * 4 + (P // 2 + 1) * box * 8, tm["fft2d_ms"]),
+               "k_fft_cols_slices (K1c)": ((P // 2 + 1) * box * 8 + side * side * 16, tm["slice_ms"]),
+               "k_gather_sticks (K2')": (wm["k2_bytes_per_particle"] + wm["k2_bytes_per_launch_fixed"] / imgs_per_launch, tm["gather_ms"]),
+               "k_edge2 + k_damped_scatter (K2e', K2r)": (None, tm["edge_ms"])}
+    per_kernel = []
+    for name, (bpp, t_ms) in k_bytes.items():
+        e = {"kernel": name, "ms_per_step": t_ms / K, "us_per_particle": 1e3 * t_ms / (K * B)}
+        if bpp is not None and t_ms > 0:
+            gbs = bpp * K * B / (t_ms * 1e-3) / 1e9
+            e.update({"algorithmic_bytes_per_particle": bpp, "achieved_GBps": gbs, "hbm_frac": gbs / hbm_peak})
+        per_kernel.append(e)
     if args.fast:
+        per_kernel = None
         # k_fast_insert: one launch per chunk; per lattice column crossing the half-disc of a plane one 16-byte folded pixel
         # is read and V (8 B) + W (4 B) are read-modified-written
         S = 2 * box
@@ -445,7 +461,7 @@ def main():
                        "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
                        "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
                        "stage_ms_per_step": stage_ms},
-            "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32": fp32, "l1_data_pipe": l1_pipe, "cpu_baseline": cpu_baseline,
+            "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "per_kernel_roofline": per_kernel, "fp32": fp32, "l1_data_pipe": l1_pipe, "cpu_baseline": cpu_baseline,
         }
         line.update(extra)
         sys.stdout.flush()
