@@ -294,8 +294,11 @@ int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs
     const Geometry& g = h->geo;
     const int threads = kFftSeqs * P / 8;
     const size_t smem = sizeof(float2) * (P + kFftSeqs * kFftBuf<P>);
+    constexpr int NC = kColsPerCta<P>;
+    const int threadsC = (NC + 1) * P / 8;
+    const size_t smemC = sizeof(float2) * (P + (NC + 1) * kFftBuf<P> + (P + 2));      // twiddles, NC + 1 sequences, halo values
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     {
@@ -307,7 +310,7 @@ int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs
         StageTimer t(h, Stage::SLICE, h->compute);
         if (h->dDampedMask)
             RF_CUDA(h, cudaMemsetAsync(h->dDampedMask, 0, sizeof(uint32_t) * (size_t)n * (2 * g.R + 1) * ((g.R + 1 + 31) / 32), h->compute));
-        k_fft_cols_slices<P><<<dim3((g.R + 1 + kFftSeqs - 1) / kFftSeqs, n), threads, smem, h->compute>>>(ca);
+        k_fft_cols_slices<P><<<dim3((g.R + 2 + NC - 1) / NC, n), threadsC, smemC, h->compute>>>(ca);
         RF_CUDA(h, cudaGetLastError());
     }
     h->nKernelLaunches += 2;
