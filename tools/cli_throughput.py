@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--thr", type=int, nargs="+", default=[1, 4, 16])
     ap.add_argument("--buffer", type=int, default=1024)
     ap.add_argument("--dir", default=None)
+    ap.add_argument("--gpus", default="1", help="passed to the CLI as --gpus (a number or 'all')")
     a = ap.parse_args()
     import torch
     from bench import synth_batch_torch
@@ -48,7 +49,8 @@ def main():
     for thr in a.thr:
         t0 = time.perf_counter()
         out = subprocess.run([exe, "-i", md, "-o", os.path.join(d, "rec.vol"), "--useCTF", "--sampling", "1.5", "--thr", str(thr),
-                              "--bufferSize", str(a.buffer), "-v", "1"], capture_output=True, text=True)
+                              "--bufferSize", str(a.buffer), "-v", "1"] + (["--gpus", a.gpus] if a.gpus != "1" else []),
+                             capture_output=True, text=True)
         dt = time.perf_counter() - t0
         tail = [l for l in out.stdout.replace("\r", "\n").splitlines() if "images in" in l or "GPU time" in l]
         print("thr=%d wall %.2f s (%.0f images/s incl. process start) rc=%d | %s" % (thr, dt, a.n / dt, out.returncode, " | ".join(t.strip() for t in tail)), flush=True)
