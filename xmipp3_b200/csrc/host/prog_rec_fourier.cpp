@@ -569,9 +569,11 @@ void ProgRecFourierB200::run() {
         std::vector<float> vol((size_t)N * N * N);
         auto insertRange = [&](size_t begin, size_t end) {
             if (worldSize > 1) {    // this rank's contiguous shard of [begin, end)
-                const size_t len = end - begin;
-                end = begin + len * (size_t)(rank + 1) / (size_t)worldSize;
-                begin = begin + len * (size_t)rank / (size_t)worldSize;
+                // sizes differ by at most one, earlier ranks get the extra (same rule as xmipp3_b200/sharding.py)
+                const size_t len = end - begin, base = len / (size_t)worldSize, extra = len % (size_t)worldSize;
+                const size_t r = (size_t)rank;
+                begin = begin + r * base + std::min(r, extra);
+                end = begin + base + (r < extra ? 1 : 0);
             }
             if (begin >= end) return;
             loadBatch(begin, std::min(B, end - begin), slot);
