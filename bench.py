@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1024, help="particles per preprocessing chunk inside the library (max_batch)")
     ap.add_argument("--sym", default="c1", help="point group (e.g. d7 = BASELINE config 4: 14 insertions per image); "
                     "not the headline configuration")
+    ap.add_argument("--no-ctf", action="store_true", help="particles without CTF columns (BASELINE configs 1, 4, 5 name none)")
     ap.add_argument("--fast", action="store_true", help="measure the --fast arithmetic (nearest-pixel insertion + final blob "
                     "convolution) instead of the exact blob insertion; not the headline configuration")
     args = ap.parse_args()
@@ -261,7 +262,7 @@ def main():
     # two distinct device-resident batches (each >> L2) used alternately
     batches = []
     for s in range(2):
-        img, cols = synth_batch_torch(B, box, 1000 * rank + 10 * s, dev, ctf=True)
+        img, cols = synth_batch_torch(B, box, 1000 * rank + 10 * s, dev, ctf=not args.no_ctf)
         batches.append((img, make_particles(B, **cols)))
     torch.cuda.synchronize()
 
@@ -271,7 +272,7 @@ def main():
         from xmipp3_b200 import geometry
         sym_mats = geometry.point_group_matrices(args.sym)
         n_ops = len(sym_mats) + 1
-    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local, max_batch=args.chunk, fast=args.fast, sym_matrices=sym_mats)
+    r = Reconstructor(box, use_ctf=not args.no_ctf, sampling=SAMPLING, device=local, max_batch=args.chunk, fast=args.fast, sym_matrices=sym_mats)
     if world > 1:
         ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -445,9 +446,9 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate0, _ = time_oracle(box, max(2 * cores, 32), cores)
+        rate0, _ = time_oracle(box, max(2 * cores, 32), cores, ctf=not args.no_ctf)
         n_s = int(min(4000, max(64, rate0 * 15)))
-        rate, dt = time_oracle(box, n_s, cores)
+        rate, dt = time_oracle(box, n_s, cores, ctf=not args.no_ctf)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d particles of the same workload in %.1f s (oracle/recfourier_oracle.cpp, double, reference thread scheme)" % (n_s, dt)}
 
@@ -456,8 +457,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections with CTF, padding 2, %s, blob 1.9/0/15, max_resolution 0.5%s" % (box, box, args.sym.upper(), ", --fast arithmetic" if args.fast else ""),
-                       "box": box, "padding": 2, "sym": args.sym.lower(), "insertions_per_particle": n_ops, "ctf": True, "particles_per_step_per_gpu": B,
+            "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections %s, padding 2, %s, blob 1.9/0/15, max_resolution 0.5%s" % (box, box, "without CTF" if args.no_ctf else "with CTF", args.sym.upper(), ", --fast arithmetic" if args.fast else ""),
+                       "box": box, "padding": 2, "sym": args.sym.lower(), "insertions_per_particle": n_ops, "ctf": not args.no_ctf, "particles_per_step_per_gpu": B,
                        "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
                        "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
                        "stage_ms_per_step": stage_ms},

@@ -262,8 +262,14 @@ int fetch_params(rfb200_handle h, void* dst, const void* srcPinned, size_t bytes
 
 template <int K, int CLS>
 int launch_sticks_kc(rfb200_handle h, const StickArgs& a, int grid) {
-    RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
-    k_gather_sticks<K, CLS><<<grid, kStickThreads, kStickSmem, h->compute>>>(a);
+    // only a CTF can damp (flag) a pixel: without it the gather runs the variant without the per-candidate flag test
+    if (h->cfg.use_ctf) {
+        RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K, CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
+        k_gather_sticks<K, CLS, true><<<grid, kStickThreads, kStickSmem, h->compute>>>(a);
+    } else {
+        RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K, CLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
+        k_gather_sticks<K, CLS, false><<<grid, kStickThreads, kStickSmem, h->compute>>>(a);
+    }
     RF_CUDA(h, cudaGetLastError());
     return RFB200_OK;
 }

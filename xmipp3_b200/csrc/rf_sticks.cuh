@@ -211,11 +211,51 @@ __device__ __forceinline__ void d_candidate1(const float S, const float sMax, co
         : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im));
 }
 
+// Without CTF no pixel is ever flagged: the same two candidates minus the three instructions of the flag test.
+__device__ __forceinline__ void d_candidate_nf(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
+                                               const float mult, float& accRe, float& accIm, float& accW) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f32 w, t;\n\t"
+        ".reg .b32 a;\n\t"
+        "setp.le.f32 p, %3, %4;\n\t"
+        "add.rn.f32 t, %3, 0f4B000000;\n\t"
+        "mov.b32 a, t;\n\t"
+        "shl.b32 a, a, 2;\n\t"
+        "add.u32 a, a, %5;\n\t"
+        "@p ld.shared.f32 w, [a];\n\t"
+        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
+        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
+        "@p fma.rn.f32 %2, w, %8, %2;\n\t"
+        "}"
+        : "+f"(accRe), "+f"(accIm), "+f"(accW)
+        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im), "f"(mult));
+}
+__device__ __forceinline__ void d_candidate1_nf(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
+                                                float& accRe, float& accIm, float& accW) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f32 w, t;\n\t"
+        ".reg .b32 a;\n\t"
+        "setp.le.f32 p, %3, %4;\n\t"
+        "add.rn.f32 t, %3, 0f4B000000;\n\t"
+        "mov.b32 a, t;\n\t"
+        "shl.b32 a, a, 2;\n\t"
+        "add.u32 a, a, %5;\n\t"
+        "@p ld.shared.f32 w, [a];\n\t"
+        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
+        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
+        "@p add.rn.f32 %2, %2, w;\n\t"
+        "}"
+        : "+f"(accRe), "+f"(accIm), "+f"(accW)
+        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im));
+}
+
 // One step of one column: evaluate the K x K candidate window of the lane's voxel.  p points at the window origin
 // (16-byte aligned pixel pair).  kSlow additionally weighs every candidate with its multiplicity (0 outside the
 // resolution disc, 2 on column j = 0), looked up per window row.  Two accumulator sets (even / odd candidates)
 // halve the length of the dependent FMA chains.
-template <int K, bool kSlow>
+template <int K, bool kSlow, bool kFlags>
 __device__ __forceinline__ void d_stick_window(const float4* __restrict__ p, const int pitch, const float (&dxs)[K], const float (&dys)[K],
                                                const float sMax, const uint32_t tblAdj, const int jc, const int ic,
                                                const int* __restrict__ rimTab, float& accRe, float& accIm, float& accW) {
@@ -258,11 +298,21 @@ __device__ __forceinline__ void d_stick_window(const float4* __restrict__ p, con
                     const float S = dys[ti] + dxs[tj];
                     const float re = e ? px[ti][q].z : px[ti][q].x, im = e ? px[ti][q].w : px[ti][q].y;
                     if (e) {
-                        if (kSlow) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), re1, im1, w1);
-                        else d_candidate1(S, sMax, tblAdj, re, im, re1, im1, w1);
+                        if (kSlow) {
+                            if (kFlags) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), re1, im1, w1);
+                            else d_candidate_nf(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), re1, im1, w1);
+                        } else {
+                            if (kFlags) d_candidate1(S, sMax, tblAdj, re, im, re1, im1, w1);
+                            else d_candidate1_nf(S, sMax, tblAdj, re, im, re1, im1, w1);
+                        }
                     } else {
-                        if (kSlow) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), accRe, accIm, accW);
-                        else d_candidate1(S, sMax, tblAdj, re, im, accRe, accIm, accW);
+                        if (kSlow) {
+                            if (kFlags) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), accRe, accIm, accW);
+                            else d_candidate_nf(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), accRe, accIm, accW);
+                        } else {
+                            if (kFlags) d_candidate1(S, sMax, tblAdj, re, im, accRe, accIm, accW);
+                            else d_candidate1_nf(S, sMax, tblAdj, re, im, accRe, accIm, accW);
+                        }
                     }
                 }
             }
@@ -323,7 +373,7 @@ __device__ __forceinline__ const float4* d_window_ptr(const StickConsts& c, cons
 // Walk the columns of one task, two depths per column and iteration.  kChecked = false: every step of every
 // active lane is known to be in bounds and to need no multiplicity handling (both ends of each column were
 // tested; the conditions are convex along it).
-template <int K, bool kChecked>
+template <int K, bool kChecked, bool kFlags>
 __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const StickTask& t, const int nIter, const float4* __restrict__ slices,
                                                const int imgStride, const int* __restrict__ rimTab, float2* accV, float* accW, const int col) {
     const PlaneS& pl = c_planesS[t.k];
@@ -352,9 +402,9 @@ __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const Stick
             const float4* p = d_window_ptr<K>(c, sl, t, jw, iw);
             float accRe = 0.f, accIm = 0.f, accWt = 0.f;
             if (kChecked && anySlow)
-                d_stick_window<K, true>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+                d_stick_window<K, true, kFlags>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
             else
-                d_stick_window<K, false>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+                d_stick_window<K, false, kFlags>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
             const int o = tau * kStickCols + col;
             float2 v = accV[o];
             v.x += accRe;
@@ -372,7 +422,7 @@ __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const Stick
 #else
 #define RF_STICK_BOUNDS __launch_bounds__(kStickThreads, 1)
 #endif
-template <int K, int CLS>
+template <int K, int CLS, bool kFlags>
 __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArgs a) {
     const Geometry& geo = a.geo;
     __shared__ __align__(16) float tbl[kBlobTable];   // static: its shared address is a compile-time constant
@@ -533,8 +583,8 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
                 // which of a column's two lanes owns an accumulator depends on the parity of the column's first depth in
                 // THIS plane, so consecutive tasks may touch the same shared address from different lanes: order them
                 __syncwarp();
-                if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
-                else touched |= d_task_run<K, true>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false, kFlags>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                else touched |= d_task_run<K, true, kFlags>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
             }
         }
 
