@@ -170,6 +170,8 @@ struct rfb200_handle_s {
     bool fast = false;
     FastGeo fgeo{};
     float4* dFastPix = nullptr;     // per image sy x sx folded pixels
+    float4* dFastAcc = nullptr;     // interleaved scratch accumulators of the insertion, flushed into dVb / dWb on demand
+    bool fastDirty = false;
     FastSpace* dFastSpaces = nullptr;
     float2* dFastVh = nullptr;      // finalisation: mirrored half space, then its blob convolution
     float2* dFastVc = nullptr;
@@ -335,6 +337,12 @@ int launch_fused_fft(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& 
 
 // W += weights of the CTF-damped pixels; must run before W is read, reduced or copied
 int flush_deficit(rfb200_handle h) {
+    if (h->fast && h->fastDirty) {      // --fast: fold the scratch accumulators into V and W
+        k_fast_flush<<<2048, 256, 0, h->compute>>>(h->dFastAcc, h->dVb, h->dWb, h->nBlocked);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+        h->fastDirty = false;
+    }
     if (!h->dampedDirty || !h->dD) return RFB200_OK;
     k_fold_damped<<<2048, 256, 0, h->compute>>>(h->dWb, h->dD, h->nBlocked);
     if (h->dD2) k_fold_damped<<<2048, 256, 0, h->compute>>>(h->dWb2, h->dD2, h->nBlocked);
@@ -608,7 +616,8 @@ int process_chunk_fast(rfb200_handle h, const float* dRaw, const rfb200_particle
         for (int p0 = 0; p0 < np; p0 += 65535) {
             const int cnt = std::min(65535, np - p0);
             FastInsertArgs a{};
-            a.g = fg; a.spaces = h->dFastSpaces + p0; a.pix = h->dFastPix; a.V = h->dVb; a.W = h->dWb;
+            a.g = fg; a.spaces = h->dFastSpaces + p0; a.pix = h->dFastPix; a.A = h->dFastAcc;
+            h->fastDirty = true;
             dim3 grid((fg.S + 1 + 31) / 32, (fg.S + 1 + 7) / 8, cnt);
             k_fast_insert<<<grid, dim3(32, 8), 0, h->compute>>>(a);
             RF_CUDA(h, cudaGetLastError());
@@ -692,7 +701,7 @@ void free_all(rfb200_handle h) {
                    h->dPad, h->dCoef, h->dFft, h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dNorm,
                    h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dDampedMask, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
                    h->dStickCounters, h->dTwiddle, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0,
-                   h->dFastPix, h->dFastSpaces, h->dFastVh, h->dFastVc, h->dFastWh, h->dFastWc};
+                   h->dFastPix, h->dFastSpaces, h->dFastVh, h->dFastVc, h->dFastWh, h->dFastWc, h->dFastAcc};
     for (void* p : dev) if (p) cudaFree(p);
     for (auto& s : h->slots) {
         void* hp[] = {s.img, s.ctf, s.planesD, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0, s.fast};
@@ -749,6 +758,8 @@ int do_create_fast(rfb200_handle h) {
     RF_CUDA(h, cudaMalloc(&h->dWb, sizeof(float) * h->nBlocked));
     RF_CUDA(h, cudaMemset(h->dVb, 0, sizeof(float2) * h->nBlocked));
     RF_CUDA(h, cudaMemset(h->dWb, 0, sizeof(float) * h->nBlocked));
+    RF_CUDA(h, cudaMalloc(&h->dFastAcc, sizeof(float4) * h->nBlocked));
+    RF_CUDA(h, cudaMemset(h->dFastAcc, 0, sizeof(float4) * h->nBlocked));
     const size_t CH = h->chunkImages;
     const size_t nRaw = CH * g.N * g.N, nPad = CH * (size_t)g.P * g.P, nFft = CH * (size_t)g.P * (g.P / 2 + 1);
     for (int i = 0; i < 2; ++i) RF_CUDA(h, cudaMalloc(&h->dRaw[i], sizeof(float) * nRaw));
@@ -792,6 +803,7 @@ int finalize_fast(rfb200_handle h, float* out, float* fourierOut = nullptr) {
     if (!h->dNorm) RF_CUDA(h, cudaMalloc(&h->dNorm, sizeof(float2) * nHalf));
     if (!h->dVol) RF_CUDA(h, cudaMalloc(&h->dVol, sizeof(float) * nVol));
     if (!h->dOut) RF_CUDA(h, cudaMalloc(&h->dOut, sizeof(float) * nOut));
+    if (int rcf = flush_deficit(h)) return rcf;
     {
         StageTimer t(h, Stage::FINALIZE, h->compute);
         const unsigned gh = (unsigned)((nH + 255) / 256);
@@ -1086,6 +1098,8 @@ int rfb200_reset(rfb200_handle h) {
     if (h->dWb2) RF_CUDA(h, cudaMemsetAsync(h->dWb2, 0, sizeof(float) * h->nBlocked, h->compute));
     if (h->dD) RF_CUDA(h, cudaMemsetAsync(h->dD, 0, sizeof(unsigned long long) * h->nBlocked, h->compute));
     if (h->dD2) RF_CUDA(h, cudaMemsetAsync(h->dD2, 0, sizeof(unsigned long long) * h->nBlocked, h->compute));
+    if (h->dFastAcc) RF_CUDA(h, cudaMemsetAsync(h->dFastAcc, 0, sizeof(float4) * h->nBlocked, h->compute));
+    h->fastDirty = false;
     h->dampedDirty = false;
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
     for (double& m : h->ms) m = 0;
@@ -1162,6 +1176,7 @@ int rfb200_export_accumulators(rfb200_handle h, float* V, float* W) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     if (h->fast) {
         // --fast: the (S+1)^3 temporary volume and weights [z][y][x], as the reference copies them back (copyTempVolumes)
+        if (int rcf = flush_deficit(h)) return rcf;
         RF_CUDA(h, cudaMemcpyAsync(V, h->dVb, sizeof(float2) * h->nBlocked, cudaMemcpyDeviceToHost, h->compute));
         RF_CUDA(h, cudaMemcpyAsync(W, h->dWb, sizeof(float) * h->nBlocked, cudaMemcpyDeviceToHost, h->compute));
         RF_CUDA(h, cudaStreamSynchronize(h->compute));
@@ -1299,8 +1314,11 @@ int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms) {
 int rfb200_weight_sum_begin(rfb200_handle h) {
     if (!h) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
-    if (int rcf = flush_deficit(h)) return rcf;
-    k_weight_sum_partial<<<1024, 256, 0, h->compute>>>(h->dWb, h->nBlocked, h->dSum);
+    const bool scratch = h->fast && h->fastDirty;       // --fast: add the W lane of the scratch instead of flushing it per step
+    if (!scratch)
+        if (int rcf = flush_deficit(h)) return rcf;
+    k_weight_sum_partial<<<1024, 256, 0, h->compute>>>(h->dWb, h->nBlocked, h->dSum,
+                                                        scratch ? reinterpret_cast<const float*>(h->dFastAcc) : nullptr);
     RF_CUDA(h, cudaGetLastError());
     k_weight_sum_final<<<1, 256, 0, h->compute>>>(h->dSum, 1024, h->dSum + 1024);
     RF_CUDA(h, cudaGetLastError());

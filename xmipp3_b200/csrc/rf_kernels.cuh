@@ -407,10 +407,15 @@ __global__ void __launch_bounds__(256) k_axpy(float* __restrict__ y, const float
 }
 
 // deterministic two-stage FP64 sum of the weight accumulator (fixed grid, fixed tree)
-__global__ void __launch_bounds__(256) k_weight_sum_partial(const float* __restrict__ Wb, int64_t n, double* __restrict__ partial) {
+// partial sums of Wb[i] (+ extra[4 i + 2] when `extra` is given: the W lane of the --fast scratch accumulators)
+__global__ void __launch_bounds__(256) k_weight_sum_partial(const float* __restrict__ Wb, int64_t n, double* __restrict__ partial,
+                                                            const float* __restrict__ extra = nullptr) {
     __shared__ double sh[256];
     double acc = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += (double)Wb[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        acc += (double)Wb[i];
+        if (extra) acc += (double)extra[4 * i + 2];
+    }
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
