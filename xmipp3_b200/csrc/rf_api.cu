@@ -606,6 +606,8 @@ int process_chunk_fast(rfb200_handle h, const float* dRaw, const rfb200_particle
         a.iTs = h->cfg.use_ctf ? 1.0 / h->cfg.sampling : 1.0;
         a.minCtf = h->cfg.min_ctf;
         a.maxRes2 = (float)(h->cfg.max_resolution * h->cfg.max_resolution);
+        a.ctfInt = (fg.Pv & (fg.Pv - 1)) == 0 ? 1 : 0;
+        a.sp = make_slice_params(h);          // frequency step 1/(Pv * sampling), --minCTF, --phaseFlipped
         dim3 grid((fg.sx * fg.sy + 255) / 256, n);
         k_fast_prepare<<<grid, 256, 0, h->compute>>>(a);
         RF_CUDA(h, cudaGetLastError());

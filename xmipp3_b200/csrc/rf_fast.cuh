@@ -190,14 +190,24 @@ struct FastPrepArgs {
     int useCtf, phaseFlipped;
     double iTs, minCtf;
     float maxRes2;                // float member maxResolutionSqr of the reference program
+    // Power-of-two padded sizes: the reference's single-precision frequencies x/Pv and (y - Pv/2)/Pv are exact, i.e. integer
+    // multiples of 1/Pv, so the CTF can go through the exact-path evaluator (exact fixed-point phase, FP32 sin/cos,
+    // FP64 re-evaluation next to the --minCTF threshold) instead of FP64 per pixel
+    int ctfInt;
+    SliceParams sp;
 };
 
 // cropAndShift + computeCTFCorrection, the per-pixel products of processVoxel folded in.  grid (ceil(sx*sy/256), nImg)
 __global__ void __launch_bounds__(256) k_fast_prepare(const __grid_constant__ FastPrepArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const FastGeo& g = a.g;
-    if (idx >= g.sx * g.sy) return;
     const int img = blockIdx.y;
+    __shared__ CtfFloat sCtfF;
+    if (a.useCtf && a.ctfInt) {
+        if (threadIdx.x == 0) d_ctf_prepare(a.ctfs[img], a.sp, sCtfF);
+        __syncthreads();
+    }
+    if (idx >= g.sx * g.sy) return;
     const int y = idx / g.sx, x = idx - y * g.sx;
     const int i = (y >= g.sx) ? y - g.sx : y + g.Pv - g.sx;                    // inverse of myPadI (G:314)
     const int Xh = g.Pv / 2 + 1;
@@ -210,7 +220,9 @@ __global__ void __launch_bounds__(256) k_fast_prepare(const __grid_constant__ Fa
         if (f0 * f0 + f1 * f1 > (double)a.maxRes2) re = im = 0.f;               // G:308-310
     }
     float wCTF = 1.f, wMod = 1.f;
-    if (a.useCtf) {
+    if (a.useCtf && a.ctfInt) {
+        d_ctf_weights(a.ctfs[img], sCtfF, a.sp, x, y - g.Pv / 2, wCTF, wMod);
+    } else if (a.useCtf) {
         const float freqY = __fdiv_rn(__fsub_rn((float)y, (float)g.Pv / 2.f), (float)g.Pv);   // G:562
         const float freqX = (float)((double)x / (double)g.Pv);                  // G:566
         float CTFVal = (float)d_ctf_value_xy(a.ctfs[img], (double)freqX * a.iTs, (double)freqY * a.iTs);
