@@ -75,6 +75,25 @@ def test_reads_reference_sample_metadata():
     assert names[0].endswith("images/proj_sh000001.spi")
 
 
+@pytest.mark.skipif(not os.path.exists(REF_XMD), reason="reference tree not present")
+def test_every_reference_xmd_fixture_parses_or_fails_cleanly():
+    """All .xmd fixtures of the reference's test resources: particle sets (an `image` column) are read, the others
+    (sampling tables, block files, a row pointing at a missing ctfModel) are refused with a message, never a crash."""
+    import glob
+    root = os.path.dirname(os.path.dirname(REF_XMD))
+    files = sorted(glob.glob(os.path.join(root, "**", "*.xmd"), recursive=True))
+    assert len(files) >= 15
+    read = 0
+    for f in files:
+        try:
+            p, names, _ = _host.read_particles(f, use_ctf=True)
+            assert len(p) == len(names) > 0
+            read += 1
+        except _host.HostError as e:
+            assert "image" in str(e) or "cannot open" in str(e), (f, str(e))
+    assert read >= 4
+
+
 def test_image_roundtrips(tmp_path):
     rng = np.random.default_rng(0)
     imgs = rng.normal(size=(5, 12, 12)).astype(np.float32)
