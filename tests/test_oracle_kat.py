@@ -327,3 +327,30 @@ def test_readapplygeo_golden_images(oracle_mod):
             got_true[i, j] = O.bspline_interp_2d(c, xw[i, j] - lo, yw[i, j] - lo)
     assert np.abs(got_false - g["wrap_false"]).max() <= 2e-6
     assert np.abs(got_true - g["wrap_true"]).max() <= 2e-6
+
+
+def test_icosahedral_orientation_against_reference_asymmetric_unit():
+    """The reference's fixture lists the 30 projection directions of the i3h ASYMMETRIC UNIT (3-degree sampling): under the
+    right group in the right orientation no two of them are equivalent.  Our i3 rotations keep them >= 3 degrees apart
+    (measured 4.35); with the mirror of i3h only a direction lying (almost) on the mirror plane maps next to itself, while
+    the other icosahedral orientations (i1h, i2h, i4h) produce many equivalent pairs.  Pins the orientation of the
+    symmetry matrices handed to the reconstruction (--sym)."""
+    k = GOLD["i3h_asymmetric_unit"]
+    d = np.array(k["directions"])[:, 3:6]
+
+    def equivalences(name, tol):
+        n, mn = 0, 180.0
+        for R in geometry.point_group_matrices(name):
+            ang = np.degrees(np.arccos(np.clip((R @ d.T).T @ d.T, -1, 1)))
+            fixed = np.eye(len(d), dtype=bool) & (ang < 1e-3)          # a direction on an axis / mirror plane maps to itself
+            ang = np.where(fixed, 180.0, ang)
+            n += int((ang < tol).sum())
+            mn = min(mn, float(ang.min()))
+        return n, mn
+
+    n3, mn3 = equivalences("i3", 0.5 * k["sampling_deg"])
+    assert n3 == 0 and mn3 >= k["sampling_deg"]
+    n3h, _ = equivalences("i3h", 0.5 * k["sampling_deg"])
+    assert n3h <= 1
+    for other in ("i1h", "i2h", "i4h"):
+        assert equivalences(other, 0.5 * k["sampling_deg"])[0] > 4 * max(n3h, 1), other
