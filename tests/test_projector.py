@@ -103,3 +103,60 @@ def test_gpu_project_then_reconstruct_round_trip():
     # the Gaussian phantom has no power near Nyquist (the last shells compare interpolation error with nothing); measured:
     # >= 0.9995 in the first 14 shells, 0.988 at shell 21, falling to 0.14 at the last one
     assert np.nanmin(f[1:N // 2 - 10]) >= 0.97
+
+
+# ---- the drop-in CLI (Fourier mode of xmipp_phantom_project, reconstruction/project.cpp:35-86)
+def _project_bin():
+    from xmipp3_b200 import _build
+    _build.build_host()
+    return _build.PROJECT_BIN
+
+
+def test_phantom_project_cli_argument_errors(tmp_path):
+    import subprocess
+    exe = _project_bin()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "-i <volume_file>" in r.stderr
+    r = subprocess.run([exe, "-i", "v.vol", "-o", "p.xmp", "--angles", "0", "0", "0"], capture_output=True, text=True)
+    assert r.returncode == 2 and "--method fourier" in r.stderr                       # real_space (the reference default) is not here
+    r = subprocess.run([exe, "-i", "v.vol", "-o", "p.xmp", "--method", "fourier", "2", "0.5", "cubic", "--angles", "0", "0", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "nearest, linear, bspline" in r.stderr               # message of project.cpp:59
+    r = subprocess.run([exe, "-i", str(tmp_path / "nope.vol"), "-o", "p.xmp", "--method", "fourier", "--angles", "0", "0", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "XMIPP_ERROR" in r.stderr
+    r = subprocess.run([exe, "-i", "v.vol", "-o", "p.xmp", "--method", "fourier", "--params", "x.param"], capture_output=True, text=True)
+    assert r.returncode == 2 and "--params" in r.stderr
+
+
+@gpu
+def test_phantom_project_cli_matches_the_restatement(tmp_path, oracle_mod):
+    import subprocess
+    from xmipp3_b200 import io
+    O = oracle_mod
+    exe = _project_bin()
+    N = 32
+    ph, vol = _phantom(N, seed=6)
+    io.write_spider(str(tmp_path / "vol.vol"), vol)
+    pr = O.ProjectorOracle(vol, 2.0, 0.5, 3)
+    # single projection (PhantomProject.test_case1 of the reference runs exactly this shape of command)
+    out = str(tmp_path / "image.xmp")
+    r = subprocess.run([exe, "-i", str(tmp_path / "vol.vol"), "-o", out, "--method", "fourier", "2", "0.5", "bspline",
+                        "--angles", "30", "60", "-45"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    img = io.read_spider(out).reshape(N, N)
+    assert synth.rel_l2(img, pr.project(30.0, 60.0, -45.0)) <= 2e-5
+    # a set of orientations from a metadata file -> stack + metadata that the reconstruction program reads
+    rot, tilt, psi = synth.random_orientations(5, 3)
+    io.write_xmd(str(tmp_path / "angles.xmd"), {"angleRot": rot, "angleTilt": tilt, "anglePsi": psi})
+    stack = str(tmp_path / "proj.stk")
+    r = subprocess.run([exe, "-i", str(tmp_path / "vol.vol"), "-o", stack, "--method", "fourier", "2", "0.5", "linear",
+                        "--angles_md", str(tmp_path / "angles.xmd")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pl = O.ProjectorOracle(vol, 2.0, 0.5, 1)
+    from xmipp3_b200 import _host
+    p, names, _ = _host.read_particles(str(tmp_path / "proj.xmd"))
+    assert len(names) == 5 and abs(p["rot"][2] - rot[2]) < 1e-4
+    for k in range(5):
+        got = _host.read_image(names[k], N, N)
+        assert synth.rel_l2(got, pl.project(rot[k], tilt[k], psi[k])) <= 2e-5

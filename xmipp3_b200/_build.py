@@ -13,6 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_CUDA = os.path.join(_HERE, "librecfourier_b200.so")
 LIB_HOST = os.path.join(_HERE, "librecfourier_host.so")
 CLI_BIN = os.path.join(_HERE, "xmipp_reconstruct_fourier_b200")
+PROJECT_BIN = os.path.join(_HERE, "xmipp_phantom_project_b200")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
@@ -73,6 +74,11 @@ def build_host(force=False):
     if os.path.exists(main) and (force or not _newer(CLI_BIN, deps)):
         cmd = ["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(_ROOT, "include"), "-I", CSRC, "-o", CLI_BIN,
                main, "-L", _HERE, "-lrecfourier_host", "-Wl,-rpath,$ORIGIN", "-ldl"]
+        subprocess.check_call(cmd, cwd=_ROOT)
+    pmain = os.path.join(hdir, "phantom_project_main.cpp")
+    if os.path.exists(pmain) and (force or not _newer(PROJECT_BIN, deps)):
+        cmd = ["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(_ROOT, "include"), "-I", CSRC, "-o", PROJECT_BIN,
+               pmain, "-L", _HERE, "-lrecfourier_host", "-Wl,-rpath,$ORIGIN", "-ldl"]
         subprocess.check_call(cmd, cwd=_ROOT)
     return LIB_HOST
 
