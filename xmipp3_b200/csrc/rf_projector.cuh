@@ -266,27 +266,33 @@ inline int proj_build(rfb200_projector p, const float* volume) {
     const size_t nVol = (size_t)N * N * N, nPad = (size_t)P * P * P, nHalf = (size_t)P * P * (P / 2 + 1);
     float *dVol = nullptr, *dPad = nullptr;
     float2* dF = nullptr;
-    RFP_CUDA(p, cudaMalloc(&dVol, sizeof(float) * nVol));
-    RFP_CUDA(p, cudaMalloc(&dPad, sizeof(float) * nPad));
-    RFP_CUDA(p, cudaMalloc(&dF, sizeof(float2) * nHalf));
-    RFP_CUDA(p, cudaMalloc(&p->dC, sizeof(float2) * nPad));
-    RFP_CUDA(p, cudaMemcpyAsync(dVol, volume, sizeof(float) * nVol, cudaMemcpyHostToDevice, p->stream));
-    RFP_CUDA(p, cudaMemsetAsync(dPad, 0, sizeof(float) * nPad, p->stream));
-    k_proj_pad<<<(unsigned)((nVol + 255) / 256), 256, 0, p->stream>>>(dVol, dPad, N, P);
-    cufftHandle plan;
-    RFP_CUFFT(p, cufftPlan3d(&plan, P, P, P, CUFFT_R2C));
-    RFP_CUFFT(p, cufftSetStream(plan, p->stream));
-    RFP_CUFFT(p, cufftExecR2C(plan, dPad, reinterpret_cast<cufftComplex*>(dF)));
-    k_proj_center<<<(unsigned)((nPad + 255) / 256), 256, 0, p->stream>>>(dF, p->dC, P, N);
-    if (g.degree == 3)
-        for (int axis = 0; axis < 3; ++axis) k_proj_prefilter<<<(unsigned)(((size_t)P * P + 127) / 128), 128, 0, p->stream>>>(p->dC, P, axis);
-    RFP_CUDA(p, cudaGetLastError());
-    RFP_CUDA(p, cudaStreamSynchronize(p->stream));
-    cufftDestroy(plan);
+    cufftHandle plan = 0;
+    bool havePlan = false;
+    auto body = [&]() -> int {
+        RFP_CUDA(p, cudaMalloc(&dVol, sizeof(float) * nVol));
+        RFP_CUDA(p, cudaMalloc(&dPad, sizeof(float) * nPad));
+        RFP_CUDA(p, cudaMalloc(&dF, sizeof(float2) * nHalf));
+        RFP_CUDA(p, cudaMalloc(&p->dC, sizeof(float2) * nPad));
+        RFP_CUDA(p, cudaMemcpyAsync(dVol, volume, sizeof(float) * nVol, cudaMemcpyHostToDevice, p->stream));
+        RFP_CUDA(p, cudaMemsetAsync(dPad, 0, sizeof(float) * nPad, p->stream));
+        k_proj_pad<<<(unsigned)((nVol + 255) / 256), 256, 0, p->stream>>>(dVol, dPad, N, P);
+        RFP_CUFFT(p, cufftPlan3d(&plan, P, P, P, CUFFT_R2C));
+        havePlan = true;
+        RFP_CUFFT(p, cufftSetStream(plan, p->stream));
+        RFP_CUFFT(p, cufftExecR2C(plan, dPad, reinterpret_cast<cufftComplex*>(dF)));
+        k_proj_center<<<(unsigned)((nPad + 255) / 256), 256, 0, p->stream>>>(dF, p->dC, P, N);
+        if (g.degree == 3)
+            for (int axis = 0; axis < 3; ++axis) k_proj_prefilter<<<(unsigned)(((size_t)P * P + 127) / 128), 128, 0, p->stream>>>(p->dC, P, axis);
+        RFP_CUDA(p, cudaGetLastError());
+        RFP_CUDA(p, cudaStreamSynchronize(p->stream));
+        return RFB200_OK;
+    };
+    const int rc = body();          // the temporaries are released on every path
+    if (havePlan) cufftDestroy(plan);
     cudaFree(dVol);
     cudaFree(dPad);
     cudaFree(dF);
-    return RFB200_OK;
+    return rc;
 }
 
 inline int proj_run(rfb200_projector p, const double* angles, const float* ctf, bool ctfOnDevice, int n, float* images, bool imagesOnDevice) {
