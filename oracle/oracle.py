@@ -30,7 +30,9 @@ def build(force=False):
         raise RuntimeError("oracle source missing")
     base = ["g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-fPIC", "-pthread"]
     obj = [os.path.join(_HERE, "_oracle_main.o"), os.path.join(_HERE, "_oracle_fast.o")]
-    subprocess.check_call(base + ["-c", _SRC, "-o", obj[0]], cwd=_HERE)
+    # no a*b+c contraction in the exact restatement either: the reference is built for baseline x86-64 (no FMA), and the
+    # race-free "slabs" mode is then bit-identical to the single-thread result
+    subprocess.check_call(base + ["-ffp-contract=off", "-c", _SRC, "-o", obj[0]], cwd=_HERE)
     subprocess.check_call(base + ["-ffp-contract=off", "-c", _SRC_FAST, "-o", obj[1]], cwd=_HERE)
     subprocess.check_call(["g++", "-shared", "-pthread", "-o", _SO] + obj, cwd=_HERE)
     for o in obj:
@@ -85,6 +87,7 @@ def lib():
         L.orf_destroy.argtypes = [C.c_void_p]
         L.orf_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
         L.orf_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orf_insert_slabs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orf_get_accumulators.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orf_add_accumulators.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orf_finalize.argtypes = [C.c_void_p, C.c_void_p]
@@ -281,11 +284,18 @@ class Oracle:
         except Exception:
             pass
 
-    def insert(self, images, particles, threads=1):
+    def insert(self, images, particles, threads=1, scheme="reference"):
+        """scheme "reference": the reference's thread scheme (rows handed out under a mutex; exact for threads = 1, loses
+        updates with >= 3 threads like the reference).  scheme "slabs": race-free parallel mode, every slab of the volume
+        owned by one task; bit-identical to threads = 1 for any thread count (used for the large parity cases)."""
         images = np.ascontiguousarray(images, dtype=np.float32)
         particles = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
         assert images.shape == (len(particles), self.N, self.N)
-        self._L.orf_insert(self._h, _ptr(images), _ptr(particles), len(particles), int(threads))
+        if scheme == "slabs":
+            self._L.orf_insert_slabs(self._h, _ptr(images), _ptr(particles), len(particles), int(threads))
+        else:
+            assert scheme == "reference"
+            self._L.orf_insert(self._h, _ptr(images), _ptr(particles), len(particles), int(threads))
 
     def accumulators(self):
         Z, X = self.Z, self.Z // 2 + 1

@@ -35,6 +35,8 @@ void* orf_create(const orf_config* cfg);
 void orf_destroy(void* h);
 void orf_dims(void* h, int* N, int* P, int* Z);
 void orf_insert(void* h, const float* imgs, const orf_particle* meta, int n, int threads);
+/* race-free parallel insertion (slabs of the volume owned by one task each): bit-identical to threads = 1 */
+void orf_insert_slabs(void* h, const float* imgs, const orf_particle* meta, int n, int threads);
 void orf_get_accumulators(void* h, double* V, double* W);
 void orf_add_accumulators(void* h, const double* V, const double* W);
 void orf_finalize(void* h, double* out);

@@ -707,6 +707,185 @@ struct Oracle {
         for (auto& x : th) x.join();
     }
 
+    // ---- race-free parallel insertion (test infrastructure for large cases; NOT the reference's thread scheme).
+    // The reference's row scheduler loses updates with >= 3 threads, so big parity runs use this
+    // mode instead: the stored volume is cut into slabs of z indices, every slab is owned by exactly one task, and a
+    // task walks all (image, symmetry, row, pixel) in the single-thread order but only applies the updates that land in
+    // its slab.  Every voxel therefore receives the same additions in the same order as with threads = 1: the
+    // accumulators are BIT-IDENTICAL to the single-thread result (tests/test_oracle_kat.py).  Per row the pixels that can
+    // reach the slab form at most four column intervals (pz is linear in j), so a task only visits those.
+    void scatter_row_slab(const std::vector<cd>& F, int i, const M3& A_SL, double weight, const double* ctfW, int zLo, int zHi,
+                          const double (*Q)[2], int nQ) {
+        const int Xh = P / 2 + 1;
+        const double r = cfg.blob_radius, r2 = r * r;
+        const int xsize_1 = X - 1;
+        const double fy = idx2digfreq(i, P);
+        // columns j whose pz (or -pz: conjugate targets sit at -z) comes within r of one of the centred z intervals Q
+        const double c0 = (A_SL.m[7] * fy) * Z, g = A_SL.m[6] * Z / (double)P;
+        int iv[8][2];
+        int nIv = 0;
+        for (int q = 0; q < nQ; ++q)
+            for (int sgnz = 0; sgnz < 2; ++sgnz) {
+                // sgnz = 0: pz in [Q0 - r, Q1 + r];  sgnz = 1: -pz in that range
+                double lo = Q[q][0] - r - 1e-6, hi = Q[q][1] + r + 1e-6;
+                if (sgnz) { double t = -hi; hi = -lo; lo = t; }
+                int jl, jh;
+                if (std::fabs(g) < 1e-12) {
+                    if (c0 < lo - 1e-6 || c0 > hi + 1e-6) continue;
+                    jl = 0; jh = Xh - 1;
+                } else {
+                    double a = (lo - c0) / g, b = (hi - c0) / g;
+                    if (a > b) std::swap(a, b);
+                    if (b < -1 || a > Xh) continue;
+                    jl = std::max(0, (int)std::floor(a) - 1);
+                    jh = std::min(Xh - 1, (int)std::ceil(b) + 1);
+                    if (jl > jh) continue;
+                }
+                iv[nIv][0] = jl; iv[nIv][1] = jh; ++nIv;
+            }
+        if (!nIv) return;
+        // sort + merge so that every pixel is visited once
+        for (int a = 1; a < nIv; ++a)
+            for (int b = a; b > 0 && iv[b][0] < iv[b - 1][0]; --b) { std::swap(iv[b][0], iv[b - 1][0]); std::swap(iv[b][1], iv[b - 1][1]); }
+        int m = 0;
+        for (int a = 1; a < nIv; ++a) {
+            if (iv[a][0] <= iv[m][1] + 1) iv[m][1] = std::max(iv[m][1], iv[a][1]);
+            else { ++m; iv[m][0] = iv[a][0]; iv[m][1] = iv[a][1]; }
+        }
+        nIv = m + 1;
+        for (int q = 0; q < nIv; ++q)
+        for (int j = iv[q][0]; j <= iv[q][1]; ++j) {
+            double fx = idx2digfreq(j, P);                              // :594
+            if (fx * fx + fy * fy > maxRes2) continue;                  // :597
+            double qx = A_SL.m[0] * fx + A_SL.m[1] * fy;
+            double qy = A_SL.m[3] * fx + A_SL.m[4] * fy;
+            double qz = A_SL.m[6] * fx + A_SL.m[7] * fy;
+            double px = qx * Z, py = qy * Z, pz = qz * Z;               // :631-633
+            int z0 = (int)std::ceil(pz - r), z1 = (int)std::floor(pz + r);
+            bool any = false;
+            for (int iz = z0; iz <= z1 && !any; ++iz) {
+                int wz = wrap(iz, Z), wzn = wrap(-wz, Z);
+                any = (wz >= zLo && wz < zHi) || (wzn >= zLo && wzn < zHi);
+            }
+            if (!any) continue;
+            double wCTF = 1, wModulator = 1.0;
+            if (ctfW) { wCTF = ctfW[2 * ((size_t)i * Xh + j)]; wModulator = ctfW[2 * ((size_t)i * Xh + j) + 1]; }   // ctf_weights(), hoisted
+            int x0 = (int)std::ceil(px - r), x1 = (int)std::floor(px + r);   // :636-641
+            int y0 = (int)std::ceil(py - r), y1 = (int)std::floor(py + r);
+            const cd in = F[(size_t)i * Xh + j];
+            for (int iz = z0; iz <= z1; ++iz) {                         // :699
+                double dz = iz - pz, z2 = dz * dz;
+                int wz = wrap(iz, Z), wzn = wrap(-wz, Z);               // :662-666
+                const bool okN = wz >= zLo && wz < zHi, okC = wzn >= zLo && wzn < zHi;
+                if (!okN && !okC) continue;
+                for (int iy = y0; iy <= y1; ++iy) {
+                    double dy = iy - py, y2z2 = dy * dy + z2;
+                    if (y2z2 > r2) continue;                            // :708
+                    int wy = wrap(iy, Z), wyn = wrap(-wy, Z);
+                    for (int ix = x0; ix <= x1; ++ix) {
+                        double dx = ix - px, d2 = dx * dx + y2z2;
+                        if (d2 > r2) continue;                          // :723
+                        int wx = wrap(ix, Z);
+                        bool conj = wx > xsize_1;                       // :748
+                        if (conj ? !okC : !okN) continue;               // not this slab's voxel
+                        int aux = (int)(d2 * iDeltaSqrt + 0.5);         // :725
+                        double w = blobTableSqrt[aux] * weight * wModulator;   // :726
+                        size_t idx;
+                        if (conj) idx = ((size_t)wzn * Z + wyn) * X + wrap(-wx, Z);   // :750-754
+                        else idx = ((size_t)wz * Z + wy) * X + wx;                    // :758-761
+                        double wEff = w * wCTF;                         // :778
+                        double re = wEff * in.real(), im = wEff * in.imag();
+                        V[idx] += cd(re, conj ? -im : im);              // :781-787
+                        W[idx] += w;                                    // :782
+                    }
+                }
+            }
+        }
+    }
+
+    void insert_slabs(const float* imgs, const orf_particle* meta, int n, int T) {
+        history.insert(history.end(), meta, meta + n);
+        if (T < 1) T = 1;
+        size_t conserveRows = (size_t)std::ceil((double)P * cfg.max_resolution * 2.0);   // :927-928
+        conserveRows = (size_t)std::ceil((double)conserveRows / 2.0);
+        const size_t bytesPerImage = sizeof(cd) * (size_t)P * (P / 2 + 1);
+        const int B = (int)std::max<size_t>(T, std::min<size_t>(256, ((size_t)1 << 30) / (2 * bytesPerImage)));   // <= 1 GiB of transforms
+        // slabs of stored z indices, several per thread, central (heaviest) ones first
+        const int nSlab = std::min(Z, 3 * T);
+        std::vector<std::pair<int, int>> slabs;
+        for (int s = 0; s < nSlab; ++s) {
+            int lo = (int)((long)Z * s / nSlab), hi = (int)((long)Z * (s + 1) / nSlab);
+            if (hi > lo) slabs.push_back({lo, hi});
+        }
+        auto centreDist = [&](const std::pair<int, int>& s) { int c = (s.first + s.second) / 2; return std::min(c, Z - c); };
+        std::stable_sort(slabs.begin(), slabs.end(), [&](const auto& a, const auto& b) { return centreDist(a) < centreDist(b); });
+        const int R1 = (int)std::ceil(cfg.blob_radius) + 1;
+
+        std::vector<Loaded> L(B);
+        std::vector<std::vector<double>> ctfW(B);    // (wCTF, wModulator) per half-plane pixel: the reference evaluates them per
+                                                     // symmetry (RF.cpp:600-625); they only depend on the pixel
+        const int Xh = P / 2 + 1;
+        for (int b0 = 0; b0 < n; b0 += B) {
+            const int nb = std::min(B, n - b0);
+            {   // phase 1: preprocess the batch, one image per task
+                std::atomic<int> next(0);
+                auto work = [&] {
+                    for (;;) {
+                        int k = next.fetch_add(1);
+                        if (k >= nb) return;
+                        L[k].p = meta[b0 + k];
+                        preprocess(imgs + (size_t)(b0 + k) * N * N, L[k].p, L[k].F, L[k].Ainv, L[k].weight);
+                        if (has_ctf()) {
+                            Ctf ctf(L[k].p);
+                            ctfW[k].assign((size_t)2 * P * Xh, 1.0);
+                            for (int i = 0; i < P; ++i) {
+                                const double fy = idx2digfreq(i, P);
+                                for (int j = 0; j < Xh; ++j) {
+                                    const double fx = idx2digfreq(j, P);
+                                    if (fx * fx + fy * fy > maxRes2) continue;
+                                    ctf_weights(ctf, i, j, fx, fy, ctfW[k][2 * ((size_t)i * Xh + j)], ctfW[k][2 * ((size_t)i * Xh + j) + 1]);
+                                }
+                            }
+                        }
+                    }
+                };
+                std::vector<std::thread> th;
+                for (int t = 0; t < T; ++t) th.emplace_back(work);
+                for (auto& x : th) x.join();
+            }
+            {   // phase 2: every slab task inserts the whole batch in the single-thread order
+                std::atomic<int> next(0);
+                auto work = [&] {
+                    for (;;) {
+                        int s = next.fetch_add(1);
+                        if (s >= (int)slabs.size()) return;
+                        const int zLo = slabs[s].first, zHi = slabs[s].second;
+                        // centred z intervals whose wrapped index falls into [zLo, zHi): q = t (t <= Z/2 + R1) and q = t - Z
+                        double Q[2][2];
+                        int nQ = 0;
+                        if (zLo <= Z / 2 + R1) { Q[nQ][0] = zLo; Q[nQ][1] = std::min(zHi - 1, Z / 2 + R1); ++nQ; }
+                        if (zHi - 1 >= Z / 2 - R1) { Q[nQ][0] = std::max(zLo, Z / 2 - R1) - Z; Q[nQ][1] = zHi - 1 - Z; ++nQ; }
+                        for (int k = 0; k < nb; ++k) {
+                            if (L[k].weight == 0.0) continue;                      // :483-484
+                            const double* cw = has_ctf() ? ctfW[k].data() : nullptr;
+                            for (size_t isym = 0; isym < R.size(); ++isym) {       // :931
+                                M3 A_SL = matmul(R[isym], L[k].Ainv);              // :936
+                                for (int i = 0; i < P; ++i) {
+                                    if ((size_t)i >= conserveRows && (size_t)i < (size_t)P - conserveRows) continue;
+                                    scatter_row_slab(L[k].F, i, A_SL, L[k].weight, cw, zLo, zHi, Q, nQ);
+                                }
+                            }
+                        }
+                    }
+                };
+                std::vector<std::thread> th;
+                for (int t = 0; t < T; ++t) th.emplace_back(work);
+                for (auto& x : th) x.join();
+            }
+            for (int k = 0; k < nb; ++k) if (L[k].weight != 0.0) ++n_inserted;
+        }
+    }
+
     // forceWeightSymmetry — RF.cpp:1188-1221
     void force_weight_symmetry() {
         int yHalf = Z / 2; if (Z % 2 == 0) yHalf--;
@@ -1073,6 +1252,9 @@ void orf_destroy(void* h) { delete static_cast<Oracle*>(h); }
 void orf_dims(void* h, int* N, int* P, int* Z) {
     auto* o = static_cast<Oracle*>(h);
     *N = o->N; *P = o->P; *Z = o->Z;
+}
+void orf_insert_slabs(void* h, const float* imgs, const orf_particle* meta, int n, int threads) {
+    static_cast<Oracle*>(h)->insert_slabs(imgs, meta, n, threads);
 }
 void orf_insert(void* h, const float* imgs, const orf_particle* meta, int n, int threads) {
     static_cast<Oracle*>(h)->insert(imgs, meta, n, threads);

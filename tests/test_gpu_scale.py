@@ -1,0 +1,134 @@
+"""GPU parity AT SCALE (run with -m gpu): the CUDA path against the CPU oracle on BASELINE's own configurations, with
+particle counts the single-thread oracle could not finish in a test run.  The oracle runs in its race-free parallel mode
+(scheme="slabs": every slab of the volume owned by one task, bit-identical to threads = 1, tests/test_oracle_kat.py).
+
+  * config 3 geometry: 2000 x 256^2 particles with CTF, padding 2, C1
+  * config 4:          200 x 256^2 particles, D7 (14 insertions per image = 2800 planes)
+  * config 5 geometry: 200 x 512^2 particles, padding 2 (Z = 1024, FFT<1024>, 6.5 GB of accumulators)
+  * FP32 accumulation: 20,000 x 256^2 particles accumulated in one go (FP32) against the FP64 sum of the per-1000
+    partial accumulators, both finalised (reference: double accumulators, reconstruct_fourier.h:182-185)
+
+Gate (north_star): rel-L2 <= 1e-4 on the real-space map, FSC >= 0.999 in every shell."""
+import os
+
+import numpy as np
+import pytest
+
+from xmipp3_b200 import geometry, synth
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_GATE = 1e-4
+FSC_GATE = 0.999
+ACC_TOL = 2e-5
+CORES = os.cpu_count() or 1
+
+
+def _free_host_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def _cols(d, ctf):
+    cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], shift_x=d["shift_x"], shift_y=d["shift_y"])
+    if ctf:
+        cols.update(d["ctf"])
+    return cols
+
+
+def _pair(oracle_mod, N, n, ctf=False, sym=None, seed=0, max_batch=1024, compare_acc=True):
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    d = synth.make_dataset(n, N, seed=seed, ctf=ctf, sym=sym)
+    cols = _cols(d, ctf)
+    mats = geometry.point_group_matrices(sym) if sym else None
+    args = dict(sym_matrices=mats, use_ctf=ctf, sampling=d["sampling"])
+    r = Reconstructor(N, max_batch=max_batch, **args)
+    r.insert(d["images"], make_particles(n, **cols))
+    v = r.finalize()
+    acc = r.accumulators() if compare_acc else None
+    r.close()
+    o = oracle_mod.Oracle(N, **args)
+    o.insert(d["images"], oracle_mod.make_particles(n, **cols), threads=CORES, scheme="slabs")
+    out = {}
+    if compare_acc:
+        Vo, Wo = o.accumulators()
+        V, W = acc
+        out["acc_V"] = float(np.linalg.norm(V[:, :, 1:] - Vo[:, :, 1:]) / np.linalg.norm(Vo[:, :, 1:]))
+        out["acc_W"] = float(np.linalg.norm(W[:, :, 1:] - Wo[:, :, 1:]) / np.linalg.norm(Wo[:, :, 1:]))
+        del Vo, Wo, V, W, acc
+    vo = o.finalize()
+    del o
+    out["rel_l2"] = float(synth.rel_l2(v, vo))
+    out["min_fsc"] = float(np.nanmin(synth.fsc(v, vo)[1:]))
+    return out
+
+
+def _gate(res):
+    print(res)
+    if "acc_V" in res:
+        assert res["acc_V"] <= ACC_TOL and res["acc_W"] <= ACC_TOL, res
+    assert res["rel_l2"] <= REL_L2_GATE, res
+    assert res["min_fsc"] >= FSC_GATE, res
+
+
+def test_config3_2000_particles_box256_ctf(oracle_mod):
+    _gate(_pair(oracle_mod, 256, 2000, ctf=True, seed=51))
+
+
+def test_config4_d7_box256_200_particles(oracle_mod):
+    _gate(_pair(oracle_mod, 256, 200, sym="d7", seed=52))
+
+
+def test_config5_box512_200_particles(oracle_mod):
+    free = _free_host_gb()
+    if free < 48:
+        pytest.skip("needs ~40 GB of host memory for the double-precision oracle at Z = 1024 (%.0f GB available)" % free)
+    _gate(_pair(oracle_mod, 512, 200, seed=53, max_batch=256, compare_acc=free >= 96))
+
+
+def test_fp32_accumulation_20k_particles_box256(oracle_mod):
+    """The library accumulates in FP32, the reference in FP64.  20 chunks of 1000 particles are inserted
+    (a) into one handle, one after the other (the FP32 running sums the product computes) and (b) each into an empty
+    handle whose accumulators are exported and summed in FP64 on the host; (b) is finalised by the FP64 oracle.  The
+    per-1000 partial sums themselves are covered by test_config3_2000_particles_box256_ctf."""
+    import torch
+    import bench
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    N, chunk, n_chunks = 256, 1000, 20
+    dev = torch.device("cuda", 0)
+    a = Reconstructor(N, use_ctf=True, sampling=bench.SAMPLING)
+    b = Reconstructor(N, use_ctf=True, sampling=bench.SAMPLING)
+    Vs = Ws = None
+    for c in range(n_chunks):
+        img, cols = bench.synth_batch_torch(chunk, N, 7000 + 10 * c, dev, ctf=True)
+        p = make_particles(chunk, **cols)
+        torch.cuda.synchronize()
+        a.insert_device_ptr(img.data_ptr(), p)
+        b.reset()
+        b.insert_device_ptr(img.data_ptr(), p)
+        V, W = b.accumulators()
+        if Vs is None:
+            Vs, Ws = V.astype(np.complex128), W.astype(np.float64)
+        else:
+            Vs += V
+            Ws += W
+        a.sync()
+        del img
+    b.close()
+    va = a.finalize()
+    Va, Wa = a.accumulators()
+    a.close()
+    res = {"acc_V": float(np.linalg.norm(Va - Vs) / np.linalg.norm(Vs)), "acc_W": float(np.linalg.norm(Wa - Ws) / np.linalg.norm(Ws))}
+    del Va, Wa
+    o = oracle_mod.Oracle(N, use_ctf=True, sampling=bench.SAMPLING)
+    o.add_accumulators(Vs, Ws)
+    vo = o.finalize()
+    res["rel_l2"] = float(synth.rel_l2(va, vo))
+    res["min_fsc"] = float(np.nanmin(synth.fsc(va, vo)[1:]))
+    res["particles"] = chunk * n_chunks
+    _gate(res)

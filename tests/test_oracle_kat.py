@@ -195,6 +195,33 @@ def test_oracle_multithread_same_scheme(oracle_mod):
     assert np.linalg.norm(W1 - W2) / np.linalg.norm(W1) < 5e-2
 
 
+@pytest.mark.parametrize("case", [dict(N=32, n=24, ctf=True, shifts=True), dict(N=24, n=17, sym="d3"), dict(N=25, n=12),
+                                  dict(N=48, n=20, ctf=True, max_resolution=0.35)],
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_oracle_slab_mode_is_bit_identical_to_single_thread(oracle_mod, case):
+    """scheme="slabs" (the mode the large GPU parity cases use): every voxel receives the single-thread sequence of
+    additions, so V and W are equal bit for bit for any thread count — including the Nyquist wrap-around (max_resolution
+    0.5) and the conjugate fold, where the slab owning a target differs from the slab the pixel sits in."""
+    from xmipp3_b200 import geometry
+    case = dict(case)
+    N, n, ctf, sym = case.pop("N"), case.pop("n"), case.pop("ctf", False), case.pop("sym", None)
+    d = synth.make_dataset(n, N, seed=3, ctf=ctf, shifts=case.pop("shifts", False), sym=sym)
+    cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], shift_x=d["shift_x"], shift_y=d["shift_y"])
+    if ctf:
+        cols.update(d["ctf"])
+    p = oracle_mod.make_particles(n, **cols)
+    kw = dict(use_ctf=ctf, sampling=d["sampling"], sym_matrices=geometry.point_group_matrices(sym) if sym else None, **case)
+    o1 = oracle_mod.Oracle(N, **kw)
+    o1.insert(d["images"], p, threads=1)
+    V1, W1 = o1.accumulators()
+    for threads in (1, 3, 7):
+        o2 = oracle_mod.Oracle(N, **kw)
+        o2.insert(d["images"][:5], p[:5], threads=threads, scheme="slabs")       # two calls: state carries over
+        o2.insert(d["images"][5:], p[5:], threads=threads, scheme="slabs")
+        V2, W2 = o2.accumulators()
+        assert np.array_equal(V1, V2) and np.array_equal(W1, W2), threads
+
+
 # ---- CTF: the reference's own known answers (test_ctf_main.cpp) over data/ctf.cpp:107-300, restated here on top of the
 # oracle's CTF value / argument (the functions the reconstruction path evaluates per pixel, RF.cpp:600-606)
 def _ctf_particle(O, md):

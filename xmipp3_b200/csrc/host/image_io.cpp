@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <vector>
@@ -21,6 +22,10 @@ namespace {
 enum class Kind { SPIDER, MRC };
 
 struct OpenFile {
+    OpenFile() = default;
+    OpenFile(const OpenFile&) = delete;
+    OpenFile& operator=(const OpenFile&) = delete;
+    ~OpenFile() { if (fd >= 0) close(fd); }      // the last holder (cache entry or a reader in flight) closes the descriptor
     int fd = -1;
     Kind kind = Kind::SPIDER;
     bool swap = false;
@@ -31,8 +36,15 @@ struct OpenFile {
     bool isStack = false;
 };
 
+// Open files are shared between the cache and the readers that are using them: evicting an entry only drops the
+// cache's reference, so a loader thread in the middle of a pread keeps a valid descriptor (the CLI runs up to 16 loader
+// threads, and a dataset stored as one file per particle cycles through far more than kMaxOpen files).
+using FilePtr = std::shared_ptr<const OpenFile>;
+struct CacheEntry { FilePtr file; uint64_t lastUse = 0; };
+constexpr size_t kMaxOpen = 256;
 std::mutex g_mutex;
-std::map<std::string, OpenFile> g_cache;
+std::map<std::string, CacheEntry> g_cache;
+uint64_t g_tick = 0;
 
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
 inline float swapf(float f) {
@@ -64,12 +76,13 @@ void preadAll(int fd, void* buf, size_t n, off_t off, const std::string& what) {
     }
 }
 
-OpenFile openFile(const std::string& path, const std::string& fmt) {
-    OpenFile f;
+FilePtr openFile(const std::string& path, const std::string& fmt) {
+    auto fp = std::make_shared<OpenFile>();      // owns the descriptor from here on: every throw below closes it
+    OpenFile& f = *fp;
     f.fd = open(path.c_str(), O_RDONLY);
     if (f.fd < 0) throw std::runtime_error("cannot open image file " + path);
     struct stat st;
-    fstat(f.fd, &st);
+    if (fstat(f.fd, &st) != 0) throw std::runtime_error("cannot stat image file " + path);
     f.kind = kindOf(fmt);
     if (f.kind == Kind::MRC) {
         unsigned char h[1024];
@@ -123,20 +136,26 @@ OpenFile openFile(const std::string& path, const std::string& fmt) {
             f.info.nImages = 1;
         }
     }
-    return f;
+    return fp;
 }
 
-const OpenFile& cached(const std::string& path, const std::string& fmt) {
+FilePtr cached(const std::string& path, const std::string& fmt) {
     std::lock_guard<std::mutex> g(g_mutex);
     std::string key = path + ":" + fmt;
     auto it = g_cache.find(key);
-    if (it != g_cache.end()) return it->second;
-    if (g_cache.size() > 256) {
-        for (auto& kv : g_cache) close(kv.second.fd);
-        g_cache.clear();
+    if (it != g_cache.end()) {
+        it->second.lastUse = ++g_tick;
+        return it->second.file;
     }
-    auto r = g_cache.emplace(key, openFile(path, fmt));
-    return r.first->second;
+    FilePtr fp = openFile(path, fmt);
+    if (g_cache.size() >= kMaxOpen) {            // evict the least recently used entry only
+        auto lru = g_cache.begin();
+        for (auto e = g_cache.begin(); e != g_cache.end(); ++e)
+            if (e->second.lastUse < lru->second.lastUse) lru = e;
+        g_cache.erase(lru);
+    }
+    g_cache[key] = CacheEntry{fp, ++g_tick};
+    return fp;
 }
 
 void writeAll(FILE* f, const void* p, size_t n, const std::string& path) {
@@ -221,14 +240,15 @@ ImageInfo readImageInfo(const std::string& spec) {
     size_t idx;
     std::string path, fmt;
     parseImageName(spec, idx, path, fmt);
-    return cached(path, fmt).info;
+    return cached(path, fmt)->info;
 }
 
 void readImage2D(const std::string& spec, float* out, int nx, int ny) {
     size_t idx;
     std::string path, fmt;
     parseImageName(spec, idx, path, fmt);
-    const OpenFile& f = cached(path, fmt);
+    const FilePtr fp = cached(path, fmt);      // keeps the descriptor open for the duration of the read
+    const OpenFile& f = *fp;
     if (f.info.nx != nx || f.info.ny != ny)
         throw std::runtime_error("image " + spec + " is " + std::to_string(f.info.nx) + "x" + std::to_string(f.info.ny) +
                                  ", expected " + std::to_string(nx) + "x" + std::to_string(ny));
@@ -331,8 +351,7 @@ void writeStack(const std::string& spec, const float* data, int nx, int ny, size
 
 void closeImageCache() {
     std::lock_guard<std::mutex> g(g_mutex);
-    for (auto& kv : g_cache) close(kv.second.fd);
-    g_cache.clear();
+    g_cache.clear();       // descriptors close when their last holder lets go
 }
 
 }  // namespace rfhost

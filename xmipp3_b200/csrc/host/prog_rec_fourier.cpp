@@ -2,6 +2,7 @@
 #include "prog_rec_fourier.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <libgen.h>
 #include <signal.h>
 #include <sys/wait.h>
@@ -365,11 +366,12 @@ void ProgRecFourierB200::runRanks() {
         run();
         return;
     }
-    char tmpl[] = "/tmp/rfb200_nccl_id_XXXXXX";
-    int tfd = mkstemp(tmpl);
-    if (tfd < 0) throw ProgramError("cannot create the rendezvous file in /tmp");
-    close(tfd);
-    unlink(tmpl);   // rank 0 creates it (atomically) once the id exists
+    // the rendezvous file lives in a private directory (mode 0700): no other local user can plant a symlink or a bogus
+    // id under its name, and a stale file of a crashed run can never be picked up (the directory name is fresh)
+    char dirTmpl[] = "/tmp/rfb200_XXXXXX";
+    if (!mkdtemp(dirTmpl)) throw ProgramError("cannot create the rendezvous directory in /tmp");
+    const std::string idPath = std::string(dirTmpl) + "/nccl_id";
+    const char* tmpl = idPath.c_str();
     std::cout.flush();
     std::cerr.flush();
     std::vector<pid_t> pids;
@@ -416,6 +418,7 @@ void ProgRecFourierB200::runRanks() {
     }
     unlink(tmpl);
     unlink((std::string(tmpl) + ".tmp").c_str());
+    rmdir(dirTmpl);
     if (failed) throw ProgramError("a GPU rank failed (exit code " + std::to_string(failed) + ")");
 }
 
@@ -491,10 +494,12 @@ void ProgRecFourierB200::run() {
                 throw ProgramError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)");
             }
             const std::string tmp = idFile + ".tmp";
-            std::ofstream f(tmp, std::ios::binary);
-            f.write(id, sizeof id);
-            f.close();
-            if (!f || rename(tmp.c_str(), idFile.c_str()) != 0) {
+            // O_EXCL | O_NOFOLLOW: never write through a pre-existing file or symlink
+            const int wfd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+            const bool wrote = wfd >= 0 && write(wfd, id, sizeof id) == (ssize_t)sizeof id;
+            if (wfd >= 0) close(wfd);
+            if (!wrote || rename(tmp.c_str(), idFile.c_str()) != 0) {
+                if (wfd >= 0) unlink(tmp.c_str());
                 api.destroy(h);
                 throw ProgramError("cannot write the rendezvous file " + idFile);
             }

@@ -218,21 +218,47 @@ cudaEvent_t get_event(rfb200_handle h) {
         h->evPool.pop_back();
         return e;
     }
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;            // stage timing is best effort: a pair with a missing event is skipped
+    }
     return e;
 }
 struct StageTimer {   // records an event pair around a stage on a stream
     rfb200_handle h; int stage; cudaStream_t s; cudaEvent_t a, b;
     StageTimer(rfb200_handle h_, int stage_, cudaStream_t s_) : h(h_), stage(stage_), s(s_) {
         a = get_event(h); b = get_event(h);
-        cudaEventRecord(a, s);
+        if (a && b) cudaEventRecord(a, s);
     }
     ~StageTimer() {
-        cudaEventRecord(b, s);
-        h->pending.push_back({stage, a, b});
+        if (a && b) {
+            cudaEventRecord(b, s);
+            h->pending.push_back({stage, a, b});
+        } else {
+            if (a) h->evPool.push_back(a);
+            if (b) h->evPool.push_back(b);
+        }
     }
 };
+// Recycle the event pairs whose stage has completed (no waiting): called at the start of every insert so that a long
+// run keeps a bounded number of live events instead of ~14 per chunk until the next sync.
+void drain_timings(rfb200_handle h) {
+    size_t keep = 0;
+    for (size_t i = 0; i < h->pending.size(); ++i) {
+        EvPair& p = h->pending[i];
+        if (cudaEventQuery(p.b) == cudaSuccess) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) h->ms[p.stage] += t;
+            h->evPool.push_back(p.a);
+            h->evPool.push_back(p.b);
+        } else {
+            cudaGetLastError();     // cudaErrorNotReady is not an error
+            h->pending[keep++] = p;
+        }
+    }
+    h->pending.resize(keep);
+}
 void resolve_timings(rfb200_handle h) {
     static const bool trace = getenv("RFB200_TRACE") != nullptr;     // developer aid: stage timeline on stderr
     static const char* names[] = {"h2d", "pad", "fft2d", "slice", "gather", "edge", "finalize", "reduce"};
@@ -1047,6 +1073,8 @@ int rfb200_get_info(rfb200_handle h, rfb200_info* info) {
 int rfb200_insert_batch(rfb200_handle h, const float* images, const rfb200_particle* meta, int32_t n) {
     if (!h || (n > 0 && (!images || !meta)) || n < 0) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    static const bool trace = getenv("RFB200_TRACE") != nullptr;
+    if (!trace) drain_timings(h);
     const Geometry& g = h->geo;
     const size_t imgElems = (size_t)g.N * g.N;
     int buf = 0;
@@ -1073,6 +1101,7 @@ int rfb200_insert_batch(rfb200_handle h, const float* images, const rfb200_parti
 int rfb200_insert_batch_device(rfb200_handle h, const float* d_images, const rfb200_particle* meta, int32_t n) {
     if (!h || (n > 0 && (!d_images || !meta)) || n < 0) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (getenv("RFB200_TRACE") == nullptr) drain_timings(h);
     const size_t imgElems = (size_t)h->geo.N * h->geo.N;
     for (int i0 = 0; i0 < n; i0 += h->chunkImages) {
         int cnt = std::min(h->chunkImages, n - i0);
