@@ -74,6 +74,11 @@ def make_particles(n, **cols):
     return p
 
 
+SPACE_DTYPE = np.dtype([("minX", np.int32), ("minY", np.int32), ("minZ", np.int32), ("maxX", np.int32), ("maxY", np.int32),
+                        ("maxZ", np.int32), ("dir", np.int32), ("projectionIndex", np.int32), ("maxDistanceSqr", np.float32),
+                        ("unitNormal", np.float32, 3), ("topOrigin", np.float32, 3), ("bottomOrigin", np.float32, 3),
+                        ("transformInv", np.float32, 9), ("weight", np.float32)])     # orf_space / refk_space
+
 _lib = None
 
 
@@ -123,6 +128,11 @@ def lib():
         L.orf_projector_project.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.orf_fast_create.restype = C.c_void_p
         L.orf_fast_create.argtypes = [C.POINTER(Config)]
+        L.orf_fast_create2.restype = C.c_void_p
+        L.orf_fast_create2.argtypes = [C.POINTER(Config), C.c_int]
+        L.orf_fast_export_buffer.restype = C.c_int
+        L.orf_fast_export_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orf_fast_tables.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orf_fast_destroy.argtypes = [C.c_void_p]
         L.orf_fast_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
         L.orf_fast_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -193,11 +203,20 @@ class FastOracle:
     precision + one final 3-D blob convolution); see recfourier_fast_oracle.cpp."""
 
     def __init__(self, img_size, padding=(2.0, 2.0), max_resolution=0.5, blob=(1.9, 0, 15.0),
-                 sym_matrices=None, use_ctf=False, sampling=1.0, min_ctf=0.01, phase_flipped=False, use_weights=False):
+                 sym_matrices=None, use_ctf=False, sampling=1.0, min_ctf=0.01, phase_flipped=False, use_weights=False,
+                 use_fast=True):
+        """use_fast=False: host side of the GPU program WITHOUT --fast (buffers with blob-thick traverse spaces, no final
+        blob convolution); the device arithmetic of that mode is not restated, insert() is then unavailable and the temporary
+        spaces come from the compiled reference kernel (oracle/ref_kernel.py) through set_temp_spaces()."""
         self._L = lib()
         self._cfg, self._sym = _make_config(img_size, padding, max_resolution, blob, sym_matrices, use_ctf, sampling,
                                             min_ctf, phase_flipped, use_weights, 1)
-        self._h = self._L.orf_fast_create(C.byref(self._cfg))
+        self.use_fast = bool(use_fast)
+        self.use_ctf = bool(use_ctf)
+        self.n_sym = 1 + (0 if sym_matrices is None else len(np.asarray(sym_matrices).reshape(-1, 9)))
+        self.blob = tuple(blob)
+        self.max_resolution = float(max_resolution)
+        self._h = self._L.orf_fast_create2(C.byref(self._cfg), int(self.use_fast))
         if not self._h:
             raise RuntimeError("orf_fast_create failed")
         v = [C.c_int() for _ in range(4)]
@@ -214,10 +233,36 @@ class FastOracle:
             pass
 
     def insert(self, images, particles):
+        assert self.use_fast, "only the --fast device arithmetic is restated on the CPU"
         images = np.ascontiguousarray(images, dtype=np.float32)
         particles = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
         assert images.shape == (len(particles), self.N, self.N)
         self._L.orf_fast_insert(self._h, _ptr(images), _ptr(particles), len(particles))
+
+    def export_buffer(self, images, particles):
+        """The RecFourierBufferData contents ProgRecFourierGPU::prepareBuffer builds for these images
+        (reconstruct_fourier_gpu.cpp:323-415): (FFTs [k, sy, sx] complex64, CTFs, modulators [k, sy, sx] float32 or None,
+        spaces [k * n_sym] SPACE_DTYPE), k = images kept."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        particles = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+        n = len(particles)
+        assert images.shape == (n, self.N, self.N)
+        F = np.zeros((n, self.sy, self.sx), dtype=np.complex64)
+        Cc = np.zeros((n, self.sy, self.sx), dtype=np.float32)
+        M = np.zeros((n, self.sy, self.sx), dtype=np.float32)
+        sp = np.zeros(n * self.n_sym, dtype=SPACE_DTYPE)
+        k = self._L.orf_fast_export_buffer(self._h, _ptr(images), _ptr(particles), n, _ptr(F), _ptr(Cc), _ptr(M), _ptr(sp))
+        if not self.use_ctf:
+            Cc = M = None
+        else:
+            Cc, M = Cc[:k], M[:k]
+        return F[:k], Cc, M, sp[:k * self.n_sym]
+
+    def tables(self):
+        t = np.empty(10000, dtype=np.float32)
+        ids, iw0 = C.c_float(), C.c_float()
+        self._L.orf_fast_tables(self._h, _ptr(t), C.byref(ids), C.byref(iw0))
+        return t, ids.value, iw0.value
 
     def temp_spaces(self):
         n = self.S + 1

@@ -52,7 +52,26 @@ void orf_projector_project(void* h, double rot, double tilt, double psi, const d
 /* ---- --fast (recfourier_fast_oracle.cpp): nearest-pixel insertion + final blob convolution, single precision,
  * restating ProgRecFourierGPU with useFast (reconstruction_adapt_cuda/reconstruct_fourier_gpu.cpp and the device
  * functions of reconstruction_cuda/cuda_gpu_reconstruct_fourier.cpp:391-503, 655-760). */
+/* one traverse space (reconstruct_fourier_projection_traverse_space.h:37-59) as plain data; same layout as refk_space in
+ * oracle/ref_harness.cu */
+typedef struct {
+    int32_t minX, minY, minZ, maxX, maxY, maxZ;
+    int32_t dir;                 /* 0 XY, 1 XZ, 2 YZ */
+    int32_t projectionIndex;
+    float maxDistanceSqr;
+    float unitNormal[3], topOrigin[3], bottomOrigin[3];
+    float transformInv[9];
+    float weight;
+} orf_space;
+
 void* orf_fast_create(const orf_config* cfg);
+/* use_fast = 0: host side of ProgRecFourierGPU WITHOUT --fast (traverse spaces with blob thickness, no final blob
+ * convolution); its device arithmetic is not restated: the temporary spaces come from the compiled reference kernel */
+void* orf_fast_create2(const orf_config* cfg, int use_fast);
+/* the buffer handed to processBufferGPU for n images; returns the number of images kept (zero-weight ones are skipped) */
+int orf_fast_export_buffer(void* h, const float* imgs, const orf_particle* meta, int n, float* FFTs, float* CTFs, float* mods,
+                           orf_space* spaces);
+void orf_fast_tables(void* h, float* blobTableSqrt, float* iDeltaSqrt, float* iw0);
 void orf_fast_destroy(void* h);
 void orf_fast_dims(void* h, int* S, int* sx, int* sy, int* Pv);
 void orf_fast_insert(void* h, const float* imgs, const orf_particle* meta, int n);

@@ -50,7 +50,7 @@ inline void multiply(const float t[9], P3& p) {
 struct TraverseSpace {           // reconstruct_fourier_projection_traverse_space.h:37-59
     int minX, minY, minZ, maxX, maxY, maxZ;
     int dir;                     // 0 = XY, 1 = XZ, 2 = YZ
-    P3 unitNormal, bottomOrigin;
+    P3 unitNormal, bottomOrigin, topOrigin;
     float maxDistanceSqr;
     float transformInv[9];
     float weight;
@@ -66,8 +66,11 @@ struct FastOracle {
     float iDeltaSqrt;
     std::vector<cf> tempVolume;  // (S+1)^3 [z][y][x]
     std::vector<float> tempWeights;
+    bool useFast = true;         // false: the GPU program WITHOUT --fast (blob applied per voxel by the device code, which
+                                 // is not restated here: the temporary spaces then come from the compiled reference kernel,
+                                 // oracle/ref_harness.cu); this object supplies its host side (buffers before, finish after)
 
-    explicit FastOracle(const orf_config& c) : cfg(c) {
+    explicit FastOracle(const orf_config& c, bool fast = true) : cfg(c), useFast(fast) {
         N = c.img_size;
         Pv = (int)(N * c.pad_vol);                                              // G:229
         size_t conserveRows = (size_t)std::ceil((double)Pv * c.max_resolution * 2.0);   // G:230-232
@@ -138,7 +141,8 @@ struct FastOracle {
     void computeTraverseSpace(const float transform[9], const float transformInv[9], TraverseSpace& sp) const {
         P3 cuboid[8], AABB[2];
         P3 origin = {S / 2.f, S / 2.f, S / 2.f};        // maxVolumeIndexX == maxVolumeIndexYZ while inserting
-        createProjectionCuboid(cuboid, (float)sx, (float)sy, 0.f);
+        const float blobSize = useFast ? 0.f : (float)cfg.blob_radius;              // G:775
+        createProjectionCuboid(cuboid, (float)sx, (float)sy, blobSize);
         for (int i = 0; i < 8; ++i) multiply(transform, cuboid[i]);
         for (int i = 0; i < 8; ++i) {
             cuboid[i].x += origin.x;
@@ -152,8 +156,9 @@ struct FastOracle {
         sp.maxZ = (int)std::ceil(AABB[1].z);
         sp.maxY = (int)std::ceil(AABB[1].y);
         sp.maxX = (int)std::ceil(AABB[1].x);
+        sp.topOrigin = cuboid[4];
         sp.bottomOrigin = cuboid[0];
-        float e = (float)sx + 0.f;
+        float e = (float)sx + blobSize;
         sp.maxDistanceSqr = e * e;
         std::memcpy(sp.transformInv, transformInv, sizeof(float) * 9);
         sp.unitNormal = {0.f, 0.f, 1.f};
@@ -257,82 +262,124 @@ struct FastOracle {
         o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
     }
 
-    // ---- prepareBuffer G:323-415 + processBufferKernel D:900-950 for n images
+    // ---- prepareBuffer G:323-415 for one image: cropped + centred transform, CTF tables, traverse spaces.
+    // Returns false when the image is skipped (zero weight, G:351-353).
+    bool prepare(const float* image, const orf_particle& p, std::vector<double>& F, cf* img, float* CTF, float* mod,
+                 std::vector<TraverseSpace>& spaces) const {
+        const int Xh = Pv / 2 + 1;
+        const float maxResolutionSqr = (float)(cfg.max_resolution * cfg.max_resolution);   // float member (reconstruct_fourier_gpu.h)
+        const double iTs = 1.0 / cfg.sampling;
+        if (cfg.use_weights && (float)p.weight == 0.f) return false;                        // G:351-353
+        double Ainv[9];
+        orf_preprocess(geo, image, &p, F.data(), Ainv);                                     // G:384-394 (double FFT, 1/size)
+        // cropAndShift G:292-321
+        std::fill(img, img + (size_t)sx * sy, cf(0, 0));
+        const int halfY = Pv / 2;
+        for (int i = 0; i < Pv; ++i)
+            for (int j = 0; j < sx; ++j) {
+                if (!(i < sx || i >= Pv - sx)) continue;
+                double re = F[2 * ((size_t)i * Xh + j)], im = F[2 * ((size_t)i * Xh + j) + 1];
+                double f0 = orf_idx2digfreq(j, Pv), f1 = orf_idx2digfreq(i, Pv);
+                if (f0 * f0 + f1 * f1 > maxResolutionSqr) re = im = 0.0;
+                int myPadI = (i < halfY) ? i + sx : i - Pv + sx;
+                img[(size_t)myPadI * sx + j] = cf((float)re, (float)im);
+            }
+        // computeCTFCorrection G:552-593 (its x loop runs to fftSizeY and spills into the following rows, which are
+        // rewritten afterwards: the surviving values are the ones of x < fftSizeX)
+        if (cfg.use_ctf) {
+            for (int y = 0; y < sy; ++y) {
+                float freqY = (y - (Pv / 2.f)) / (float)Pv;
+                for (int x = 0; x < sx; ++x) {
+                    float freqX = (float)orf_idx2digfreq(x, Pv);
+                    float CTFVal, modulatorVal = 1.f;
+                    CTFVal = (float)orf_ctf_value(&p, freqX * iTs, freqY * iTs);
+                    if (std::isnan(CTFVal)) {
+                        if (x == 0 && y == 0) modulatorVal = CTFVal = 1.0f;
+                        else modulatorVal = CTFVal = 0.0f;
+                    }
+                    if (std::fabs(CTFVal) < cfg.min_ctf) {
+                        modulatorVal = std::fabs(CTFVal);
+                        CTFVal = (CTFVal >= 0) ? 1.f : -1.f;                             // SGN
+                    } else {
+                        CTFVal = (float)(1.0 / CTFVal);
+                    }
+                    if (cfg.phase_flipped) CTFVal = std::fabs(CTFVal);
+                    CTF[(size_t)y * sx + x] = CTFVal;
+                    mod[(size_t)y * sx + x] = modulatorVal;
+                }
+            }
+        }
+        const int nSym = (int)(sym.size() / 9);
+        spaces.resize(nSym);
+        for (int s = 0; s < nSym; ++s) {                                                 // G:363-377
+            double A_SL[9], A_SLInv[9];
+            const double* R = &sym[9 * s];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) {
+                    double t = 0;
+                    for (int c = 0; c < 3; ++c) t += R[a * 3 + c] * Ainv[c * 3 + b];
+                    A_SL[a * 3 + b] = t;
+                }
+            inv3(A_SL, A_SLInv);
+            float transf[9], transfInv[9];
+            for (int a = 0; a < 9; ++a) {
+                transf[a] = (float)A_SL[a];
+                transfInv[a] = (float)A_SLInv[a];
+            }
+            computeTraverseSpace(transf, transfInv, spaces[s]);
+            spaces[s].weight = cfg.use_weights ? (float)p.weight : 1.0f;
+        }
+        return true;
+    }
+
+    // ---- prepareBuffer + processBufferKernel D:900-950 for n images (the --fast device arithmetic, restated)
     void insert(const float* imgs, const orf_particle* meta, int n) {
         const int Xh = Pv / 2 + 1;
         std::vector<double> F((size_t)Pv * Xh * 2);
         std::vector<cf> img((size_t)sx * sy);
-        std::vector<float> CTF, mod;
-        if (cfg.use_ctf) {
-            CTF.resize((size_t)sx * sy);
-            mod.resize((size_t)sx * sy);
-        }
-        const float maxResolutionSqr = (float)(cfg.max_resolution * cfg.max_resolution);   // float member (reconstruct_fourier_gpu.h)
-        const double iTs = 1.0 / cfg.sampling;
+        std::vector<float> CTF((size_t)sx * sy), mod((size_t)sx * sy);
+        std::vector<TraverseSpace> spaces;
         for (int k = 0; k < n; ++k) {
-            const orf_particle& p = meta[k];
-            if (cfg.use_weights && (float)p.weight == 0.f) continue;                        // G:351-353
-            double Ainv[9];
-            orf_preprocess(geo, imgs + (size_t)k * N * N, &p, F.data(), Ainv);              // G:384-394 (double FFT, 1/size)
-            // cropAndShift G:292-321
-            std::fill(img.begin(), img.end(), cf(0, 0));
-            const int halfY = Pv / 2;
-            for (int i = 0; i < Pv; ++i)
-                for (int j = 0; j < sx; ++j) {
-                    if (!(i < sx || i >= Pv - sx)) continue;
-                    double re = F[2 * ((size_t)i * Xh + j)], im = F[2 * ((size_t)i * Xh + j) + 1];
-                    double f0 = orf_idx2digfreq(j, Pv), f1 = orf_idx2digfreq(i, Pv);
-                    if (f0 * f0 + f1 * f1 > maxResolutionSqr) re = im = 0.0;
-                    int myPadI = (i < halfY) ? i + sx : i - Pv + sx;
-                    img[(size_t)myPadI * sx + j] = cf((float)re, (float)im);
-                }
-            // computeCTFCorrection G:552-593 (its x loop runs to fftSizeY and spills into the following rows, which are
-            // rewritten afterwards: the surviving values are the ones of x < fftSizeX)
-            if (cfg.use_ctf) {
-                for (int y = 0; y < sy; ++y) {
-                    float freqY = (y - (Pv / 2.f)) / (float)Pv;
-                    for (int x = 0; x < sx; ++x) {
-                        float freqX = (float)orf_idx2digfreq(x, Pv);
-                        float CTFVal, modulatorVal = 1.f;
-                        CTFVal = (float)orf_ctf_value(&p, freqX * iTs, freqY * iTs);
-                        if (std::isnan(CTFVal)) {
-                            if (x == 0 && y == 0) modulatorVal = CTFVal = 1.0f;
-                            else modulatorVal = CTFVal = 0.0f;
-                        }
-                        if (std::fabs(CTFVal) < cfg.min_ctf) {
-                            modulatorVal = std::fabs(CTFVal);
-                            CTFVal = (CTFVal >= 0) ? 1.f : -1.f;                             // SGN
-                        } else {
-                            CTFVal = (float)(1.0 / CTFVal);
-                        }
-                        if (cfg.phase_flipped) CTFVal = std::fabs(CTFVal);
-                        CTF[(size_t)y * sx + x] = CTFVal;
-                        mod[(size_t)y * sx + x] = modulatorVal;
-                    }
-                }
-            }
-            const int nSym = (int)(sym.size() / 9);
-            for (int s = 0; s < nSym; ++s) {                                                 // G:363-377
-                double A_SL[9], A_SLInv[9];
-                const double* R = &sym[9 * s];
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b) {
-                        double t = 0;
-                        for (int c = 0; c < 3; ++c) t += R[a * 3 + c] * Ainv[c * 3 + b];
-                        A_SL[a * 3 + b] = t;
-                    }
-                inv3(A_SL, A_SLInv);
-                float transf[9], transfInv[9];
-                for (int a = 0; a < 9; ++a) {
-                    transf[a] = (float)A_SL[a];
-                    transfInv[a] = (float)A_SLInv[a];
-                }
-                TraverseSpace sp;
-                computeTraverseSpace(transf, transfInv, sp);
-                sp.weight = cfg.use_weights ? (float)p.weight : 1.0f;
+            if (!prepare(imgs + (size_t)k * N * N, meta[k], F, img.data(), CTF.data(), mod.data(), spaces)) continue;
+            for (const TraverseSpace& sp : spaces)
                 processProjection(img.data(), cfg.use_ctf ? CTF.data() : nullptr, cfg.use_ctf ? mod.data() : nullptr, sp);
-            }
         }
+    }
+
+    // ---- the buffer ProgRecFourierGPU hands to processBufferGPU (RecFourierBufferData: FFTs, CTFs, modulators, spaces) for
+    // n images; returns the number of images kept.  FFTs: kept x sy x sx complex, CTFs / mods: kept x sy x sx (untouched
+    // without CTF), spaces: kept x nSym
+    int export_buffer(const float* imgs, const orf_particle* meta, int n, float* FFTs, float* CTFs, float* mods, orf_space* out) const {
+        const int Xh = Pv / 2 + 1;
+        std::vector<double> F((size_t)Pv * Xh * 2);
+        std::vector<float> CTF((size_t)sx * sy), mod((size_t)sx * sy);
+        std::vector<TraverseSpace> spaces;
+        const size_t px = (size_t)sx * sy;
+        const int nSym = (int)(sym.size() / 9);
+        int kept = 0;
+        for (int k = 0; k < n; ++k) {
+            cf* img = reinterpret_cast<cf*>(FFTs) + px * kept;
+            if (!prepare(imgs + (size_t)k * N * N, meta[k], F, img, CTF.data(), mod.data(), spaces)) continue;
+            if (cfg.use_ctf) {
+                std::memcpy(CTFs + px * kept, CTF.data(), sizeof(float) * px);
+                std::memcpy(mods + px * kept, mod.data(), sizeof(float) * px);
+            }
+            for (int s = 0; s < nSym; ++s) {
+                const TraverseSpace& sp = spaces[s];
+                orf_space& o = out[(size_t)kept * nSym + s];
+                o.minX = sp.minX; o.minY = sp.minY; o.minZ = sp.minZ; o.maxX = sp.maxX; o.maxY = sp.maxY; o.maxZ = sp.maxZ;
+                o.dir = sp.dir;
+                o.projectionIndex = kept;
+                o.maxDistanceSqr = sp.maxDistanceSqr;
+                o.unitNormal[0] = sp.unitNormal.x; o.unitNormal[1] = sp.unitNormal.y; o.unitNormal[2] = sp.unitNormal.z;
+                o.topOrigin[0] = sp.topOrigin.x; o.topOrigin[1] = sp.topOrigin.y; o.topOrigin[2] = sp.topOrigin.z;
+                o.bottomOrigin[0] = sp.bottomOrigin.x; o.bottomOrigin[1] = sp.bottomOrigin.y; o.bottomOrigin[2] = sp.bottomOrigin.z;
+                std::memcpy(o.transformInv, sp.transformInv, sizeof(float) * 9);
+                o.weight = sp.weight;
+            }
+            ++kept;
+        }
+        return kept;
     }
 
     // ---- applyBlob G:623-661 on the half space [S+1][S+1][X+1]
@@ -395,8 +442,10 @@ struct FastOracle {
         const int X = S / 2;                                                                  // G:698
         std::vector<float> W = mirrorAndCrop(tempWeights, X, [](float v) { return v; });
         std::vector<cf> V = mirrorAndCrop(tempVolume, X, [](cf v) { return std::conj(v); });
-        applyBlob(V, X);                                                                      // G:881-884
-        applyBlob(W, X);
+        if (useFast) {                                                                        // G:881-884
+            applyBlob(V, X);
+            applyBlob(W, X);
+        }
         const size_t oy = (size_t)(X + 1), oz = (size_t)(S + 1) * (X + 1);
         for (int z = 0; z <= S; ++z)                                                          // forceHermitianSymmetry G:732-749
             for (int y = 0; y <= S / 2; ++y) {
@@ -438,6 +487,20 @@ extern "C" {
 
 void* orf_fast_create(const orf_config* cfg) {
     try { return new FastOracle(*cfg); } catch (...) { return nullptr; }
+}
+void* orf_fast_create2(const orf_config* cfg, int use_fast) {
+    try { return new FastOracle(*cfg, use_fast != 0); } catch (...) { return nullptr; }
+}
+int orf_fast_export_buffer(void* h, const float* imgs, const orf_particle* meta, int n, float* FFTs, float* CTFs, float* mods,
+                           orf_space* spaces) {
+    return static_cast<FastOracle*>(h)->export_buffer(imgs, meta, n, FFTs, CTFs, mods, spaces);
+}
+void orf_fast_tables(void* h, float* blobTableSqrt, float* iDeltaSqrt, float* iw0) {
+    FastOracle* o = static_cast<FastOracle*>(h);
+    std::memcpy(blobTableSqrt, o->blobTableSqrt.data(), sizeof(float) * kTable);
+    *iDeltaSqrt = o->iDeltaSqrt;
+    // iw0 = 1 / kaiser_Fourier_value(0, blobnormalized.radius, alpha, order)  (G:241-243); the table already carries it
+    *iw0 = (float)(1.0 / orf_kaiser_fourier_value(0.0, o->cfg.blob_radius / (o->cfg.pad_proj / o->cfg.pad_vol), o->cfg.blob_alpha, o->cfg.blob_order));
 }
 void orf_fast_destroy(void* h) { delete static_cast<FastOracle*>(h); }
 void orf_fast_dims(void* h, int* S, int* sx, int* sy, int* Pv) {

@@ -274,3 +274,31 @@ def test_fused_fft_chain_matches_cufft_chain(monkeypatch):
         assert np.linalg.norm(Wa - Wb) <= 3e-6 * np.linalg.norm(Wb)
         a.close()
         b.close()
+
+
+def test_two_handles_on_one_device_run_concurrently(oracle_mod):
+    """The plane tables of a gather launch travel as kernel parameters, so handles share no device state: two
+    reconstructions interleaved on one GPU (the reference runs N host threads on N streams, reconstruct_fourier_gpu.cpp:
+    417-473) give the results of two separate runs, bit for bit."""
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    N, n = 64, 300
+    da = synth.make_dataset(n, N, seed=71, ctf=True)
+    db = synth.make_dataset(n, N, seed=72, sym="c3")
+    pa, pb = make_particles(n, **_cols(da, True)), make_particles(n, **_cols(db, False))
+    ref = []
+    for d, p, kw in ((da, pa, dict(use_ctf=True, sampling=da["sampling"])), (db, pb, dict(sym_matrices=geometry.point_group_matrices("c3")))):
+        r = Reconstructor(N, max_batch=50, **kw)
+        r.insert(d["images"], p)
+        ref.append(r.accumulators())
+        r.close()
+    a = Reconstructor(N, max_batch=50, use_ctf=True, sampling=da["sampling"])
+    b = Reconstructor(N, max_batch=50, sym_matrices=geometry.point_group_matrices("c3"))
+    for i0 in range(0, n, 100):          # asynchronous inserts, interleaved: the kernels of a and b overlap on the device
+        a.insert(da["images"][i0:i0 + 100], pa[i0:i0 + 100])
+        b.insert(db["images"][i0:i0 + 100], pb[i0:i0 + 100])
+    Va, Wa = a.accumulators()
+    Vb, Wb = b.accumulators()
+    a.close()
+    b.close()
+    assert np.array_equal(Va, ref[0][0]) and np.array_equal(Wa, ref[0][1])
+    assert np.array_equal(Vb, ref[1][0]) and np.array_equal(Wb, ref[1][1])

@@ -1,0 +1,96 @@
+"""GPU tests against the REFERENCE's own CUDA kernel (run with -m gpu).
+
+oracle/_ref/librefkernel.so is the reference's translation unit reconstruction_cuda/cuda_gpu_reconstruct_fourier.cpp
+compiled for sm_100a from /root/reference by oracle/build_ref.py (the C++ CPU program cannot be built here: xmippCore is
+absent).  It pins two things to reference CODE rather than to a restatement:
+
+  * --fast: the temporary volume / weights of the reference's processBufferKernel<useFast> on the buffers the restated
+    host side prepares == oracle/recfourier_fast_oracle.cpp's CPU restatement of that device code (and therefore the
+    product's k_fast_insert, which tests/test_gpu_fast.py holds against the restatement);
+  * the exact path: the reference kernel WITHOUT --fast (per-voxel Kaiser-Bessel blob gather, processVoxelBlob,
+    :510-652) is a second, independent implementation of the interpolation the CPU program performs by scattering
+    (reconstruct_fourier.cpp:586-792).  Its temporary spaces, finished by the restated host code of ProgRecFourierGPU
+    (mirrorAndCrop, forceHermitianSymmetry, processWeights, convertToExpectedSpace, inverse FFT, gridding correction),
+    give a map that must agree with the product's and with the oracle's: a shared misreading of the blob tables, the
+    Hermitian fold or the weighting in oracle/ and xmipp3_b200/ would show up here."""
+import numpy as np
+import pytest
+
+from xmipp3_b200 import geometry, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def refk():
+    from oracle import ref_kernel
+    if not ref_kernel.available():
+        pytest.skip("oracle/_ref/librefkernel.so not built (needs /root/reference at build time)")
+    return ref_kernel
+
+
+def _cols(d, ctf):
+    cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], shift_x=d["shift_x"], shift_y=d["shift_y"])
+    if ctf:
+        cols.update(d["ctf"])
+    return cols
+
+
+@pytest.mark.parametrize("case", [dict(N=32, n=60, ctf=True), dict(N=64, n=40, ctf=False, shifts=True), dict(N=32, n=10, sym="c3")],
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_reference_kernel_fast_equals_the_fast_restatement(oracle_mod, refk, case):
+    case = dict(case)
+    N, n, ctf, sym = case.pop("N"), case.pop("n"), case.pop("ctf", False), case.pop("sym", None)
+    d = synth.make_dataset(n, N, seed=11, ctf=ctf, shifts=case.pop("shifts", False), sym=sym)
+    p = oracle_mod.make_particles(n, **_cols(d, ctf))
+    kw = dict(use_ctf=ctf, sampling=d["sampling"], sym_matrices=geometry.point_group_matrices(sym) if sym else None)
+    cpu = oracle_mod.FastOracle(N, **kw)
+    cpu.insert(d["images"], p)
+    Vc, Wc = cpu.temp_spaces()
+    k = refk.RefKernel(oracle_mod.FastOracle(N, **kw), max_images=25)      # --bufferSize default (reconstruct_fourier_gpu.cpp:68)
+    try:
+        k.process(d["images"], p)
+        Vr, Wr = k.temp_spaces()
+    finally:
+        k.close()
+    assert np.array_equal(Wr != 0, Wc != 0)                  # the same voxels are touched
+    assert np.abs(Wr - Wc).max() <= 2e-6 * np.abs(Wc).max()  # float atomics: the order of the additions differs
+    assert np.linalg.norm(Vr - Vc) <= 2e-6 * np.linalg.norm(Vc)
+
+
+@pytest.mark.parametrize("case", [dict(N=64, n=300, ctf=True), dict(N=64, n=200, ctf=False), dict(N=32, n=40, sym="d2")],
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_reference_blob_kernel_agrees_with_the_exact_path(oracle_mod, refk, case):
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    case = dict(case)
+    N, n, ctf, sym = case.pop("N"), case.pop("n"), case.pop("ctf", False), case.pop("sym", None)
+    d = synth.make_dataset(n, N, seed=12, ctf=ctf, sym=sym)
+    cols = _cols(d, ctf)
+    p = oracle_mod.make_particles(n, **cols)
+    mats = geometry.point_group_matrices(sym) if sym else None
+    kw = dict(use_ctf=ctf, sampling=d["sampling"], sym_matrices=mats)
+    host = oracle_mod.FastOracle(N, use_fast=False, **kw)      # host side of ProgRecFourierGPU, no --fast
+    k = refk.RefKernel(host, max_images=25)
+    try:
+        k.process(d["images"], p)
+        Vr, Wr = k.temp_spaces()
+    finally:
+        k.close()
+    host.set_temp_spaces(Vr, Wr)
+    ref_map = host.finalize()
+    o = oracle_mod.Oracle(N, **kw)
+    o.insert(d["images"], p, threads=4, scheme="slabs")
+    oracle_map = o.finalize()
+    r = Reconstructor(N, **kw)
+    r.insert(d["images"], make_particles(n, **cols))
+    gpu_map = r.finalize()
+    r.close()
+    res = {"gpu_vs_refkernel": float(synth.rel_l2(gpu_map, ref_map)), "oracle_vs_refkernel": float(synth.rel_l2(oracle_map, ref_map)),
+           "gpu_vs_oracle": float(synth.rel_l2(gpu_map, oracle_map)),
+           "min_fsc_gpu_vs_refkernel": float(np.nanmin(synth.fsc(gpu_map, ref_map)[1:]))}
+    print(res)
+    # two different programs (single-precision gather with float atomics on a cropped cube vs double-precision scatter):
+    # the reference's own test tolerance between runs of this path is 1e-3 per voxel (tests/test.py:174-196)
+    assert res["gpu_vs_refkernel"] <= 1e-3, res
+    assert res["oracle_vs_refkernel"] <= 1e-3, res
+    assert res["min_fsc_gpu_vs_refkernel"] >= 0.999, res

@@ -108,7 +108,7 @@ def test_fp32_accumulation_20k_particles_box256(oracle_mod):
         img, cols = bench.synth_batch_torch(chunk, N, 7000 + 10 * c, dev, ctf=True)
         p = make_particles(chunk, **cols)
         torch.cuda.synchronize()
-        a.insert_device_ptr(img.data_ptr(), p)
+        a.insert_device_ptr(img.data_ptr(), p)      # a and b run concurrently on one device (independent handles)
         b.reset()
         b.insert_device_ptr(img.data_ptr(), p)
         V, W = b.accumulators()

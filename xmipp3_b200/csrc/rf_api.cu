@@ -54,6 +54,8 @@ struct ParamSlot {      // pinned host staging for one chunk's parameters
     FastSpace* fast = nullptr;     // --fast: traverse spaces of the chunk
     cudaEvent_t done = nullptr;
     bool used = false;
+    struct Launch { int cls, start, count; };
+    std::vector<Launch> launches;  // gather launches of the chunk: planesS / planesDp [start, start + count) are of class cls
 };
 
 #if RFB200_HAVE_NCCL_H
@@ -289,7 +291,7 @@ int fetch_params(rfb200_handle h, void* dst, const void* srcPinned, size_t bytes
 }
 
 template <int K, int CLS>
-int launch_sticks_kc(rfb200_handle h, const StickArgs& a, int grid) {
+int launch_sticks_kc(rfb200_handle h, const StickLaunch& a, int grid) {
     // only a CTF can damp (flag) a pixel: without it the gather runs the variant without the per-candidate flag test
     if (h->cfg.use_ctf) {
         RF_CUDA(h, cudaFuncSetAttribute(k_gather_sticks<K, CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStickSmem));
@@ -302,14 +304,14 @@ int launch_sticks_kc(rfb200_handle h, const StickArgs& a, int grid) {
     return RFB200_OK;
 }
 template <int K>
-int launch_sticks_k(rfb200_handle h, const StickArgs& a, int grid) {
-    switch (a.cls) {
+int launch_sticks_k(rfb200_handle h, const StickLaunch& a, int grid) {
+    switch (a.a.cls) {
         case 0: return launch_sticks_kc<K, 0>(h, a, grid);
         case 1: return launch_sticks_kc<K, 1>(h, a, grid);
         default: return launch_sticks_kc<K, 2>(h, a, grid);
     }
 }
-int launch_sticks(rfb200_handle h, const StickArgs& a, int grid) {
+int launch_sticks(rfb200_handle h, const StickLaunch& a, int grid) {
     switch (h->geo.K) {
         case 1: return launch_sticks_k<1>(h, a, grid);
         case 2: return launch_sticks_k<2>(h, a, grid);
@@ -448,26 +450,39 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         if (!rcf) rcf = fetch_params(h, h->dPlaneImg, s.planeImg, sizeof(int) * np);
     }
     if (!rcf) {
-        // per launch sub-range: stable sort of the planes by class (axis dominating the normal), components
-        // permuted to the (a,b,d) order of the class
-        for (int p0 = 0; p0 < np; p0 += kMaxPlanes) {
-            const int cnt = std::min(kMaxPlanes, np - p0);
-            int start[4] = {0, 0, 0, 0};
-            for (int k = 0; k < cnt; ++k) start[host::plane_class(s.planesD[p0 + k]) + 1]++;
-            for (int c = 0; c < 3; ++c) start[c + 1] += start[c];
-            int fill[3] = {start[0], start[1], start[2]};
-            float* soa = s.soaP + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
-            for (int k = 0; k < cnt; ++k) {
-                const int cls = host::plane_class(s.planesD[p0 + k]);
-                const int pos = fill[cls]++;
-                const int img = s.planeImg[p0 + k];
-                host::permute_plane(s.planesD[p0 + k], cls, img, s.img[img].weight, s.planesDp[p0 + pos], s.planesS[p0 + pos]);
-                const PlaneS& f = s.planesS[p0 + pos];
-                const float comp[9] = {f.e1a, f.e1b, f.e1d, f.e2a, f.e2b, f.e2d, f.na, f.nb, f.nd};
-                for (int c = 0; c < 9; ++c) soa[c * kMaxPlanes + pos] = comp[c];
+        // stable sort of the chunk's planes by class (axis dominating the normal), components permuted to the (a,b,d)
+        // order of the class; every class is then cut into launches of <= kLaunchPlanes planes of (nearly) equal size
+        int start[4] = {0, 0, 0, 0};
+        for (int k = 0; k < np; ++k) start[host::plane_class(s.planesD[k]) + 1]++;
+        for (int c = 0; c < 3; ++c) start[c + 1] += start[c];
+        int fill[3] = {start[0], start[1], start[2]};
+        for (int k = 0; k < np; ++k) {
+            const int cls = host::plane_class(s.planesD[k]);
+            const int pos = fill[cls]++;
+            const int img = s.planeImg[k];
+            host::permute_plane(s.planesD[k], cls, img, s.img[img].weight, s.planesDp[pos], s.planesS[pos]);
+        }
+        s.launches.clear();
+        for (int c = 0; c < 3; ++c) {
+            const int nc = start[c + 1] - start[c];
+            if (!nc) continue;
+            const int nl = (nc + kLaunchPlanes - 1) / kLaunchPlanes, base = nc / nl, rem = nc % nl;
+            int at = start[c];
+            for (int l = 0; l < nl; ++l) {
+                const int cnt = base + (l < rem ? 1 : 0);
+                s.launches.push_back({c, at, cnt});
+                at += cnt;
             }
         }
-        if (np) rcf = fetch_params(h, h->dPlanesDp, s.planesDp, sizeof(PlaneD) * np);
+        for (size_t g = 0; g < s.launches.size(); ++g) {
+            float* soa = s.soaP + g * 9 * kLaunchPlanes;
+            for (int k = 0; k < s.launches[g].count; ++k) {
+                const PlaneS& f = s.planesS[s.launches[g].start + k];
+                const float comp[9] = {f.e1a, f.e1b, f.e1d, f.e2a, f.e2b, f.e2d, f.na, f.nb, f.nd};
+                for (int c = 0; c < 9; ++c) soa[c * kLaunchPlanes + k] = comp[c];
+            }
+        }
+        if (!s.launches.empty()) rcf = fetch_params(h, h->dPlanesSoAp, s.soaP, sizeof(float) * 9 * kLaunchPlanes * s.launches.size());
         if (!rcf) rcf = fetch_params(h, h->dImgPlane0, s.imgPlane0, sizeof(int) * n);
     }
     if (rcf) return rcf;
@@ -507,50 +522,43 @@ Slice2Args make_slice_args(rfb200_handle h) {
 int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
     const Geometry& g = h->geo;
     int rc = RFB200_OK;
-    for (int p0 = 0; p0 < nPlanes; p0 += kMaxPlanes) {
-        const int np = std::min(kMaxPlanes, nPlanes - p0);
-        const float* soaChunk = slot->soaP + (size_t)(p0 / kMaxPlanes) * 9 * kMaxPlanes;
-        rc = fetch_params(h, h->dPlanesSoAp, soaChunk, sizeof(float) * 9 * kMaxPlanes);
-        if (!rc) rc = fetch_params(h, h->dPlanesSStage, slot->planesS + p0, sizeof(PlaneS) * np);
-        if (rc) return rc;
-        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planesS, h->dPlanesSStage, sizeof(PlaneS) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
-        RF_CUDA(h, cudaMemcpyToSymbolAsync(c_planesD, h->dPlanesDp + p0, sizeof(PlaneD) * np, 0, cudaMemcpyDeviceToDevice, h->compute));
-        RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, 3 * sizeof(int), h->compute));
-        int start[4] = {0, 0, 0, 0};
-        for (int k = 0; k < np; ++k) start[host::plane_class(slot->planesD[p0 + k]) + 1]++;
-        for (int c = 0; c < 3; ++c) start[c + 1] += start[c];
-        {
-            StageTimer t(h, Stage::GATHER, h->compute);
-            // the three classes touch the same voxels: launches are serialised on the stream, each owns its sticks
-            for (int cls = 0; cls < 3; ++cls) {
-                if (start[cls + 1] == start[cls] || h->nUnits[cls] == 0) continue;
-                StickArgs a{};
-                a.geo = g;
-                a.units = h->dUnits[cls]; a.nUnits = h->nUnits[cls]; a.counter = h->dStickCounters + cls;
-                a.cls = cls; a.kBegin = start[cls]; a.kEnd = start[cls + 1];
-                a.blobTable = h->dBlobTable;
-                a.planesSoA = h->dPlanesSoAp;
-                a.slices = h->dSlices2; a.rimTab = h->dRimTab + g.Rp;
-                a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
-                rc = launch_sticks(h, a, std::min(h->stickGrid, (h->nUnits[cls] + kStickWarps - 1) / kStickWarps));
-                if (rc) return rc;
-                h->nKernelLaunches += 1;
-                h->nGatherLaunches += 1;
-            }
-        }
-        if (h->nEdge) {
-            StageTimer t(h, Stage::EDGE, h->compute);
-            Edge2Args e{};
-            e.geo = g;
-            e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
-            e.planesD = h->dPlanesD + p0; e.planeImg = h->dPlaneImg + p0; e.img = h->dImg; e.nPlanes = np;
-            e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
-            e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
-            e.iDeltaD = h->tables.iDeltaSqrt;
-            k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->compute>>>(e);      // one warp per target voxel
-            RF_CUDA(h, cudaGetLastError());
+    if (nPlanes) {
+        RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, sizeof(int) * slot->launches.size(), h->compute));
+        StageTimer t(h, Stage::GATHER, h->compute);
+        // launches that touch the same voxels are serialised on the stream; each owns its sticks
+        static thread_local StickLaunch L;          // 31 KB parameter block, copied by the launch
+        for (size_t gi = 0; gi < slot->launches.size(); ++gi) {
+            const ParamSlot::Launch& la = slot->launches[gi];
+            if (h->nUnits[la.cls] == 0) continue;
+            StickArgs& a = L.a;
+            a = StickArgs{};
+            a.geo = g;
+            a.units = h->dUnits[la.cls]; a.nUnits = h->nUnits[la.cls]; a.counter = h->dStickCounters + gi;
+            a.cls = la.cls; a.nPlanes = la.count;
+            a.blobTable = h->dBlobTable;
+            a.planesSoA = h->dPlanesSoAp + gi * 9 * kLaunchPlanes;
+            a.slices = h->dSlices2; a.rimTab = h->dRimTab + g.Rp;
+            a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
+            std::memcpy(L.ps, slot->planesS + la.start, sizeof(PlaneS) * la.count);
+            std::memcpy(L.pd, slot->planesDp + la.start, sizeof(PlaneD) * la.count);
+            rc = launch_sticks(h, L, std::min(h->stickGrid, (h->nUnits[la.cls] + kStickWarps - 1) / kStickWarps));
+            if (rc) return rc;
             h->nKernelLaunches += 1;
+            h->nGatherLaunches += 1;
         }
+    }
+    if (h->nEdge && nPlanes) {
+        StageTimer t(h, Stage::EDGE, h->compute);
+        Edge2Args e{};
+        e.geo = g;
+        e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
+        e.planesD = h->dPlanesD; e.planeImg = h->dPlaneImg; e.img = h->dImg; e.nPlanes = nPlanes;
+        e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
+        e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
+        e.iDeltaD = h->tables.iDeltaSqrt;
+        k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->compute>>>(e);      // one warp per target voxel
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
     }
     if (h->dDamped && nPlanes) {
         StageTimer t(h, Stage::EDGE, h->compute);
@@ -980,18 +988,16 @@ int do_create(rfb200_handle h) {
             RF_CUDA(h, cudaMalloc(&h->dUnits[cls], sizeof(StickUnit) * units.size()));
             RF_CUDA(h, cudaMemcpy(h->dUnits[cls], units.data(), sizeof(StickUnit) * units.size(), cudaMemcpyHostToDevice));
         }
-        RF_CUDA(h, cudaMalloc(&h->dStickCounters, 3 * sizeof(int)));
+        RF_CUDA(h, cudaMalloc(&h->dStickCounters, sizeof(int) * (((size_t)h->chunkImages * h->nSymTot + kLaunchPlanes - 1) / kLaunchPlanes + 3)));
     }
     RF_CUDA(h, cudaMalloc(&h->dImg, sizeof(ImgParams) * CH));
     RF_CUDA(h, cudaMalloc(&h->dCtf, sizeof(CtfConsts) * CH));
     const size_t maxPlanes = CH * h->nSymTot;
-    const size_t nSub = (maxPlanes + kMaxPlanes - 1) / kMaxPlanes;
+    const size_t maxLaunches = (maxPlanes + kLaunchPlanes - 1) / kLaunchPlanes + 3;    // every class rounds up
     RF_CUDA(h, cudaMalloc(&h->dPlanesD, sizeof(PlaneD) * maxPlanes + 16));
     RF_CUDA(h, cudaMalloc(&h->dPlaneImg, sizeof(int) * maxPlanes + 16));
     {
-        RF_CUDA(h, cudaMalloc(&h->dPlanesDp, sizeof(PlaneD) * maxPlanes + 16));
-        RF_CUDA(h, cudaMalloc(&h->dPlanesSoAp, sizeof(float) * 9 * kMaxPlanes));
-        RF_CUDA(h, cudaMalloc(&h->dPlanesSStage, sizeof(PlaneS) * kMaxPlanes));
+        RF_CUDA(h, cudaMalloc(&h->dPlanesSoAp, sizeof(float) * 9 * kLaunchPlanes * maxLaunches));
         RF_CUDA(h, cudaMalloc(&h->dImgPlane0, sizeof(int) * CH + 16));
     }
     for (auto& s : h->slots) {
@@ -1002,7 +1008,7 @@ int do_create(rfb200_handle h) {
         {
             RF_CUDA(h, cudaMallocHost(&s.planesDp, sizeof(PlaneD) * maxPlanes + 16));
             RF_CUDA(h, cudaMallocHost(&s.planesS, sizeof(PlaneS) * maxPlanes + 16));
-            RF_CUDA(h, cudaMallocHost(&s.soaP, sizeof(float) * 9 * kMaxPlanes * nSub));
+            RF_CUDA(h, cudaMallocHost(&s.soaP, sizeof(float) * 9 * kLaunchPlanes * maxLaunches));
             RF_CUDA(h, cudaMallocHost(&s.imgPlane0, sizeof(int) * CH + 16));
         }
         RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));

@@ -23,10 +23,11 @@
 
 namespace rfb200 {
 
-// class-sorted planes of one launch, components permuted to (a,b,d): FP32 for the per-voxel arithmetic, FP64 for the
-// projection of the stick origins (24 KB + 36 KB of the 64 KB constant bank; every access is warp-uniform)
-__constant__ PlaneS c_planesS[kMaxPlanes];
-__constant__ PlaneD c_planesD[kMaxPlanes];
+// The planes of one launch (one class, components permuted to (a,b,d)) are kernel PARAMETERS: FP32 for the per-voxel
+// arithmetic, FP64 for the projection of the stick origins.  Parameters live in constant bank 0, so the (warp-uniform)
+// accesses are the same LDC / LDCU instructions a __constant__ array gives, but every launch owns its tables: two handles
+// or streams on one device never share state (the reference runs N host threads on N streams against one volume,
+// reconstruct_fourier_gpu.cpp:417-473).
 
 #ifndef RF_STICK_WARPS
 #define RF_STICK_WARPS 16
@@ -34,7 +35,7 @@ __constant__ PlaneD c_planesD[kMaxPlanes];
 constexpr int kStickWarps = RF_STICK_WARPS;
 constexpr int kStickThreads = kStickWarps * 32;
 constexpr size_t kStickSmem = (size_t)kStickWarps * kStickL * kStickCols * (sizeof(float2) + sizeof(float));
-static_assert(kStickL <= 64 && kStickL % 4 == 0, "touched-row mask is 64 bits; bricks are 4 deep along x and y");
+static_assert(kStickL <= 64 && kStickL % 4 == 0, "touched mask: one bit per two depths; bricks are 4 deep along x and y");
 constexpr double kFixedScale = 4294967296.0;   // 2^32 fixed point
 
 // rimTab entry of centred slice row i: (jPos+1) | (jNeg+1) << 14 | m0 << 28 with
@@ -151,9 +152,9 @@ struct StickArgs {
     int nUnits;
     int* counter;
     int cls;                     // 0: d = x, 1: d = y, 2: d = z
-    int kBegin, kEnd;            // planes [kBegin, kEnd) of c_planesS belong to this class
+    int nPlanes;                 // planes of this launch: StickLaunch::ps / pd [0, nPlanes)
     const float* blobTable;
-    const float* planesSoA;      // 9 x kMaxPlanes floats, same order and permutation (culling phase, lane <-> plane)
+    const float* planesSoA;      // 9 x kLaunchPlanes floats, same planes as SoA (culling phase, lane <-> plane)
     const float4* slices;        // slice format v2: overlapping pixel pairs
     const int* rimTab;           // already offset by +Rp: index with the centred row
     float2* Vb;
@@ -323,6 +324,186 @@ __device__ __forceinline__ void d_stick_window(const float4* __restrict__ p, con
     accW += w1;
 }
 
+// ---- packed single precision (sm_100: FADD2 / FMUL2 / FFMA2 operate on an aligned register pair and take a scalar
+// broadcast operand, so {x, x} pairs are free).  The gather is bound by instruction issue, not by the FP32 pipe: one
+// packed instruction does the work of two issue slots.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 d_pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void d_upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 d_add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 d_mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// Two adjacent candidates (tj = 2q, 2q+1) of one window row, fully predicated:
+//   S = dy + dx (one FADD2 with dy broadcast); idx = round(S) by the 2^23 trick (one FADD2); per candidate: accept test,
+//   table address (LEA), table load, V += w * (re, im), flag test fused into the predicate (LOP3.PAND), W += w (* multiplicity
+//   on the checked path).  (A predicated FFMA2 is lowered to FFMA2 + 2 SEL, so the complex update stays two scalar FFMAs.)
+//   Even candidates go to accumulator set A, odd ones to set B.
+struct PairAcc { float reA, imA, wA, reB, imB, wB; };
+template <bool kSlow, bool kFlags>
+__device__ __forceinline__ void d_pair(const float dy, const u64 dx2, const float sMax, const uint32_t tblAdj, const float4 px,
+                                       const float m0, const float m1, PairAcc& A) {
+    const u64 dy2 = d_pk(dy, dy);
+    const u64 magic2 = d_pk(8388608.0f, 8388608.0f);
+#define RF_PAIR_HEAD                                   \
+    "{\n\t"                                            \
+    ".reg .b64 s2, m2;\n\t"                            \
+    ".reg .f32 s0, s1, w0, w1;\n\t"                    \
+    ".reg .b32 i0, i1, t0, t1;\n\t"                    \
+    ".reg .pred p0, p1, q0, q1;\n\t"                   \
+    "add.rn.f32x2 s2, %6, %7;\n\t"                     \
+    "add.rn.f32x2 m2, s2, %8;\n\t"                     \
+    "mov.b64 {s0, s1}, s2;\n\t"                        \
+    "mov.b64 {i0, i1}, m2;\n\t"                        \
+    "setp.le.f32 p0, s0, %9;\n\t"                      \
+    "setp.le.f32 p1, s1, %9;\n\t"                      \
+    "shl.b32 i0, i0, 2;\n\t"                           \
+    "add.u32 i0, i0, %10;\n\t"                         \
+    "shl.b32 i1, i1, 2;\n\t"                           \
+    "add.u32 i1, i1, %10;\n\t"                         \
+    "@p0 ld.shared.f32 w0, [i0];\n\t"                  \
+    "@p1 ld.shared.f32 w1, [i1];\n\t"                  \
+    "@p0 fma.rn.f32 %0, w0, %11, %0;\n\t"              \
+    "@p0 fma.rn.f32 %1, w0, %12, %1;\n\t"              \
+    "@p1 fma.rn.f32 %3, w1, %13, %3;\n\t"              \
+    "@p1 fma.rn.f32 %4, w1, %14, %4;\n\t"
+#define RF_PAIR_OUT "+f"(A.reA), "+f"(A.imA), "+f"(A.wA), "+f"(A.reB), "+f"(A.imB), "+f"(A.wB)
+#define RF_PAIR_IN "l"(dy2), "l"(dx2), "l"(magic2), "f"(sMax), "r"(tblAdj), "f"(px.x), "f"(px.y), "f"(px.z), "f"(px.w)
+    if (kFlags) {
+        if (kSlow)
+            asm(RF_PAIR_HEAD
+                "lop3.and.b32 t0|q0, %15, 1, 0, 0x0C, p0;\n\t"
+                "lop3.and.b32 t1|q1, %16, 1, 0, 0x0C, p1;\n\t"
+                "@q0 fma.rn.f32 %2, w0, %17, %2;\n\t"
+                "@q1 fma.rn.f32 %5, w1, %18, %5;\n\t"
+                "}"
+                : RF_PAIR_OUT
+                : RF_PAIR_IN, "r"(__float_as_uint(px.x)), "r"(__float_as_uint(px.z)), "f"(m0), "f"(m1));
+        else
+            asm(RF_PAIR_HEAD
+                "lop3.and.b32 t0|q0, %15, 1, 0, 0x0C, p0;\n\t"
+                "lop3.and.b32 t1|q1, %16, 1, 0, 0x0C, p1;\n\t"
+                "@q0 add.rn.f32 %2, %2, w0;\n\t"
+                "@q1 add.rn.f32 %5, %5, w1;\n\t"
+                "}"
+                : RF_PAIR_OUT
+                : RF_PAIR_IN, "r"(__float_as_uint(px.x)), "r"(__float_as_uint(px.z)));
+    } else {
+        if (kSlow)
+            asm(RF_PAIR_HEAD
+                "@p0 fma.rn.f32 %2, w0, %15, %2;\n\t"
+                "@p1 fma.rn.f32 %5, w1, %16, %5;\n\t"
+                "}"
+                : RF_PAIR_OUT
+                : RF_PAIR_IN, "f"(m0), "f"(m1));
+        else
+            asm(RF_PAIR_HEAD
+                "@p0 add.rn.f32 %2, %2, w0;\n\t"
+                "@p1 add.rn.f32 %5, %5, w1;\n\t"
+                "}"
+                : RF_PAIR_OUT
+                : RF_PAIR_IN);
+    }
+#undef RF_PAIR_HEAD
+#undef RF_PAIR_OUT
+#undef RF_PAIR_IN
+}
+
+// One step of one column, second generation: the K x K candidate window of the lane's voxel, two candidates per asm
+// block.  p points at the window origin (16-byte aligned pixel pair); (da0, db0) is the offset of the projected voxel from
+// the window origin, h2s = h^2 * iDelta.  kSlow weighs every candidate with its multiplicity (0 outside the resolution
+// disc, 2 on column j = 0), looked up per window row.
+template <int K, bool kSlow, bool kFlags>
+__device__ __forceinline__ void d_stick_window2(const float4* __restrict__ p, const int pitch, const float da0, const float db0, const float h2s,
+                                                const float kI, const float sMax, const uint32_t tblAdj, const int jc, const int ic,
+                                                const int* __restrict__ rimTab, float& accRe, float& accIm, float& accW) {
+    constexpr int NP = (K + 1) / 2;
+    float dys[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        const float db = db0 - (float)q;
+        dys[q] = fmaf(kI * db, db, h2s);
+    }
+    // squared column offsets, two per register pair; lim[q]: a pair is needed iff dys <= sMax - min(dxs of the pair).  The
+    // load predicate carries a slack of 0.02 table steps, so that it can never be false for an accepted candidate whatever
+    // the rounding of dy + dx (S < 10^4, one ulp = 10^-3)
+    u64 dxs2[NP];
+    float lim[NP];
+    const u64 da2 = d_pk(da0, da0), kI2 = d_pk(kI, kI);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const u64 d = d_add2(da2, d_pk(-(float)(2 * q), -(float)(2 * q + 1)));
+        u64 v = d_mul2(d_mul2(kI2, d), d);
+        float lo, hi;
+        d_upk(v, lo, hi);
+        if (2 * q + 1 >= K) {          // odd window edge: the second candidate of the last pair does not exist
+            hi = 3.0e38f;
+            v = d_pk(lo, hi);
+        }
+        dxs2[q] = v;
+        lim[q] = (sMax + 0.02f) - fminf(lo, hi);
+    }
+    // The window is processed in groups of RF_WINDOW_ROWS rows (loads of a group, then its candidates): the live pixel
+    // registers are the dominant part of the register budget (16 warps per SM leave 128 registers per thread)
+#ifndef RF_WINDOW_ROWS
+#define RF_WINDOW_ROWS 2
+#endif
+    constexpr int G = RF_WINDOW_ROWS;
+    PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t0 = 0; t0 < K; t0 += G) {
+        float4 px[G][NP];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (t0 + g < K) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+#ifdef RF_STICK_UNCOND_LOADS
+                    px[g][q] = __ldg(p + (t0 + g) * pitch + 2 * q);
+#else
+                    // A pixel pair is fetched only if one of its two candidates can be accepted: fewer lanes per load
+                    // instruction means fewer cache lines (L1 wavefronts) per instruction.  The registers are zeroed
+                    // first: a conditionally written register is live across the whole step loop otherwise.
+                    px[g][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dys[t0 + g] <= lim[q]) px[g][q] = __ldg(p + (t0 + g) * pitch + 2 * q);
+#endif
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int ti = t0 + g;
+            if (ti < K) {
+                int rt = 0;
+                if (kSlow) rt = __ldg(rimTab + ic + ti);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    float m0 = 1.f, m1 = 1.f;
+                    if (kSlow) {
+                        m0 = d_rim_mult(rt, jc + 2 * q);
+                        m1 = d_rim_mult(rt, jc + 2 * q + 1);
+                    }
+                    d_pair<kSlow, kFlags>(dys[ti], dxs2[q], sMax, tblAdj, px[g][q], m0, m1, A);
+                }
+            }
+        }
+    }
+    accRe = A.reA + A.reB;
+    accIm = A.imA + A.imB;
+    accW = A.wA + A.wB;
+}
+
 // fire-and-forget adds to the accumulators: one writer per address per launch (exclusive stick ownership) and
 // launches are ordered on the stream, so the result is still bit-reproducible; no load latency in the write-out
 __device__ __forceinline__ void d_red_add2(float2* addr, float a, float b) {
@@ -332,7 +513,14 @@ __device__ __forceinline__ void d_red_add(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
-// A task = one plane crossing one stick.  Per-lane state of the column walk; `k` indexes c_planesS.
+struct StickLaunch {             // the whole parameter block of one launch (< 32,764 bytes)
+    StickArgs a;
+    PlaneS ps[kLaunchPlanes];
+    PlaneD pd[kLaunchPlanes];
+};
+static_assert(sizeof(StickLaunch) <= 32764, "kernel parameter space");
+
+// A task = one plane crossing one stick.  Per-lane state of the column walk; `k` indexes StickLaunch::ps.
 struct StickTask {
     int k;
     int ja0, jb0;          // integer pixel of the stick origin's projection
@@ -350,7 +538,7 @@ struct StickConsts {
 // window origin of the lane's voxel at depth tau: returns in-bounds flag, sets special (needs the multiplicity path)
 template <int K>
 __device__ __forceinline__ bool d_window_origin(const StickConsts& c, const StickTask& t, const PlaneS& pl, int tau, int& jw, int& iw,
-                                                float& ar, float& br, float& h, bool& special) {
+                                                float& ar, float& br, float& h, bool& special, float* aAbsOut = nullptr) {
     const float ft = (float)tau;
     ar = fmaf(ft, pl.e1d, t.arL);
     br = fmaf(ft, pl.e2d, t.brL);
@@ -362,6 +550,7 @@ __device__ __forceinline__ bool d_window_origin(const StickConsts& c, const Stic
     // inside the all-valid disc and away from column 0.
     const float Aabs = (float)t.ja0 + ar, Babs = (float)t.jb0 + br;
     special = (Aabs * Aabs + Babs * Babs > c.rimIn2) || (fabsf(Aabs) <= c.rhoCol0);
+    if (aAbsOut) *aAbsOut = Aabs;
     return (unsigned)jAbs <= (unsigned)(c.side - K) && (unsigned)iAbs <= (unsigned)(c.side - K);
 }
 template <int K>
@@ -374,12 +563,11 @@ __device__ __forceinline__ const float4* d_window_ptr(const StickConsts& c, cons
 // active lane is known to be in bounds and to need no multiplicity handling (both ends of each column were
 // tested; the conditions are convex along it).
 template <int K, bool kChecked, bool kFlags>
-__device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const StickTask& t, const int nIter, const float4* __restrict__ slices,
+__device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const StickTask& t, const PlaneS& pl, const int nIter, const float4* __restrict__ slices,
                                                const int imgStride, const int* __restrict__ rimTab, float2* accV, float* accW, const int col) {
-    const PlaneS& pl = c_planesS[t.k];
     const float4* sl = slices + (size_t)pl.img * imgStride;
     const float weight = pl.weight;
-    uint64_t touched = 0;
+    uint32_t touched = 0;          // bit b <-> depths 2b, 2b + 1 of the stick hold something
     for (int s = 0; s < nIter; ++s) {
         const int tau = t.tauLo + 2 * s;
         int jw, iw;
@@ -390,28 +578,35 @@ __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const Stick
         bool anySlow = false;
         if (kChecked) anySlow = __any_sync(0xffffffffu, ok && special);
         if (ok) {
-            float dxs[K], dys[K];
             const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
             const float h2s = h * h * c.iDelta;
+            const float4* p = d_window_ptr<K>(c, sl, t, jw, iw);
+            float accRe = 0.f, accIm = 0.f, accWt = 0.f;
+#ifdef RF_GATHER_V1
+            float dxs[K], dys[K];
 #pragma unroll
             for (int q = 0; q < K; ++q) {
                 const float da = da0 - (float)q, db = db0 - (float)q;
                 dxs[q] = c.kI * da * da;
                 dys[q] = fmaf(c.kI * db, db, h2s);
             }
-            const float4* p = d_window_ptr<K>(c, sl, t, jw, iw);
-            float accRe = 0.f, accIm = 0.f, accWt = 0.f;
             if (kChecked && anySlow)
                 d_stick_window<K, true, kFlags>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
             else
                 d_stick_window<K, false, kFlags>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+#else
+            if (kChecked && anySlow)
+                d_stick_window2<K, true, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+            else
+                d_stick_window2<K, false, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+#endif
             const int o = tau * kStickCols + col;
             float2 v = accV[o];
             v.x += accRe;
             v.y += accIm;
             accV[o] = v;
             accW[o] = fmaf(weight, accWt, accW[o]);
-            touched |= 1ull << tau;
+            touched |= 1u << (tau >> 1);
         }
     }
     return touched;
@@ -423,7 +618,8 @@ __device__ __forceinline__ uint64_t d_task_run(const StickConsts& c, const Stick
 #define RF_STICK_BOUNDS __launch_bounds__(kStickThreads, 1)
 #endif
 template <int K, int CLS, bool kFlags>
-__global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArgs a) {
+__global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLaunch L) {
+    const StickArgs& a = L.a;
     const Geometry& geo = a.geo;
     __shared__ __align__(16) float tbl[kBlobTable];   // static: its shared address is a compile-time constant
     __shared__ __align__(8) unsigned long long tblBar;    // mbarrier of the table's bulk copy
@@ -523,15 +719,16 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
         }
         int tauMin = max(tMin - T0c, 0), tauMax = min(tMax - T0c, kStickL - 1);
         if (!colOk) tauMax = -1;
-        uint64_t touched = 0;
+        uint32_t touched = 0;
 
         // ---- planes of this class: lane <-> plane culling, then the warp walks the hits in plane order
         const float cA = (float)A0c + hA, cB = (float)B0c + hB, cD = (float)T0c + hD;
-        for (int kb = a.kBegin; kb < a.kEnd; kb += 32) {
+        for (int kb = 0; kb < a.nPlanes; kb += 32) {
             const int kk = kb + lane;
             bool hit = false;
-            if (kk < a.kEnd) {
+            if (kk < a.nPlanes) {
                 const float* s = a.planesSoA + kk;
+                constexpr int kMaxPlanes = kLaunchPlanes;
                 const float na = __ldg(s + 6 * kMaxPlanes), nb = __ldg(s + 7 * kMaxPlanes), nd = __ldg(s + 8 * kMaxPlanes);
                 const float hc = cA * na + cB * nb + cD * nd;
                 const float supp = hA * fabsf(na) + hB * fabsf(nb) + hD * fabsf(nd);
@@ -546,8 +743,8 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
                 const int k = kb + __ffs(m) - 1;
                 m &= m - 1;
                 // ---- set up task k
-                const PlaneS& pl = c_planesS[k];
-                const PlaneD& pd = c_planesD[k];
+                const PlaneS& pl = L.ps[k];
+                const PlaneD& pd = L.pd[k];
                 const double a0 = A0c * pd.e1[0] + B0c * pd.e1[1] + T0c * pd.e1[2];
                 const double b0 = A0c * pd.e2[0] + B0c * pd.e2[1] + T0c * pd.e2[2];
                 const double h0 = A0c * pd.n[0] + B0c * pd.n[1] + T0c * pd.n[2];
@@ -571,26 +768,29 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
                 bool plain = true;
                 if (t.tauLo <= t.tauHi) {
                     const int last = t.tauLo + ((t.tauHi - t.tauLo) & ~1);
+                    float aEnd[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         int jw, iw;
                         float ar, br, h;
                         bool special;
-                        const bool inb = d_window_origin<K>(c, t, pl, e ? last : t.tauLo, jw, iw, ar, br, h, special);
+                        const bool inb = d_window_origin<K>(c, t, pl, e ? last : t.tauLo, jw, iw, ar, br, h, special, &aEnd[e]);
                         plain = plain && inb && !special;
                     }
+                    // "away from column 0" is the union of two half planes: both ends must lie in the SAME one (a steep
+                    // column can enter the strip |alpha| <= rho between two ends that are outside it on opposite sides)
+                    plain = plain && (aEnd[0] * aEnd[1] > 0.f);
                 }
                 // which of a column's two lanes owns an accumulator depends on the parity of the column's first depth in
                 // THIS plane, so consecutive tasks may touch the same shared address from different lanes: order them
                 __syncwarp();
-                if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false, kFlags>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
-                else touched |= d_task_run<K, true, kFlags>(c, t, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false, kFlags>(c, t, pl, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                else touched |= d_task_run<K, true, kFlags>(c, t, pl, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
             }
         }
 
         // ---- write-out: one coalesced reduction per touched brick of the stick (blocked layout)
-        touched = (uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)touched) |
-                  ((uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)(touched >> 32)) << 32);
+        touched = __reduce_or_sync(0xffffffffu, touched);
         if (touched) {
             __syncwarp();
             const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
@@ -600,7 +800,7 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickArg
             constexpr int nBa = kStickA / 4, nBb = kStickB / spanB, nBt = kStickL / spanT;
 #pragma unroll 1
             for (int bt = 0; bt < nBt; ++bt) {
-                const uint64_t rows = ((1ull << spanT) - 1ull) << (bt * spanT);
+                const uint32_t rows = ((1u << (spanT / 2)) - 1u) << (bt * (spanT / 2));
                 if (!(touched & rows)) continue;
 #pragma unroll
                 for (int bb = 0; bb < nBb; ++bb) {
