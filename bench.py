@@ -214,6 +214,162 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------------- other configurations, scaling, checks
+OTHER_CONFIGS = [
+    # BASELINE.json configs 1, 2, 4, 5 (config 3 is the headline).  batch = particles per step and GPU
+    dict(name="config[0]: 64x64 phantom projections, padding 2, C1", box=64, sym="c1", ctf=False, shifts=False, batch=1000, steps=3, chunk=1024),
+    dict(name="config[1]: 128x128 particles with CTF + integer shifts, C1", box=128, sym="c1", ctf=True, shifts=True, batch=2048, steps=3, chunk=1024),
+    dict(name="config[3]: 256x256 particles, D7 (14 insertions per image)", box=256, sym="d7", ctf=False, shifts=False, batch=512, steps=2, chunk=512),
+    dict(name="config[4]: 512x512 particles, padding 2 (1024^3 volume)", box=512, sym="c1", ctf=False, shifts=False, batch=512, steps=2, chunk=256),
+]
+
+
+def measure_other_config(cfg, dev, local, rank, world, max_over_ranks, barrier_all):
+    """Short device-resident measurement of one of BASELINE's other configurations (same metric, same timing rules:
+    1 warm-up pass over each of the two batches, `steps` timed passes, CUDA events on the library's stream, max over
+    ranks).  Every batch is larger than L2 except config[0] (16 MB per batch; two batches alternate)."""
+    import torch
+    from xmipp3_b200 import geometry
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    box, B, K = cfg["box"], cfg["batch"], cfg["steps"]
+    mats = geometry.point_group_matrices(cfg["sym"]) if cfg["sym"] != "c1" else None
+    n_ops = 1 + (len(mats) if mats is not None else 0)
+    batches = []
+    for s in range(2):
+        img, cols = synth_batch_torch(B, box, 50000 + 1000 * rank + 10 * s, dev, ctf=cfg["ctf"])
+        if cfg["shifts"]:
+            rng = np.random.default_rng(7 + s)
+            cols["shift_x"] = rng.integers(-5, 6, B).astype(np.float64)
+            cols["shift_y"] = rng.integers(-5, 6, B).astype(np.float64)
+        batches.append((img, make_particles(B, **cols)))
+    torch.cuda.synchronize()
+    r = Reconstructor(box, use_ctf=cfg["ctf"], sampling=SAMPLING, device=local, max_batch=cfg["chunk"], sym_matrices=mats)
+    for img, p in batches:
+        r.insert_device_ptr(img.data_ptr(), p)
+    r.sync()
+    r.reset()
+    barrier_all()
+    r.timer_start()
+    for i in range(K):
+        img, p = batches[i & 1]
+        r.insert_device_ptr(img.data_ptr(), p)
+    ms = max_over_ranks(r.timer_stop())
+    tm = r.timings()
+    r.close()
+    del batches
+    torch.cuda.empty_cache()
+    value = world * K * B / (ms * 1e-3)
+    return {"workload": cfg["name"], "box": box, "sym": cfg["sym"], "ctf": cfg["ctf"], "insertions_per_particle": n_ops,
+            "particles_per_step_per_gpu": B, "steps": K, "value": value, "unit": UNIT, "insertions_per_s": value * n_ops,
+            "ms_per_step": ms / K, "gpu_launches": int(tm["kernel_launches"]),
+            "stage_ms_per_step": {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}}
+
+
+def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_over_ranks, vol_ptr):
+    """Config 3 AS STATED: `total` particles in all, sharded over the ranks, end to end (pinned host batches -> H2D ->
+    insertion -> one NCCL reduce -> normalisation + 3-D inverse FFT + D2H of the map on rank 0).  The two pinned batches
+    are cycled: the bytes moved and the work done are those of `total` distinct particles."""
+    from xmipp3_b200.sharding import shard_range
+    lo, hi = shard_range(total, world, rank)
+    mine = hi - lo
+    r.reset()
+    barrier_all()
+    t0 = time.perf_counter()
+    done, i = 0, 0
+    while done < mine:
+        hbuf, p = host[i & 1]
+        n = min(len(p), mine - done)
+        r.insert_host_ptr(hbuf.data_ptr(), p[:n])
+        done += n
+        i += 1
+    if world > 1:
+        r.reduce(0)
+    if rank == 0:
+        r.finalize_into(vol_ptr)
+    else:
+        r.sync()
+    barrier_all()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    return {"workload": "config[2] as stated: %d particles %dx%d with CTF in total, sharded over %d GPU(s)" % (total, box, box, world),
+            "scaling": "strong", "particles_total": total, "particles_per_gpu": int(mine), "seconds": dt, "value": total / dt, "unit": UNIT,
+            "includes": "H2D from pinned host memory, insertion, NCCL reduce (N>1), normalise + 3-D IFFT + D2H of the map"}
+
+
+def reduce_check(dev, local, rank, world):
+    """N > 1: is the volume rank 0 finalises after rfb200_reduce_nccl the sum over the ranks?  Every rank inserts its own
+    96 particles (box 64, CTF); (a) the FP64 checksum of W on rank 0 after the reduce against the sum of the per-rank
+    checksums, (b) the finalised map against rank 0 inserting all world x 96 particles by itself."""
+    import torch
+    import torch.distributed as dist
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    box, n = 64, 96
+    def data(rk):
+        img, cols = synth_batch_torch(n, box, 777000 + 13 * rk, dev, ctf=True)
+        return img, make_particles(n, **cols)
+    r = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local)
+    ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    r.nccl_init(ids[0], world, rank)
+    img, p = data(rank)
+    r.insert_device_ptr(img.data_ptr(), p)
+    mine = r.weight_sum()
+    t = torch.tensor([mine], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    r.reduce(0)
+    out = None
+    if rank == 0:
+        after = r.weight_sum()
+        vol = r.finalize()
+        solo = Reconstructor(box, use_ctf=True, sampling=SAMPLING, device=local)
+        for rk in range(world):
+            im2, p2 = data(rk)
+            solo.insert_device_ptr(im2.data_ptr(), p2)
+        solo_sum = solo.weight_sum()
+        ref = solo.finalize()
+        solo.close()
+        out = {"ranks": world, "particles_per_rank": n, "weight_sum_after_reduce": after, "sum_of_rank_weight_sums": float(t.item()),
+               "weight_sum_rel_err": abs(after - float(t.item())) / abs(float(t.item())),
+               "weight_sum_one_rank_all_particles": solo_sum,
+               "map_rel_l2_vs_one_rank": float(np.linalg.norm(vol - ref) / np.linalg.norm(ref))}
+        out["ok"] = bool(out["weight_sum_rel_err"] <= 1e-6 and out["map_rel_l2_vs_one_rank"] <= 1e-5)
+    else:
+        r.sync()
+    r.close()
+    dist.barrier()
+    return out
+
+
+def measure_ref_gpu_kernel(box, n_images=50):
+    """Same-box GPU baseline: the REFERENCE's own CUDA kernel for this path (processBufferKernel<false, hasCTF, 0, ...>,
+    reconstruction_cuda/cuda_gpu_reconstruct_fourier.cpp:898-951, blob path :510-652), compiled for sm_100a from the
+    reference tree by oracle/build_ref.py, timed on buffers prepared as ProgRecFourierGPU::prepareBuffer does (restated
+    host side, oracle/recfourier_fast_oracle.cpp).  Kernel only (CUDA events on its stream), and the whole
+    processBufferGPU call (host copy of the buffer + H2D + kernel)."""
+    from oracle import oracle as O
+    from oracle import ref_kernel
+    if not ref_kernel.available():
+        return {"unavailable": "oracle/_ref/librefkernel.so not built (needs /root/reference at build time)"}
+    img, cols = synth_batch_numpy(n_images, box, 4242, True)
+    p = O.make_particles(n_images, **cols)
+    host = O.FastOracle(box, use_ctf=True, sampling=SAMPLING, use_fast=False)
+    out = {"kernel": "processBufferKernel<useFast=false, hasCTF=true, blobOrder=0> (reference, recompiled for sm_100a)",
+           "source": "reconstruction_cuda/cuda_gpu_reconstruct_fourier.cpp:898-951 via oracle/ref_harness.cu", "unit": UNIT, "runs": []}
+    for buf in (25, n_images):       # --bufferSize default of the reference (25) and a larger buffer
+        k = ref_kernel.RefKernel(host, max_images=buf)
+        try:
+            out["profile"] = k.profile()
+            k.process(img[:buf], p[:buf])
+            call_ms, kernel_ms = k.time(reps=3)
+        finally:
+            k.close()
+        out["runs"].append({"images_per_buffer": buf, "kernel_ms": kernel_ms, "call_ms": call_ms,
+                            "kernel_particles_per_s": buf / (kernel_ms * 1e-3), "call_particles_per_s": buf / (call_ms * 1e-3)})
+    best = max(out["runs"], key=lambda x: x["kernel_particles_per_s"])
+    out["value"] = best["kernel_particles_per_s"]
+    out["value_whole_call"] = max(x["call_particles_per_s"] for x in out["runs"])
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -226,6 +382,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=192, help="particles per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs, strong_scaling, reduce_check and ref_gpu_kernel")
+    ap.add_argument("--strong-total", type=int, default=100000, help="particles of the strong-scaling block (config 3 as stated)")
     ap.add_argument("--chunk", type=int, default=1024, help="particles per preprocessing chunk inside the library (max_batch)")
     ap.add_argument("--sym", default="c1", help="point group (e.g. d7 = BASELINE config 4: 14 insertions per image); "
                     "not the headline configuration")
@@ -335,33 +493,51 @@ def main():
     traffic = prof.get("dram_bytes_per_launch")
     cs = clocks.summary()
     sm_mhz = cs.get("sm_mhz") or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_nominal = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    try:
+        from xmipp3_b200._lib import measure_fp32_peak
+        fp32_peak = measure_fp32_peak(local)
+        fp32_src = "measured: FFMA-chain micro-benchmark on this GPU (rfb200_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f" % (sm_mhz, fp32_nominal)
+    except Exception as e:          # older library build
+        fp32_peak = fp32_nominal
+        fp32_src = "nominal 148 SM x 128 lanes x 2 x %.0f MHz (micro-benchmark unavailable: %s)" % (sm_mhz, e)
     roofline = {"kernel": "k_gather_sticks<4,cls>", "bound": "hbm", "achieved": alg_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": alg_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": prof.get("source", "none: no ncu summary in profiles/gather_ncu.json") +
+                                  " (one ncu --set full capture of this kernel, committed; NOT measured in this run)",
                 "ms_per_launch": g_ms, "particles_per_launch": imgs_per_launch,
+                "bound_actual": "instruction issue + L1/shared-memory data pipe (ncu: l1_data_pipe); the contract's `bound` only admits hbm|tensor",
                 "note": "the gather is bound by the L1/shared-memory data pipe (per-pair pixel and blob-table fetches), "
                         "not by HBM or FP32: see l1_data_pipe (ncu) and fp32"}
     fp32 = {"achieved": alg_flops / (g_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": alg_flops / (g_ms * 1e-3) / 1e12 / fp32_peak,
-            "peak_source": "148 SM x 128 lanes x 2 x %.0f MHz (median SM clock during the run)" % sm_mhz}
+            "peak_source": fp32_src}
     l1_pipe = {"frac": prof.get("l1_data_pipe_frac"), "issue_frac": prof.get("issue_active_frac"),
                "source": prof.get("source", "no ncu summary in profiles/gather_ncu.json"),
                "note": "ncu l1tex__data_pipe_lsu_wavefronts / smsp__issue_active of the same kernel (cold, serialised)"}
     stage_ms = {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}
     # roofline fraction of every kernel of the step against the measured HBM peak, from the stage timers (CUDA events on
-    # the compute stream) and the algorithmic bytes of DESIGN.md section 5 (fused chain: power-of-two padded sizes)
+    # the compute stream).  algorithmic bytes = SURVEY section 8d: K1 (whole preprocessing) = N^2*4 (raw image) +
+    # P(P/2+1)*8 (half-plane transform) + Npix*8 (compact slice) per particle; format bytes = what this implementation's
+    # buffers move (intermediate T of the fused chain written + read once, half-plane pair-format slice write)
     P = wm["P"]
-    side = 2 * (P // 2) + 11                       # slice edge incl. apron (Geometry::side at pad 2, r 1.9)
-    k_bytes = {"k_fft_rows (K1r)": (box * box * 4 + (P // 2 + 1) * box * 8, tm["fft2d_ms"]),
-               "k_fft_cols_slices (K1c)": ((P // 2 + 1) * box * 8 + side * side * 16, tm["slice_ms"]),
-               "k_gather_sticks (K2')": (wm["k2_bytes_per_particle"] + wm["k2_bytes_per_launch_fixed"] / imgs_per_launch, tm["gather_ms"]),
-               "k_edge2 + k_damped_scatter (K2e', K2r)": (None, tm["edge_ms"])}
+    Xh = P // 2 + 1
+    Rp, col_off = P // 2 + 5, 4                    # Geometry::Rp / colOff at pad 2, r 1.9 (K = 4)
+    side, pitch = 2 * Rp + 1, (Rp + col_off + 3) & ~1
+    k1_alg = box * box * 4 + P * Xh * 8 + wm["npix"] * 8
+    k_bytes = {"k_fft_rows (K1r)": (None, box * box * 4 + Xh * box * 8, tm["fft2d_ms"]),
+               "k_fft_cols_slices (K1c)": (None, Xh * box * 8 + side * pitch * 16, tm["slice_ms"]),
+               "K1 chain (K1r + K1c)": (k1_alg, box * box * 4 + 2 * Xh * box * 8 + side * pitch * 16, tm["fft2d_ms"] + tm["slice_ms"]),
+               "k_gather_sticks (K2')": (wm["k2_bytes_per_particle"] + wm["k2_bytes_per_launch_fixed"] / imgs_per_launch, None, tm["gather_ms"]),
+               "k_edge2 + k_damped_scatter (K2e', K2r)": (None, None, tm["edge_ms"])}
     per_kernel = []
-    for name, (bpp, t_ms) in k_bytes.items():
+    for name, (alg, fmt, t_ms) in k_bytes.items():
         e = {"kernel": name, "ms_per_step": t_ms / K, "us_per_particle": 1e3 * t_ms / (K * B)}
-        if bpp is not None and t_ms > 0:
-            gbs = bpp * K * B / (t_ms * 1e-3) / 1e9
-            e.update({"algorithmic_bytes_per_particle": bpp, "achieved_GBps": gbs, "hbm_frac": gbs / hbm_peak})
+        if alg is not None and t_ms > 0:
+            gbs = alg * K * B / (t_ms * 1e-3) / 1e9
+            e.update({"algorithmic_bytes_per_particle": alg, "achieved_GBps": gbs, "hbm_frac": gbs / hbm_peak})
+        if fmt is not None and t_ms > 0:
+            e.update({"format_bytes_per_particle": fmt, "format_GBps": fmt * K * B / (t_ms * 1e-3) / 1e9})
         per_kernel.append(e)
     if args.fast:
         per_kernel = None
@@ -442,6 +618,38 @@ def main():
         extra["e2e_h2d_ms_per_step"] = tm2["h2d_ms"] / K
         extra["e2e_h2d_GBps"] = (B * box * box * 4 / 1e9) / (tm2["h2d_ms"] / K * 1e-3) if tm2["h2d_ms"] > 0 else None
 
+    # ---------------- strong scaling, the other BASELINE configurations, reduce check, the reference's own GPU kernel
+    headline = box == 256 and args.sym.lower() == "c1" and not args.no_ctf and not args.fast
+    if not args.no_extras and not args.no_e2e and headline:
+        vol_ptr = vol_pinned.data_ptr() if rank == 0 else 0
+        extra["strong_scaling"] = measure_strong_scaling(r, host, box, world, rank, args.strong_total, barrier, max_over_ranks, vol_ptr)
+    r.close()
+    r = None
+    del batches
+    if not args.no_e2e:
+        del host
+    torch.cuda.empty_cache()
+    if not args.no_extras and headline:
+        def barrier_all():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        oc = []
+        for cfg in OTHER_CONFIGS:
+            try:
+                oc.append(measure_other_config(cfg, dev, local, rank, world, max_over_ranks, barrier_all))
+            except Exception as e:      # one configuration failing must not take the headline line with it
+                oc.append({"workload": cfg["name"], "error": "%s: %s" % (type(e).__name__, e)})
+        extra["other_configs"] = oc
+        if world > 1:
+            extra["reduce_check"] = reduce_check(dev, local, rank, world)
+        if rank == 0 and world == 1:
+            try:
+                extra["ref_gpu_kernel"] = measure_ref_gpu_kernel(box)
+                extra["ref_gpu_kernel"]["ours_over_reference_kernel"] = value / extra["ref_gpu_kernel"]["value"] if extra["ref_gpu_kernel"].get("value") else None
+            except Exception as e:
+                extra["ref_gpu_kernel"] = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -467,7 +675,8 @@ def main():
         line.update(extra)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    r.close()
+    if r is not None:
+        r.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -174,6 +174,10 @@ int rfb200_weight_sum_end(rfb200_handle h, double* sum);
 
 /* Number of CUDA devices visible to the process (for host programs that start one process per GPU). */
 int rfb200_device_count(int32_t* n);
+/* Measured FP32 SIMT peak of a device: a register-resident FFMA chain kernel (8 independent chains per thread, 2048
+ * threads per SM) timed with CUDA events; *tflops = 2 * FMAs / time.  The denominator of the FP32 roofline fraction the
+ * benchmark reports, instead of the nominal SMs x 128 lanes x 2 x clock. */
+int rfb200_measure_fp32_peak(int32_t device, double* tflops);
 
 /* Page-locked host memory for the image batches handed to rfb200_insert_batch: transfers from it run at full PCIe
  * speed and asynchronously (cudaHostAlloc / cudaFreeHost; replaces pinMemory / unpinMemory of

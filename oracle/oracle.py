@@ -140,6 +140,7 @@ def lib():
         L.orf_fast_finalize.argtypes = [C.c_void_p, C.c_void_p]
         L.orf_fast_set_temp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orf_fast_fourier.argtypes = [C.c_void_p, C.c_void_p]
+        L.orf_fast_half_spaces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -278,6 +279,15 @@ class FastOracle:
         W = np.ascontiguousarray(W, dtype=np.float32)
         assert V.shape == (n, n, n) and W.shape == (n, n, n)
         self._L.orf_fast_set_temp(self._h, _ptr(V), _ptr(W))
+
+    def half_spaces(self):
+        """mirrorAndCrop of the temporary spaces (reconstruct_fourier_gpu.cpp:697-730): V, W on [S+1, S+1, S/2+1], last axis =
+        centred x >= 0, before symmetrisation and weighting."""
+        n, X = self.S + 1, self.S // 2 + 1
+        V = np.empty((n, n, X), dtype=np.complex64)
+        W = np.empty((n, n, X), dtype=np.float32)
+        self._L.orf_fast_half_spaces(self._h, _ptr(V), _ptr(W))
+        return V, W
 
     def fourier(self):
         """The Fourier volume handed to the inverse transform (after blob convolution, symmetrisation and weights)."""

@@ -77,6 +77,8 @@ void orf_fast_dims(void* h, int* S, int* sx, int* sy, int* Pv);
 void orf_fast_insert(void* h, const float* imgs, const orf_particle* meta, int n);
 void orf_fast_get_temp(void* h, float* Vri, float* W);     /* (S+1)^3 interleaved complex / real, [z][y][x] */
 void orf_fast_set_temp(void* h, const float* Vri, const float* W);
+void orf_fast_half_spaces(void* h, float* Vri, float* W);    /* mirrorAndCrop only: [S+1][S+1][S/2+1] */
+void orf_fast_half_spaces(void* h, float* Vri, float* W);    /* mirrorAndCrop only: [S+1][S+1][S/2+1] */
 void orf_fast_fourier(void* h, double* VFri);                /* Pv*Pv*(Pv/2+1) interleaved: input of the inverse transform */
 void orf_fast_finalize(void* h, double* out);
 void orf_tables(void* h, double* blobTableSqrt, double* fourierBlobTable, double* iDeltaSqrt, double* iDeltaFourier);

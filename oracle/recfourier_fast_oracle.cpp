@@ -518,6 +518,16 @@ void orf_fast_set_temp(void* h, const float* Vri, const float* W) {
     std::memcpy(o->tempVolume.data(), Vri, sizeof(cf) * o->tempVolume.size());
     std::memcpy(o->tempWeights.data(), W, sizeof(float) * o->tempWeights.size());
 }
+/* mirrorAndCrop (G:697-730) of the temporary spaces only: the accumulated half space [S+1][S+1][S/2+1] (interleaved complex /
+ * real), index 0 of the last axis = centred x 0, before symmetrisation and weighting */
+void orf_fast_half_spaces(void* h, float* Vri, float* W) {
+    FastOracle* o = static_cast<FastOracle*>(h);
+    const int X = o->S / 2;
+    std::vector<float> w = o->mirrorAndCrop(o->tempWeights, X, [](float v) { return v; });
+    std::vector<cf> v = o->mirrorAndCrop(o->tempVolume, X, [](cf c) { return std::conj(c); });
+    std::memcpy(Vri, v.data(), sizeof(cf) * v.size());
+    std::memcpy(W, w.data(), sizeof(float) * w.size());
+}
 void orf_fast_fourier(void* h, double* VFri) {
     std::vector<double> v = static_cast<FastOracle*>(h)->fourier();
     std::memcpy(VFri, v.data(), sizeof(double) * v.size());

@@ -61,6 +61,12 @@ def test_reference_kernel_fast_equals_the_fast_restatement(oracle_mod, refk, cas
 @pytest.mark.parametrize("case", [dict(N=64, n=300, ctf=True), dict(N=64, n=200, ctf=False), dict(N=32, n=40, sym="d2")],
                          ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
 def test_reference_blob_kernel_agrees_with_the_exact_path(oracle_mod, refk, case):
+    """ACCUMULATORS, voxel by voxel: the reference kernel's temporary spaces, folded by the restated mirrorAndCrop
+    (reconstruct_fourier_gpu.cpp:697-730), against the product's V and W and the oracle's.  Compared inside 80 % of the
+    resolution sphere: ProgRecFourierGPU zeroes the pixels beyond --max_resolution but still counts their blob weights
+    (cropAndShift :292-321 + processVoxelBlob :560-650), the CPU program skips them (reconstruct_fourier.cpp:597), so the
+    two programs differ by design in the outermost shells — the reference's own words for its GPU program are "gives
+    slightly different results".  The final maps are compared with that caveat (loose gate)."""
     from xmipp3_b200._lib import Reconstructor, make_particles
     case = dict(case)
     N, n, ctf, sym = case.pop("N"), case.pop("n"), case.pop("ctf", False), case.pop("sym", None)
@@ -77,20 +83,30 @@ def test_reference_blob_kernel_agrees_with_the_exact_path(oracle_mod, refk, case
     finally:
         k.close()
     host.set_temp_spaces(Vr, Wr)
+    Vh, Wh = host.half_spaces()                                # [S+1, S+1, S/2+1], centred (z, y), x >= 0
     ref_map = host.finalize()
     o = oracle_mod.Oracle(N, **kw)
     o.insert(d["images"], p, threads=4, scheme="slabs")
+    Vo, Wo = o.accumulators()                                  # [Z, Z, Z/2+1], FFT index order
     oracle_map = o.finalize()
     r = Reconstructor(N, **kw)
     r.insert(d["images"], make_particles(n, **cols))
+    Vg, Wg = r.accumulators()
     gpu_map = r.finalize()
     r.close()
-    res = {"gpu_vs_refkernel": float(synth.rel_l2(gpu_map, ref_map)), "oracle_vs_refkernel": float(synth.rel_l2(oracle_map, ref_map)),
-           "gpu_vs_oracle": float(synth.rel_l2(gpu_map, oracle_map)),
-           "min_fsc_gpu_vs_refkernel": float(np.nanmin(synth.fsc(gpu_map, ref_map)[1:]))}
+    S, Z = host.S, o.Z
+    c = np.arange(-(S // 2), S // 2 + 1)
+    zz, yy, xx = np.meshgrid(c, c, np.arange(0, S // 2 + 1), indexing="ij")
+    inner = (zz ** 2 + yy ** 2 + xx ** 2 <= (0.8 * S / 2) ** 2) & (xx >= 1)
+    iz, iy, ix = zz[inner] % Z, yy[inner] % Z, xx[inner]
+    res = {}
+    for name, (V, W) in (("oracle", (Vo, Wo)), ("gpu", (Vg, Wg))):
+        res["acc_W_%s_vs_refkernel" % name] = float(np.linalg.norm(W[iz, iy, ix] - Wh[inner]) / np.linalg.norm(Wh[inner]))
+        res["acc_V_%s_vs_refkernel" % name] = float(np.linalg.norm(V[iz, iy, ix] - Vh[inner]) / np.linalg.norm(Vh[inner]))
+    res.update({"map_gpu_vs_refkernel": float(synth.rel_l2(gpu_map, ref_map)), "map_oracle_vs_refkernel": float(synth.rel_l2(oracle_map, ref_map)),
+                "map_gpu_vs_oracle": float(synth.rel_l2(gpu_map, oracle_map)), "voxels_compared": int(inner.sum())})
     print(res)
-    # two different programs (single-precision gather with float atomics on a cropped cube vs double-precision scatter):
-    # the reference's own test tolerance between runs of this path is 1e-3 per voxel (tests/test.py:174-196)
-    assert res["gpu_vs_refkernel"] <= 1e-3, res
-    assert res["oracle_vs_refkernel"] <= 1e-3, res
-    assert res["min_fsc_gpu_vs_refkernel"] >= 0.999, res
+    # single-precision gather with float atomics (reference kernel) vs FP64 scatter (oracle) vs FP32 gather (product)
+    for key in ("acc_W_oracle_vs_refkernel", "acc_V_oracle_vs_refkernel", "acc_W_gpu_vs_refkernel", "acc_V_gpu_vs_refkernel"):
+        assert res[key] <= 2e-5, res
+    assert res["map_gpu_vs_refkernel"] <= 5e-2 and res["map_gpu_vs_oracle"] <= 1e-4, res

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
-    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count", "rfb200_debug_fast_fourier",
+    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count", "rfb200_measure_fp32_peak", "rfb200_debug_fast_fourier",
     "rfb200_projector_create", "rfb200_projector_project", "rfb200_projector_project_device", "rfb200_projector_last_error",
     "rfb200_projector_destroy",
 ]
@@ -120,6 +120,7 @@ def load(build=True):
     L.rfb200_debug_slice_dims.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rfb200_debug_get_slice.argtypes = [H, C.c_int32, C.c_void_p]
     L.rfb200_debug_fast_fourier.argtypes = [H, C.c_void_p]
+    L.rfb200_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.rfb200_projector_create.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.POINTER(H)]
     L.rfb200_projector_project.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.rfb200_projector_project_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -129,6 +130,15 @@ def load(build=True):
     L.rfb200_projector_destroy.restype = None
     _lib = L
     return L
+
+
+def measure_fp32_peak(device=0):
+    """Measured FP32 SIMT peak (TFLOP/s) of a device: FFMA chain micro-benchmark inside the library."""
+    v = C.c_double()
+    rc = load().rfb200_measure_fp32_peak(int(device), C.byref(v))
+    if rc != OK:
+        raise RecFourierError(rc, "rfb200_measure_fp32_peak failed")
+    return v.value
 
 
 class RecFourierError(RuntimeError):

@@ -513,7 +513,7 @@ Slice2Args make_slice_args(rfb200_handle h) {
     const Geometry& g = h->geo;
     Slice2Args a{};
     a.sp = make_slice_params(h);
-    a.pitch = g.pitch; a.planeStride = g.planeStride;
+    a.pitch = g.pitch; a.planeStride = g.planeStride; a.colOff = g.colOff;
     a.fft = h->dFft; a.slices = h->dSlices2; a.col0 = h->dCol02; a.damped = h->dDamped; a.damped2 = h->dDamped2; a.dampedMask = h->dDampedMask;
     a.ip = h->dImg; a.ctfs = h->dCtf; a.jmax = h->dJmax;
     return a;
@@ -1394,6 +1394,52 @@ int rfb200_device_count(int32_t* n) {
     return RFB200_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678f) out[0] = s;          // keeps the chains alive without a store per thread
+}
+}  // namespace
+
+int rfb200_measure_fp32_peak(int32_t device, double* tflops) {
+    if (!tflops) return RFB200_ERR_ARG;
+    *tflops = 0;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return RFB200_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RFB200_ERR_CUDA;
+    float* d = nullptr;
+    if (cudaMalloc(&d, 256) != cudaSuccess) return RFB200_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;      // 8 x 256 threads per SM
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_fma_peak<<<blocks, 256>>>(d, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess || best <= 0) return RFB200_ERR_CUDA;
+    *tflops = best;
+    return RFB200_OK;
+}
+
 int rfb200_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return RFB200_ERR_ARG;
     *ptr = nullptr;
@@ -1439,15 +1485,21 @@ int rfb200_debug_get_slice(rfb200_handle h, int32_t idx, float* out4) {
     if (h->fast) return fail(h, RFB200_ERR_UNSUPPORTED, "no slices in --fast mode");
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
-    // format v2: plane A holds (re, im); the third channel is rebuilt from the validity table (multiplicity of the
-    // pixel: 1 inside the resolution disc, 2 on column 0, 0 outside)
+    // The full-plane view of the stored half-plane slice: (re, im) of pixel (i, j), columns j < -colOff from the Hermitian
+    // mate; the third channel is rebuilt from the validity table (multiplicity of the pixel: 1 inside the resolution
+    // disc, 2 on column 0, 0 outside)
     const Geometry& g = h->geo;
     std::vector<float4> A((size_t)g.planeStride);
     RF_CUDA(h, cudaMemcpy(A.data(), h->dSlices2 + (size_t)idx * g.planeStride, sizeof(float4) * A.size(), cudaMemcpyDeviceToHost));
     std::vector<int32_t> rim = host::build_rim_table(h->geo, h->jmax, h->iLo, h->iHi);
     for (int i = 0; i < g.side; ++i)
         for (int j = 0; j < g.side; ++j) {
-            const float4 v = A[(size_t)i * g.pitch + j];
+            float4 v;
+            if (j - g.Rp >= -g.colOff) v = A[(size_t)i * g.pitch + (j - g.Rp + g.colOff)];
+            else {
+                v = A[(size_t)(g.side - 1 - i) * g.pitch + (g.Rp - j + g.colOff)];
+                v.y = -v.y;
+            }
             const int rt = rim[i], jc = j - g.Rp;
             const int jPos = (rt & 0x3fff) - 1, jNeg = ((rt >> 14) & 0x3fff) - 1;
             float m = jc > 0 ? (jc <= jPos ? 1.f : 0.f) : (jc < 0 ? (-jc <= jNeg ? 1.f : 0.f) : (float)(rt >> 28));

@@ -210,10 +210,11 @@ __device__ __forceinline__ bool d_pixel_valid(const int* __restrict__ jmax, cons
 template <int P> constexpr int kColsPerCta = (P >= 1024) ? 4 : 8;
 
 // grid (ceil((R+2) / NC), nImg), block (NC+1) * P/8 threads: columns kx = NC*blockIdx.x .. +NC-1 and the halo column
-// NC*blockIdx.x - 1.  With the left neighbour's pixel at hand every lane writes two WHOLE 16-byte entries,
-// E(r, j-1) = (p(r,j-1), p(r,j)) and its mirror E(-r, -j) = (conj p(r,j), conj p(r,j-1)), so a row piece of a CTA is NC
-// consecutive entries = full 32-byte sectors and one store request (measured before: 7.7 GB of L1->L2 store traffic per
-// 1024 particles for 4.3 GB of data, from the 8-byte halves of the entries shared between neighbouring CTAs).
+// NC*blockIdx.x - 1.  With the left neighbour's pixel at hand every lane writes a WHOLE 16-byte entry,
+// E(r, j-1) = (p(r,j-1), p(r,j)) (and, for the few columns next to j = 0 that the half-plane format keeps on the mirrored
+// side, E(-r, -j) = (conj p(r,j), conj p(r,j-1))), so a row piece of a CTA is NC consecutive entries = full 32-byte sectors
+// and one store request.  (Round 1 stored the full plane: every pixel four times, 4.3 GB of DRAM writes per 1024
+// particles at box 256; the half-plane format halves that.)
 template <int P>
 __global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
     constexpr int NC = kColsPerCta<P>, NS = NC + 1;
@@ -302,10 +303,12 @@ __global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slice
         if (!act) continue;
         if (c == 0) prv = (j0 >= 2) ? sHalo[r] : make_float2(0.f, 0.f);
         if (j > 0) {
-            const size_t o1 = (size_t)(ipx + sp.Rp) * a.s.pitch + (j + sp.Rp);
-            const size_t o2 = (size_t)(-ipx + sp.Rp) * a.s.pitch + (-j + sp.Rp);
+            const size_t o1 = (size_t)(ipx + sp.Rp) * a.s.pitch + (j + a.s.colOff);
             S4[o1 - 1] = make_float4(prv.x, prv.y, pv.x, pv.y);            // E(r, j-1)
-            S4[o2] = make_float4(pv.x, -pv.y, prv.x, -prv.y);             // E(-r, -j)
+            if (j <= a.s.colOff) {                                         // half-plane format: the first colOff mirrored columns only
+                const size_t o2 = (size_t)(-ipx + sp.Rp) * a.s.pitch + (-j + a.s.colOff);
+                S4[o2] = make_float4(pv.x, -pv.y, prv.x, -prv.y);         // E(-r, -j)
+            }
         }
         if (flag) {
             if (a.s.damped) a.s.damped[dOff + (size_t)r * (sp.R + 1) + j] = wDamped;

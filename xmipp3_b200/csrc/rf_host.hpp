@@ -271,7 +271,8 @@ inline Geometry make_geometry(int N, double padProj, double padVol, double maxRe
     g.sMax = g.r2 * g.iDelta;
     g.reach = (float)(maxRes * g.Z + r);
     g.inplane_reach = (float)(R + rho);
-    g.pitch = (g.side + 2 + 1) & ~1;
+    g.colOff = g.K;
+    g.pitch = (g.Rp + g.colOff + 2 + 1) & ~1;
     g.planeStride = g.side * g.pitch;
     g.xOwnMax = (g.Z % 2 == 0) ? g.Z / 2 - 1 : g.Z / 2;
     g.rimIn2 = -1.f;   // set by build_rim_table

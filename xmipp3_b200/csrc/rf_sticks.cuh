@@ -1,8 +1,9 @@
 // rf_sticks.cuh — second-generation insertion kernels (sm_100a).
 //
-//   K1b' k_make_slices2     half-plane FFT -> full-plane slice of overlapping pixel PAIRS: entry (i,j) is the float4
+//   K1b' k_make_slices2     half-plane FFT -> half-plane slice of overlapping pixel PAIRS: entry (i,j) is the float4
 //                           (pixel(i,j), pixel(i,j+1)), so a candidate-window row is two 16-byte loads whatever the
-//                           parity of its origin, and neighbouring lanes share cache lines + the
+//                           parity of its origin, and neighbouring lanes share cache lines; columns j >= -colOff only
+//                           (the slice is Hermitian: a voxel at alpha < 0 reads (-alpha, -beta) and conjugates) + the
 //                           true weights of the CTF-damped pixels (RF.cpp:600-625 hoisted)
 //   K2'  k_gather_sticks    voxel-centric gather, "column walk": a warp owns a stick of 4 x 4 columns that run
 //                           along the axis dominating the plane normal; two lanes per column (even / odd depth);
@@ -72,7 +73,7 @@ __device__ __forceinline__ float d_set_flag(float re, bool flag) {
 
 struct Slice2Args {
     SliceParams sp;
-    int pitch, planeStride;
+    int pitch, planeStride, colOff;
     const float2* fft;
     float4* slices;       // per image side x pitch entries (pixel(i,j), pixel(i,j+1))
     float2* col0;         // per image `side` originals-only entries of column j = 0
@@ -116,15 +117,17 @@ __global__ void __launch_bounds__(256, 3) k_make_slices2(const __grid_constant__
         bool flag = false;
         if (active) {
             float4 c = d_pixel_contrib2(f, a.jmax, sp, ctf, sCtfF, weight, j, ipx);
-            const size_t o1 = (size_t)(ipx + sp.Rp) * a.pitch + (j + sp.Rp);
+            const size_t o1 = (size_t)(ipx + sp.Rp) * a.pitch + (j + a.colOff);
             flag = c.w != 0.f;
             float unmod = (c.z != 0.f || flag) ? weight : 0.f;       // weight of a valid pixel without the CTF modulator
             if (j > 0) {
-                const size_t o2 = (size_t)(-ipx + sp.Rp) * a.pitch + (-j + sp.Rp);
                 const float re = d_set_flag(c.x, flag);
                 const float2 v = make_float2(re, c.y), vm = make_float2(re, -c.y);
                 S2[2 * o1] = v;  S2[2 * o1 - 1] = v;
-                S2[2 * o2] = vm; S2[2 * o2 - 1] = vm;
+                // only the first colOff mirrored columns are stored (half-plane format)
+                const size_t o2 = (size_t)(-ipx + sp.Rp) * a.pitch + (-j + a.colOff);
+                if (j <= a.colOff) S2[2 * o2] = vm;
+                if (j < a.colOff) S2[2 * o2 - 1] = vm;
             } else {
                 // column j = 0 holds original (0,ip) plus the mirror of original (0,-ip): the reference inserts this
                 // column twice for x > 0 voxels.  The combined entry is flagged if either part is
@@ -161,168 +164,6 @@ struct StickArgs {
     float* Wb;
     float* Wb2;                  // un-modulated weight sum for --iter > 1 with CTF (else nullptr)
 };
-
-// One candidate, fully predicated (no branches, so that the 16 candidates of a window interleave):
-//   if (S <= sMax) { w = table[round(S)]; accRe += w*re; accIm += w*im; if (re is not flagged) accW += w*mult; }
-// (int)(d2*iDelta + 0.5) of RF.cpp:725: adding 2^23 rounds S to the nearest integer in the mantissa; (bits << 2) +
-// tblAdj is then the shared-memory byte address of the table entry.  The LSB of `re` flags a CTF-damped pixel whose
-// weight comes from k_damped_scatter instead.
-__device__ __forceinline__ void d_candidate(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
-                                            const float mult, float& accRe, float& accIm, float& accW) {
-    asm("{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .f32 w, t;\n\t"
-        ".reg .b32 a, f;\n\t"
-        "setp.le.f32 p, %3, %4;\n\t"
-        "add.rn.f32 t, %3, 0f4B000000;\n\t"
-        "mov.b32 a, t;\n\t"
-        "shl.b32 a, a, 2;\n\t"
-        "add.u32 a, a, %5;\n\t"
-        "@p ld.shared.f32 w, [a];\n\t"
-        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
-        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
-        "mov.b32 f, %6;\n\t"
-        "and.b32 f, f, 1;\n\t"
-        "setp.eq.and.u32 q, f, 0, p;\n\t"
-        "@q fma.rn.f32 %2, w, %8, %2;\n\t"
-        "}"
-        : "+f"(accRe), "+f"(accIm), "+f"(accW)
-        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im), "f"(mult));
-}
-__device__ __forceinline__ void d_candidate1(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
-                                             float& accRe, float& accIm, float& accW) {
-    asm("{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .f32 w, t;\n\t"
-        ".reg .b32 a, f;\n\t"
-        "setp.le.f32 p, %3, %4;\n\t"
-        "add.rn.f32 t, %3, 0f4B000000;\n\t"
-        "mov.b32 a, t;\n\t"
-        "shl.b32 a, a, 2;\n\t"
-        "add.u32 a, a, %5;\n\t"
-        "@p ld.shared.f32 w, [a];\n\t"
-        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
-        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
-        "mov.b32 f, %6;\n\t"
-        "and.b32 f, f, 1;\n\t"
-        "setp.eq.and.u32 q, f, 0, p;\n\t"
-        "@q add.rn.f32 %2, %2, w;\n\t"
-        "}"
-        : "+f"(accRe), "+f"(accIm), "+f"(accW)
-        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im));
-}
-
-// Without CTF no pixel is ever flagged: the same two candidates minus the three instructions of the flag test.
-__device__ __forceinline__ void d_candidate_nf(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
-                                               const float mult, float& accRe, float& accIm, float& accW) {
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .f32 w, t;\n\t"
-        ".reg .b32 a;\n\t"
-        "setp.le.f32 p, %3, %4;\n\t"
-        "add.rn.f32 t, %3, 0f4B000000;\n\t"
-        "mov.b32 a, t;\n\t"
-        "shl.b32 a, a, 2;\n\t"
-        "add.u32 a, a, %5;\n\t"
-        "@p ld.shared.f32 w, [a];\n\t"
-        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
-        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
-        "@p fma.rn.f32 %2, w, %8, %2;\n\t"
-        "}"
-        : "+f"(accRe), "+f"(accIm), "+f"(accW)
-        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im), "f"(mult));
-}
-__device__ __forceinline__ void d_candidate1_nf(const float S, const float sMax, const uint32_t tblAdj, const float re, const float im,
-                                                float& accRe, float& accIm, float& accW) {
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .f32 w, t;\n\t"
-        ".reg .b32 a;\n\t"
-        "setp.le.f32 p, %3, %4;\n\t"
-        "add.rn.f32 t, %3, 0f4B000000;\n\t"
-        "mov.b32 a, t;\n\t"
-        "shl.b32 a, a, 2;\n\t"
-        "add.u32 a, a, %5;\n\t"
-        "@p ld.shared.f32 w, [a];\n\t"
-        "@p fma.rn.f32 %0, w, %6, %0;\n\t"
-        "@p fma.rn.f32 %1, w, %7, %1;\n\t"
-        "@p add.rn.f32 %2, %2, w;\n\t"
-        "}"
-        : "+f"(accRe), "+f"(accIm), "+f"(accW)
-        : "f"(S), "f"(sMax), "r"(tblAdj), "f"(re), "f"(im));
-}
-
-// One step of one column: evaluate the K x K candidate window of the lane's voxel.  p points at the window origin
-// (16-byte aligned pixel pair).  kSlow additionally weighs every candidate with its multiplicity (0 outside the
-// resolution disc, 2 on column j = 0), looked up per window row.  Two accumulator sets (even / odd candidates)
-// halve the length of the dependent FMA chains.
-template <int K, bool kSlow, bool kFlags>
-__device__ __forceinline__ void d_stick_window(const float4* __restrict__ p, const int pitch, const float (&dxs)[K], const float (&dys)[K],
-                                               const float sMax, const uint32_t tblAdj, const int jc, const int ic,
-                                               const int* __restrict__ rimTab, float& accRe, float& accIm, float& accW) {
-    constexpr int NP = (K + 1) / 2;
-#ifdef RF_STICK_UNCOND_LOADS
-    float4 px[K][NP];
-#pragma unroll
-    for (int ti = 0; ti < K; ++ti) {
-#pragma unroll
-        for (int q = 0; q < NP; ++q) px[ti][q] = __ldg(p + ti * pitch + 2 * q);
-    }
-#else
-    // A pixel pair is fetched only if one of its two candidates is accepted: fewer lanes per load instruction means
-    // fewer cache lines (L1 wavefronts) per instruction, and the kernel is bound by the L1 data pipe.  The registers
-    // are zeroed first: a conditionally defined register would stay live across the whole step loop.
-    float4 px[K][NP];
-#pragma unroll
-    for (int ti = 0; ti < K; ++ti) {
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            const int t0 = 2 * q, t1 = 2 * q + 1;
-            bool in = dys[ti] + dxs[t0] <= sMax;
-            if (t1 < K) in = in || (dys[ti] + dxs[t1] <= sMax);
-            px[ti][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in) px[ti][q] = __ldg(p + ti * pitch + t0);
-        }
-    }
-#endif
-    float re1 = 0.f, im1 = 0.f, w1 = 0.f;
-#pragma unroll
-    for (int ti = 0; ti < K; ++ti) {
-        int rt = 0;
-        if (kSlow) rt = __ldg(rimTab + ic + ti);
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int tj = 2 * q + e;
-                if (tj < K) {
-                    const float S = dys[ti] + dxs[tj];
-                    const float re = e ? px[ti][q].z : px[ti][q].x, im = e ? px[ti][q].w : px[ti][q].y;
-                    if (e) {
-                        if (kSlow) {
-                            if (kFlags) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), re1, im1, w1);
-                            else d_candidate_nf(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), re1, im1, w1);
-                        } else {
-                            if (kFlags) d_candidate1(S, sMax, tblAdj, re, im, re1, im1, w1);
-                            else d_candidate1_nf(S, sMax, tblAdj, re, im, re1, im1, w1);
-                        }
-                    } else {
-                        if (kSlow) {
-                            if (kFlags) d_candidate(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), accRe, accIm, accW);
-                            else d_candidate_nf(S, sMax, tblAdj, re, im, d_rim_mult(rt, jc + tj), accRe, accIm, accW);
-                        } else {
-                            if (kFlags) d_candidate1(S, sMax, tblAdj, re, im, accRe, accIm, accW);
-                            else d_candidate1_nf(S, sMax, tblAdj, re, im, accRe, accIm, accW);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    accRe += re1;
-    accIm += im1;
-    accW += w1;
-}
 
 // ---- packed single precision (sm_100: FADD2 / FMUL2 / FFMA2 operate on an aligned register pair and take a scalar
 // broadcast operand, so {x, x} pairs are free).  The gather is bound by instruction issue, not by the FP32 pipe: one
@@ -521,47 +362,68 @@ struct StickLaunch {             // the whole parameter block of one launch (< 3
 static_assert(sizeof(StickLaunch) <= 32764, "kernel parameter space");
 
 // A task = one plane crossing one stick.  Per-lane state of the column walk; `k` indexes StickLaunch::ps.
+// Half-plane slices: a voxel projecting to alpha < 0 is gathered at (-alpha, -beta) and its sum conjugated.  On the
+// unchecked path the sign is constant along a lane's walk and is folded into the task state once (sg, and the signs of
+// ja0, jb0, arL, brL, e1d, e2d); on the checked path the state is unflipped (sg = 1) and every step decides for itself.
 struct StickTask {
     int k;
     int ja0, jb0;          // integer pixel of the stick origin's projection
     float arL, brL, hL;    // lane's column at tau = 0: fractional in-plane position and height above the plane
+    float e1d, e2d;        // in-plane step per unit depth
+    float sg;              // +1 / -1: sign already applied to the in-plane quantities above (unchecked path)
     int tauLo, tauHi;      // the lane's first depth (column start + parity) and the column's last depth inside the slab
 };
 
 // geometry constants of the kernel that the step functions need
 struct StickConsts {
-    int Rp, side, pitch, planeStride;
+    int Rp, side, pitch, planeStride, colOff;
     float rho, iDelta, sMax, kI, rimIn2, rhoCol0;
     uint32_t tblAdj;
 };
 
-// window origin of the lane's voxel at depth tau: returns in-bounds flag, sets special (needs the multiplicity path)
-template <int K>
-__device__ __forceinline__ bool d_window_origin(const StickConsts& c, const StickTask& t, const PlaneS& pl, int tau, int& jw, int& iw,
-                                                float& ar, float& br, float& h, bool& special, float* aAbsOut = nullptr) {
+// State of one step (one voxel of the lane's column) in the coordinates of the STORED half plane.
+struct StickStep {
+    int ja, jb;            // integer pixel of the stick origin's projection, sign applied
+    int jw, iw;            // window origin relative to (ja, jb)
+    float ar, br, h;       // in-plane position relative to (ja, jb), sign applied; height above the plane
+    float sg;              // the sign: the voxel's sum is conjugated when sg < 0
+    bool special, inb;     // needs the multiplicity path / window inside the stored slice
+};
+template <int K, bool kChecked>
+__device__ __forceinline__ StickStep d_step(const StickConsts& c, const StickTask& t, const float nd, const int tau) {
+    StickStep q;
     const float ft = (float)tau;
-    ar = fmaf(ft, pl.e1d, t.arL);
-    br = fmaf(ft, pl.e2d, t.brL);
-    h = fmaf(ft, pl.nd, t.hL);
-    jw = __float2int_ru(ar - c.rho);
-    iw = __float2int_ru(br - c.rho);
-    const int jAbs = t.ja0 + jw + c.Rp, iAbs = t.jb0 + iw + c.Rp;
-    // Fast path needs every ACCEPTED candidate (in-plane distance <= rho) to be a valid pixel of multiplicity 1:
-    // inside the all-valid disc and away from column 0.
-    const float Aabs = (float)t.ja0 + ar, Babs = (float)t.jb0 + br;
-    special = (Aabs * Aabs + Babs * Babs > c.rimIn2) || (fabsf(Aabs) <= c.rhoCol0);
-    if (aAbsOut) *aAbsOut = Aabs;
-    return (unsigned)jAbs <= (unsigned)(c.side - K) && (unsigned)iAbs <= (unsigned)(c.side - K);
-}
-template <int K>
-__device__ __forceinline__ const float4* d_window_ptr(const StickConsts& c, const float4* sl, const StickTask& t, int jw, int iw) {
-    const int jAbs = t.ja0 + jw + c.Rp, iAbs = t.jb0 + iw + c.Rp;
-    return sl + (iAbs * c.pitch + jAbs);
+    q.ar = fmaf(ft, t.e1d, t.arL);
+    q.br = fmaf(ft, t.e2d, t.brL);
+    q.h = fmaf(ft, nd, t.hL);
+    q.ja = t.ja0;
+    q.jb = t.jb0;
+    q.sg = t.sg;
+    q.special = false;
+    q.inb = true;
+    if (kChecked) {
+        // Fast path needs every ACCEPTED candidate (in-plane distance <= rho) to be a valid pixel of multiplicity 1:
+        // inside the all-valid disc and away from column 0.
+        const float Aabs = (float)t.ja0 + q.ar, Babs = (float)t.jb0 + q.br;
+        q.special = (Aabs * Aabs + Babs * Babs > c.rimIn2) || (fabsf(Aabs) <= c.rhoCol0);
+        if (Aabs < 0.f) {          // mirrored half: F(-i, -j) = conj F(i, j)
+            q.sg = -1.f;
+            q.ar = -q.ar; q.br = -q.br;
+            q.ja = -q.ja; q.jb = -q.jb;
+        }
+    }
+    q.jw = __float2int_ru(q.ar - c.rho);
+    q.iw = __float2int_ru(q.br - c.rho);
+    if (kChecked) {
+        const int jAbs = q.ja + q.jw + c.colOff, iAbs = q.jb + q.iw + c.Rp;
+        q.inb = (unsigned)jAbs <= (unsigned)(c.colOff + c.Rp + 1 - K) && (unsigned)iAbs <= (unsigned)(c.side - K);
+    }
+    return q;
 }
 
 // Walk the columns of one task, two depths per column and iteration.  kChecked = false: every step of every
-// active lane is known to be in bounds and to need no multiplicity handling (both ends of each column were
-// tested; the conditions are convex along it).
+// active lane is known to be in bounds, on one side of column 0 and to need no multiplicity handling (both ends of
+// each column were tested; the conditions are convex along it).
 template <int K, bool kChecked, bool kFlags>
 __device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const StickTask& t, const PlaneS& pl, const int nIter, const float4* __restrict__ slices,
                                                const int imgStride, const int* __restrict__ rimTab, float2* accV, float* accW, const int col) {
@@ -570,40 +432,24 @@ __device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const Stick
     uint32_t touched = 0;          // bit b <-> depths 2b, 2b + 1 of the stick hold something
     for (int s = 0; s < nIter; ++s) {
         const int tau = t.tauLo + 2 * s;
-        int jw, iw;
-        float ar, br, h;
-        bool special = false;
-        bool ok = d_window_origin<K>(c, t, pl, tau, jw, iw, ar, br, h, special);
-        ok = (kChecked ? ok : true) && tau <= t.tauHi;
+        const StickStep q = d_step<K, kChecked>(c, t, pl.nd, tau);
+        const bool ok = q.inb && tau <= t.tauHi;
         bool anySlow = false;
-        if (kChecked) anySlow = __any_sync(0xffffffffu, ok && special);
+        if (kChecked) anySlow = __any_sync(0xffffffffu, ok && q.special);
         if (ok) {
-            const float da0 = ar - __int2float_rn(jw), db0 = br - __int2float_rn(iw);
-            const float h2s = h * h * c.iDelta;
-            const float4* p = d_window_ptr<K>(c, sl, t, jw, iw);
+            const float da0 = q.ar - __int2float_rn(q.jw), db0 = q.br - __int2float_rn(q.iw);
+            const float h2s = q.h * q.h * c.iDelta;
+            const int jc = q.ja + q.jw, ic = q.jb + q.iw;
+            const float4* p = sl + ((ic + c.Rp) * c.pitch + (jc + c.colOff));
             float accRe = 0.f, accIm = 0.f, accWt = 0.f;
-#ifdef RF_GATHER_V1
-            float dxs[K], dys[K];
-#pragma unroll
-            for (int q = 0; q < K; ++q) {
-                const float da = da0 - (float)q, db = db0 - (float)q;
-                dxs[q] = c.kI * da * da;
-                dys[q] = fmaf(c.kI * db, db, h2s);
-            }
             if (kChecked && anySlow)
-                d_stick_window<K, true, kFlags>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
+                d_stick_window2<K, true, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
             else
-                d_stick_window<K, false, kFlags>(p, c.pitch, dxs, dys, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
-#else
-            if (kChecked && anySlow)
-                d_stick_window2<K, true, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
-            else
-                d_stick_window2<K, false, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, t.ja0 + jw, t.jb0 + iw, rimTab, accRe, accIm, accWt);
-#endif
+                d_stick_window2<K, false, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
             const int o = tau * kStickCols + col;
             float2 v = accV[o];
             v.x += accRe;
-            v.y += accIm;
+            v.y = fmaf(q.sg, accIm, v.y);
             accV[o] = v;
             accW[o] = fmaf(weight, accWt, accW[o]);
             touched |= 1u << (tau >> 1);
@@ -669,7 +515,7 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
 
     constexpr int cls = CLS;
     StickConsts c;
-    c.Rp = geo.Rp; c.side = geo.side; c.pitch = geo.pitch; c.planeStride = geo.planeStride;
+    c.Rp = geo.Rp; c.side = geo.side; c.pitch = geo.pitch; c.planeStride = geo.planeStride; c.colOff = geo.colOff;
     c.rho = geo.rho; c.iDelta = geo.iDelta; c.sMax = geo.sMax; c.kI = geo.s2 * geo.iDelta;
     c.rimIn2 = geo.rimIn2; c.rhoCol0 = geo.rho + 1e-2f;
     c.tblAdj = (uint32_t)(*(volatile int*)&sAdj);
@@ -757,6 +603,9 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
                 t.arL = fmaf(lbf, pl.e1b, fmaf(laf, pl.e1a, (float)(a0 - ja)));
                 t.brL = fmaf(lbf, pl.e2b, fmaf(laf, pl.e2a, (float)(b0 - jb)));
                 t.hL = fmaf(lbf, pl.nb, fmaf(laf, pl.na, (float)h0));
+                t.e1d = pl.e1d;
+                t.e2d = pl.e2d;
+                t.sg = 1.f;
                 // segment of the column inside the slab |h| <= r:  h(tau) = hL + tau * nd
                 const float c0 = -t.hL * pl.invNd, hw = rSlab * fabsf(pl.invNd);
                 const int colLo = max(__float2int_ru(c0 - hw), tauMin);
@@ -766,26 +615,28 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
                 if (nIter == 0) continue;
                 // both ends of the lane's walk in bounds and free of special pixels -> unchecked loop
                 bool plain = true;
+                float aFirst = 1.f;
                 if (t.tauLo <= t.tauHi) {
                     const int last = t.tauLo + ((t.tauHi - t.tauLo) & ~1);
-                    float aEnd[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        int jw, iw;
-                        float ar, br, h;
-                        bool special;
-                        const bool inb = d_window_origin<K>(c, t, pl, e ? last : t.tauLo, jw, iw, ar, br, h, special, &aEnd[e]);
-                        plain = plain && inb && !special;
-                    }
+                    const StickStep q0 = d_step<K, true>(c, t, pl.nd, t.tauLo), q1 = d_step<K, true>(c, t, pl.nd, last);
                     // "away from column 0" is the union of two half planes: both ends must lie in the SAME one (a steep
                     // column can enter the strip |alpha| <= rho between two ends that are outside it on opposite sides)
-                    plain = plain && (aEnd[0] * aEnd[1] > 0.f);
+                    plain = q0.inb && q1.inb && !q0.special && !q1.special && (q0.sg == q1.sg);
+                    aFirst = q0.sg;
                 }
                 // which of a column's two lanes owns an accumulator depends on the parity of the column's first depth in
                 // THIS plane, so consecutive tasks may touch the same shared address from different lanes: order them
                 __syncwarp();
-                if (__all_sync(0xffffffffu, plain)) touched |= d_task_run<K, false, kFlags>(c, t, pl, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
-                else touched |= d_task_run<K, true, kFlags>(c, t, pl, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                if (__all_sync(0xffffffffu, plain)) {
+                    if (aFirst < 0.f) {        // the lane's whole walk lies in the mirrored half: flip it once
+                        t.sg = -1.f;
+                        t.ja0 = -t.ja0; t.jb0 = -t.jb0;
+                        t.arL = -t.arL; t.brL = -t.brL;
+                        t.e1d = -t.e1d; t.e2d = -t.e2d;
+                    }
+                    touched |= d_task_run<K, false, kFlags>(c, t, pl, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
+                } else
+                    touched |= d_task_run<K, true, kFlags>(c, t, pl, nIter, a.slices, imgStride, a.rimTab, accV, accW, col);
             }
         }
 
@@ -904,7 +755,13 @@ __global__ void __launch_bounds__(128) k_edge2(const __grid_constant__ Edge2Args
                         px = __ldg(C0 + (ip + Rp));
                         mult = ((rt & 0x3fff) - 1) >= 0 ? 1.f : 0.f;   // original (0, ip) valid?
                     } else {
-                        px = __ldg(reinterpret_cast<const float2*>(S + (size_t)(ip + Rp) * pitch + (j + Rp)));
+                        // half-plane slices: columns j < -colOff are the conjugates of the stored (-ip, -j)
+                        if (j >= -geo.colOff) {
+                            px = __ldg(reinterpret_cast<const float2*>(S + (size_t)(ip + Rp) * pitch + (j + geo.colOff)));
+                        } else {
+                            px = __ldg(reinterpret_cast<const float2*>(S + (size_t)(-ip + Rp) * pitch + (-j + geo.colOff)));
+                            px.y = -px.y;
+                        }
                         mult = d_rim_mult(rt, j);
                     }
                     accRe += (double)w * px.x;

@@ -96,7 +96,12 @@ struct Geometry {
     float sMax;                    // r^2 * iDelta: largest scaled squared distance inside the blob
     float reach;                   // maxRes*Z + r: no lattice point farther than this is touched
     float inplane_reach;           // R + rho (pixel units)
-    // slice format v2 (stick gather): per image side x pitch float4 entries (pixel(i,j), pixel(i,j+1))
+    // slice format v3 (stick gather): HALF-plane slices of overlapping pixel pairs.  Per image `side` rows (centred row i
+    // at i + Rp) of `pitch` float4 entries; entry (i, j) = (pixel(i,j), pixel(i,j+1)) sits at column j + colOff for
+    // j in [-colOff, Rp].  Pixels with j < -colOff are not stored: the full-plane slice F is Hermitian, F(-i,-j) =
+    // conj F(i,j) (originals for j > 0, mirrors for j < 0, their sum on j = 0), so a voxel projecting to alpha < 0 is
+    // gathered at (-alpha, -beta) and its sum conjugated.  Half the bytes of the full-plane format for K1c to write.
+    int32_t colOff;                // stored columns left of j = 0 (= K: enough for any window of a voxel with alpha >= 0)
     int32_t pitch;                 // row pitch in entries
     int32_t planeStride;           // side * pitch entries per image
     int32_t xOwnMax;               // largest ux owned by the main gather (originals and mirrors both land there)
