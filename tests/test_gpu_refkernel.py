@@ -82,6 +82,11 @@ def test_reference_blob_kernel_agrees_with_the_exact_path(oracle_mod, refk, case
         Vr, Wr = k.temp_spaces()
     finally:
         k.close()
+    bad = ~(np.isfinite(Wr) & np.isfinite(Vr.real) & np.isfinite(Vr.imag))
+    if bad.any():        # diagnostic: where does the reference kernel produce non-finite sums?
+        zz0, yy0, xx0 = np.nonzero(bad)
+        rad = np.sqrt((zz0 - host.S / 2.0) ** 2 + (yy0 - host.S / 2.0) ** 2 + (xx0 - host.S / 2.0) ** 2)
+        print("reference kernel: %d non-finite voxels, radius %.1f .. %.1f of %d" % (bad.sum(), rad.min(), rad.max(), host.S // 2))
     host.set_temp_spaces(Vr, Wr)
     Vh, Wh = host.half_spaces()                                # [S+1, S+1, S/2+1], centred (z, y), x >= 0
     ref_map = host.finalize()
@@ -97,7 +102,7 @@ def test_reference_blob_kernel_agrees_with_the_exact_path(oracle_mod, refk, case
     S, Z = host.S, o.Z
     c = np.arange(-(S // 2), S // 2 + 1)
     zz, yy, xx = np.meshgrid(c, c, np.arange(0, S // 2 + 1), indexing="ij")
-    inner = (zz ** 2 + yy ** 2 + xx ** 2 <= (0.8 * S / 2) ** 2) & (xx >= 1)
+    inner = (zz ** 2 + yy ** 2 + xx ** 2 <= (0.8 * S / 2) ** 2) & (xx >= 1) & np.isfinite(Wh) & np.isfinite(Vh.real) & np.isfinite(Vh.imag)
     iz, iy, ix = zz[inner] % Z, yy[inner] % Z, xx[inner]
     res = {}
     for name, (V, W) in (("oracle", (Vo, Wo)), ("gpu", (Vg, Wg))):
