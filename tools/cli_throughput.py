@@ -16,9 +16,9 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("-n", type=int, default=16384)
+    ap.add_argument("-n", type=int, default=32768)
     ap.add_argument("--box", type=int, default=256)
-    ap.add_argument("--thr", type=int, nargs="+", default=[1, 4, 16])
+    ap.add_argument("--thr", type=int, nargs="+", default=[4, 16])
     ap.add_argument("--buffer", type=int, default=1024)
     ap.add_argument("--dir", default=None)
     ap.add_argument("--gpus", default="1", help="passed to the CLI as --gpus (a number or 'all')")

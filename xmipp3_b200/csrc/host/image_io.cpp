@@ -17,17 +17,18 @@
 
 namespace rfhost {
 
-namespace {
+enum class ImageKind { SPIDER, MRC };
 
-enum class Kind { SPIDER, MRC };
-
-struct OpenFile {
-    OpenFile() = default;
-    OpenFile(const OpenFile&) = delete;
-    OpenFile& operator=(const OpenFile&) = delete;
-    ~OpenFile() { if (fd >= 0) close(fd); }      // the last holder (cache entry or a reader in flight) closes the descriptor
+// An open image file: header decoded once, descriptor owned (closed by the last holder: the cache entry or a reader in
+// flight).
+struct ImageSource {
+    ImageSource() = default;
+    ImageSource(const ImageSource&) = delete;
+    ImageSource& operator=(const ImageSource&) = delete;
+    ~ImageSource() { if (fd >= 0) close(fd); }
+    std::string path;
     int fd = -1;
-    Kind kind = Kind::SPIDER;
+    ImageKind kind = ImageKind::SPIDER;
     bool swap = false;
     ImageInfo info;
     // Spider: header bytes of the file and of each stacked image; MRC: data offset and mode
@@ -35,6 +36,11 @@ struct OpenFile {
     int mrcMode = 2;
     bool isStack = false;
 };
+
+namespace {
+
+using Kind = ImageKind;
+using OpenFile = ImageSource;
 
 // Open files are shared between the cache and the readers that are using them: evicting an entry only drops the
 // cache's reference, so a loader thread in the middle of a pread keeps a valid descriptor (the CLI runs up to 16 loader
@@ -79,6 +85,7 @@ void preadAll(int fd, void* buf, size_t n, off_t off, const std::string& what) {
 FilePtr openFile(const std::string& path, const std::string& fmt) {
     auto fp = std::make_shared<OpenFile>();      // owns the descriptor from here on: every throw below closes it
     OpenFile& f = *fp;
+    f.path = path;
     f.fd = open(path.c_str(), O_RDONLY);
     if (f.fd < 0) throw std::runtime_error("cannot open image file " + path);
     struct stat st;
@@ -248,7 +255,13 @@ void readImage2D(const std::string& spec, float* out, int nx, int ny) {
     std::string path, fmt;
     parseImageName(spec, idx, path, fmt);
     const FilePtr fp = cached(path, fmt);      // keeps the descriptor open for the duration of the read
-    const OpenFile& f = *fp;
+    readImage2D(*fp, idx, out, nx, ny);
+}
+
+std::shared_ptr<const ImageSource> openImageSource(const std::string& path, const std::string& fmt) { return cached(path, fmt); }
+
+void readImage2D(const ImageSource& f, size_t idx, float* out, int nx, int ny) {
+    const std::string& spec = f.path;
     if (f.info.nx != nx || f.info.ny != ny)
         throw std::runtime_error("image " + spec + " is " + std::to_string(f.info.nx) + "x" + std::to_string(f.info.ny) +
                                  ", expected " + std::to_string(nx) + "x" + std::to_string(ny));
@@ -256,7 +269,7 @@ void readImage2D(const std::string& spec, float* out, int nx, int ny) {
     size_t k = idx ? idx - 1 : 0;
     // a ".mrc" volume addressed with an index is treated as a stack of slices
     size_t avail = f.isStack ? f.info.nImages : (size_t)f.info.nz * f.info.nImages;
-    if (k >= avail) throw std::runtime_error("image index out of range: " + spec);
+    if (k >= avail) throw std::runtime_error("image index " + std::to_string(idx) + " out of range in " + spec);
     if (f.kind == Kind::SPIDER) {
         off_t off = f.isStack ? (off_t)(f.fileHeader + k * (f.imgHeader + count * 4) + f.imgHeader) : (off_t)(f.fileHeader + k * count * 4);
         preadAll(f.fd, out, count * 4, off, spec);

@@ -10,6 +10,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <string>
 
 namespace rfhost {
@@ -27,6 +28,13 @@ ImageInfo readImageInfo(const std::string& spec);
 // Read the 2-D image designated by `spec` as float32 (nx*ny values, row-major, y outer).
 // Throws std::runtime_error if the file is unreadable or the size differs from (nx, ny).
 void readImage2D(const std::string& spec, float* out, int nx, int ny);
+
+// The same in two steps, for loaders that read many images of few files: an ImageSource is an open file with its
+// header decoded (shared with the descriptor cache; the descriptor stays valid for as long as the pointer is held), and
+// reading from it involves no name parsing, no lock and no copy: one pread per image straight into `out`.
+struct ImageSource;
+std::shared_ptr<const ImageSource> openImageSource(const std::string& path, const std::string& fmt);
+void readImage2D(const ImageSource& src, size_t index /* 1-based, 0 = the only image */, float* out, int nx, int ny);
 
 // Write helpers.  The format is chosen from the extension / ":fmt" suffix:
 //   .vol .spi .xmp .stk -> Spider,  .mrc .mrcs .map -> MRC (mode 2)

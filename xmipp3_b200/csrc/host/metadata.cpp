@@ -87,6 +87,15 @@ double MetaData::getValueOrDefault(const std::string& label, size_t i, double de
     return getValue(label, i, v) ? v : def;
 }
 
+double MetaData::cellOrDefault(size_t i, int col, double def) const {
+    if (col < 0) return def;
+    const std::string& s = rows_[i][(size_t)col];
+    if (s.empty()) return def;
+    char* end = nullptr;
+    const double v = strtod(s.c_str(), &end);
+    return end == s.c_str() ? def : v;
+}
+
 void MetaData::removeDisabled() {
     auto it = index_.find("enabled");
     if (it == index_.end()) return;

@@ -34,6 +34,14 @@ public:
     bool getValue(const std::string& label, size_t i, double& out) const;
     double getValueOrDefault(const std::string& label, size_t i, double def) const;
 
+    // column access for loops over many rows: resolve the label once (-1 if absent), then read cells by index
+    int column(const std::string& label) const {
+        auto it = index_.find(label);
+        return it == index_.end() ? -1 : (int)it->second;
+    }
+    const std::string& cell(size_t i, int col) const { return rows_[i][(size_t)col]; }
+    double cellOrDefault(size_t i, int col, double def) const;
+
     // drop rows whose `enabled` column is <= 0 (MetaData::removeDisabled)
     void removeDisabled();
 

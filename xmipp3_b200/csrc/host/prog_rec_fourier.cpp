@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <libgen.h>
+#include <sched.h>
 #include <signal.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -16,6 +17,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -123,6 +125,55 @@ void ctfFromRow(const MetaData& md, size_t i, rfb200_particle& p) {
     p.envR2 = md.getValueOrDefault("ctfEnvR2", i, 0);
     p.phase_shift = md.getValueOrDefault("ctfPhaseShift", i, 0);
     p.vpp_radius = md.getValueOrDefault("ctfVPPRadius", i, 0);
+}
+
+// Columns of the particle metadata resolved once (the per-row accessors look labels up in a map and build strings).
+struct ParticleCols {
+    int rot, tilt, psi, sx, sy, weight, image, ctfModel;
+    int ctf[18];
+    bool inlineCtf = false;
+    explicit ParticleCols(const MetaData& md) {
+        rot = md.column("angleRot"); tilt = md.column("angleTilt"); psi = md.column("anglePsi");
+        sx = md.column("shiftX"); sy = md.column("shiftY"); weight = md.column("weight");
+        image = md.column("image"); ctfModel = md.column("ctfModel");
+        static const char* names[18] = {"ctfVoltage", "ctfDefocusU", "ctfDefocusV", "ctfDefocusAngle", "ctfSphericalAberration",
+                                        "ctfChromaticAberration", "ctfEnergyLoss", "ctfLensStability", "ctfConvergenceCone",
+                                        "ctfLongitudinalDisplacement", "ctfTransversalDisplacement", "ctfQ0", "ctfK", "ctfEnvR0",
+                                        "ctfEnvR1", "ctfEnvR2", "ctfPhaseShift", "ctfVPPRadius"};
+        for (int k = 0; k < 18; ++k) ctf[k] = md.column(names[k]);
+        inlineCtf = ctf[1] >= 0;
+    }
+};
+// same values as ctfFromRow / particleFromRow, by column index
+void particleFromCols(const MetaData& md, const ParticleCols& c, size_t i, bool hasCtf, rfb200_particle& p) {
+    memset(&p, 0, sizeof p);
+    p.rot = md.cellOrDefault(i, c.rot, 0);
+    p.tilt = md.cellOrDefault(i, c.tilt, 0);
+    p.psi = md.cellOrDefault(i, c.psi, 0);
+    p.shift_x = md.cellOrDefault(i, c.sx, 0);
+    p.shift_y = md.cellOrDefault(i, c.sy, 0);
+    p.weight = md.cellOrDefault(i, c.weight, 1);
+    p.kV = 100;
+    p.K = 1;
+    if (!hasCtf || !c.inlineCtf) return;
+    p.kV = md.cellOrDefault(i, c.ctf[0], 100);
+    p.defocusU = md.cellOrDefault(i, c.ctf[1], 0);
+    p.defocusV = md.cellOrDefault(i, c.ctf[2], p.defocusU);
+    p.defocus_angle = md.cellOrDefault(i, c.ctf[3], 0);
+    p.Cs = md.cellOrDefault(i, c.ctf[4], 0);
+    p.Ca = md.cellOrDefault(i, c.ctf[5], 0);
+    p.espr = md.cellOrDefault(i, c.ctf[6], 0);
+    p.ispr = md.cellOrDefault(i, c.ctf[7], 0);
+    p.alpha = md.cellOrDefault(i, c.ctf[8], 0);
+    p.DeltaF = md.cellOrDefault(i, c.ctf[9], 0);
+    p.DeltaR = md.cellOrDefault(i, c.ctf[10], 0);
+    p.Q0 = md.cellOrDefault(i, c.ctf[11], 0);
+    p.K = md.cellOrDefault(i, c.ctf[12], 1);
+    p.envR0 = md.cellOrDefault(i, c.ctf[13], 0);
+    p.envR1 = md.cellOrDefault(i, c.ctf[14], 0);
+    p.envR2 = md.cellOrDefault(i, c.ctf[15], 0);
+    p.phase_shift = md.cellOrDefault(i, c.ctf[16], 0);
+    p.vpp_radius = md.cellOrDefault(i, c.ctf[17], 0);
 }
 
 struct Args {
@@ -385,6 +436,17 @@ void ProgRecFourierB200::runRanks() {
             rank = r;
             worldSize = n;
             idFile = tmpl;
+            // the ranks share the host: every rank gets its slice of the loader threads and of the cores (the reference's
+            // MPI program leaves this to mpirun's binding)
+            {
+                const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+                numThreads = std::max(1, numThreads / n);
+                const int c0 = (int)((long)cores * r / n), c1 = std::max(c0 + 1, (int)((long)cores * (r + 1) / n));
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                for (int c = c0; c < c1 && c < CPU_SETSIZE; ++c) CPU_SET(c, &set);
+                sched_setaffinity(0, sizeof set, &set);       // best effort
+            }
             device += r;
             gpus = 1;
             if (r > 0) verbose = 0;
@@ -543,15 +605,56 @@ void ProgRecFourierB200::run() {
     auto t0 = std::chrono::steady_clock::now();
     std::string loadError;
     std::mutex errM;
+    // ---- loader (the reference's prepareBuffer threads, reconstruct_fourier_gpu.cpp:323-415, minus their CPU FFT): every
+    // row is resolved ONCE to (file, image index) — the path lookups and stat() calls of imageOfRow happen per distinct
+    // file, not per particle — and a loader thread then needs one pread per image, straight into the page-locked batch
+    // buffer: no name parsing, no lock, no intermediate copy.  Metadata cells are read by column index.
+    const ParticleCols cols(SF);
+    if (cols.image < 0) throw ProgramError("metadata has no 'image' column");
+    struct RowRef { uint32_t file; uint32_t index; };
+    std::vector<RowRef> rowRef(n);
+    std::vector<std::pair<std::string, std::string>> files;       // resolved path, format
+    {
+        std::map<std::string, uint32_t> known;                    // "path:fmt" as written in the metadata -> files[]
+        for (size_t i = 0; i < n; ++i) {
+            size_t idx;
+            std::string path, fmt;
+            parseImageName(SF.cell(i, cols.image), idx, path, fmt);
+            const std::string key = path + ":" + fmt;
+            auto it = known.find(key);
+            if (it == known.end()) {
+                std::string resolved = path;
+                if (!path.empty() && path[0] != '/' && !fileExists(path) && !mdDir.empty() && fileExists(mdDir + "/" + path))
+                    resolved = mdDir + "/" + path;                // relative to the metadata file
+                files.emplace_back(resolved, fmt);
+                it = known.emplace(key, (uint32_t)files.size() - 1).first;
+            }
+            rowRef[i] = {it->second, (uint32_t)idx};
+        }
+    }
+    const bool ctfFromModel = hasCtf && !cols.inlineCtf;          // .ctfparam indirection: the slow accessor handles it
     auto loadBatch = [&](size_t first, size_t cnt, int slot) {
         std::atomic<size_t> next(0);
         auto worker = [&] {
+            std::shared_ptr<const ImageSource> src;               // the file of the previous image: stacks hit this every time
+            uint32_t srcFile = UINT32_MAX;
             for (;;) {
-                size_t k = next.fetch_add(1);
-                if (k >= cnt) return;
+                // blocks of 8 consecutive images per grab: neighbouring reads stay on one thread (read-ahead friendly)
+                const size_t k0 = next.fetch_add(8);
+                if (k0 >= cnt) return;
+                const size_t k1 = std::min(cnt, k0 + 8);
                 try {
-                    particleFromRow(SF, first + k, hasCtf, mdDir, meta[slot][k]);
-                    readImage2D(imageOfRow(SF, first + k, mdDir), &buf[slot][k * (size_t)N * N], N, N);
+                    for (size_t k = k0; k < k1; ++k) {
+                        const size_t row = first + k;
+                        if (ctfFromModel) particleFromRow(SF, row, hasCtf, mdDir, meta[slot][k]);
+                        else particleFromCols(SF, cols, row, hasCtf, meta[slot][k]);
+                        const RowRef& rr = rowRef[row];
+                        if (rr.file != srcFile) {
+                            src = openImageSource(files[rr.file].first, files[rr.file].second);
+                            srcFile = rr.file;
+                        }
+                        readImage2D(*src, rr.index, &buf[slot][k * (size_t)N * N], N, N);
+                    }
                 } catch (const std::exception& e) {
                     std::lock_guard<std::mutex> g(errM);
                     if (loadError.empty()) loadError = e.what();
