@@ -161,6 +161,10 @@ def test_cli_parsing_defaults_and_errors():
     assert d["gpus"] == "1" and d["worldSize"] == "1"
     assert _host.parse_cli(["-i", "a.xmd", "--gpus", "4"])["gpus"] == "4"
     assert _host.parse_cli(["-i", "a.xmd", "--gpus", "all"])["gpus"] == "-1"
+    # flags of xmipp_mpi_cuda_reconstruct_fourier (mpi_reconstruct_fourier_gpu.cpp:52-65): one node, static sharding
+    d = _host.parse_cli(["-i", "a.xmd", "--mpi_job_size", "500", "-gpusPerNode", "4", "-threadsPerGPU", "3"])
+    assert d["gpus"] == "4" and d["threads"] == "12"
+    assert _host.parse_cli(["-i", "a.xmd", "-gpusPerNode", "4", "--gpus", "2"])["gpus"] == "2"
     for bad in (["-o", "x.vol"], ["-i", "a.xmd", "--bogus"], ["-i", "a.xmd", "--padding", "two"], ["-i", "a.xmd", "--gpus", "0"],
                 ["-i", "a.xmd", "--gpus"]):
         with pytest.raises(_host.HostError):

@@ -233,6 +233,10 @@ std::string ProgRecFourierB200::usage() {
         "                                       per GPU on a shard of the particles, one NCCL reduce before the\n"
         "                                       normalisation (replaces mpirun xmipp_mpi_cuda_reconstruct_fourier)\n"
         "  [--fftOnGPU]                       : accepted for compatibility (the FFT always runs on the GPU)\n"
+        "  [-gpusPerNode <num>]               : (xmipp_mpi_cuda_reconstruct_fourier) GPUs to use on this node: same as --gpus\n"
+        "  [-threadsPerGPU <num>]             : (xmipp_mpi_cuda_reconstruct_fourier) loader threads per GPU: --thr = num x gpus\n"
+        "  [--mpi_job_size <size=1000>]       : (xmipp_mpi_cuda_reconstruct_fourier) accepted and ignored: the particles are\n"
+        "                                       sharded statically, one contiguous range per GPU\n"
         "  [--fast]                           : Do the blobing at the end of the computation (nearest-pixel insertion,\n"
         "                                       one final blob convolution). Gives slightly different results;\n"
         "                                       --iter and --padding <proj> are then ignored like in the reference\n"
@@ -245,7 +249,8 @@ void ProgRecFourierB200::readParams(int argc, const char* const* argv) {
     for (int i = 1; i < argc; ++i) a.v.push_back(argv[i]);
     static const char* known[] = {"-i", "-o", "--iter", "--sym", "--padding", "--prepare_fsc", "--max_resolution", "--weight",
                                   "--thr", "--blob", "--useCTF", "--sampling", "--phaseFlipped", "--minCTF", "--device",
-                                  "--bufferSize", "--fftOnGPU", "--fast", "--gpus", "-v", "-h", "--help"};
+                                  "--bufferSize", "--fftOnGPU", "--fast", "--gpus", "-v", "-h", "--help",
+                                  "--mpi_job_size", "-gpusPerNode", "-threadsPerGPU"};
     for (auto& t : a.v) {
         bool isOpt = t.size() > 1 && t[0] == '-' && !(isdigit((unsigned char)t[1]) || t[1] == '.');
         if (!isOpt) continue;
@@ -303,6 +308,11 @@ void ProgRecFourierB200::readParams(int argc, const char* const* argv) {
             gpus = v[0] == "all" ? -1 : (int)toDouble(v[0], "--gpus");
             if (gpus == 0 || gpus < -1) throw ProgramError("--gpus must be a positive number or \"all\"");
         }
+        // flags of the MPI + CUDA program (parallel_adapt_cuda/mpi_reconstruct_fourier_gpu.cpp:52-65): one node here
+        d = 0; num("-gpusPerNode", 0, d);
+        if (d >= 1 && a.find("--gpus") == std::string::npos) gpus = (int)d;
+        d = 0; num("-threadsPerGPU", 0, d);
+        if (d >= 1 && a.find("--thr") == std::string::npos) numThreads = std::max(1, (int)d * std::max(1, gpus));
     }
     // ranks started by an external launcher (one process per GPU, like the MPI program's workers)
     if (const char* e = getenv("RFB200_WORLD_SIZE")) {
@@ -675,6 +685,12 @@ void ProgRecFourierB200::run() {
         const bool saveFSC = !fn_fsc.empty();
         const size_t FSCIndex = (n - 1) / 2;
         std::vector<float> vol((size_t)N * N * N);
+        double tInsert = 0, tReduce = 0, tFinish = 0;      // wall seconds per phase (this rank)
+        struct PhaseTimer {
+            double& t;
+            std::chrono::steady_clock::time_point a;
+            ~PhaseTimer() { t += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); }
+        };
         auto insertRange = [&](size_t begin, size_t end) {
             if (worldSize > 1) {    // this rank's contiguous shard of [begin, end)
                 // sizes differ by at most one, earlier ranks get the extra (same rule as xmipp3_b200/sharding.py)
@@ -684,6 +700,7 @@ void ProgRecFourierB200::run() {
                 end = begin + base + (r < extra ? 1 : 0);
             }
             if (begin >= end) return;
+            PhaseTimer acc{tInsert, std::chrono::steady_clock::now()};
             loadBatch(begin, std::min(B, end - begin), slot);
             for (size_t first = begin; first < end; first += B, slot ^= 1) {
                 const size_t cnt = std::min(B, end - first);
@@ -703,12 +720,14 @@ void ProgRecFourierB200::run() {
         // every rank's partial V and W are summed onto rank 0 over NVLink; the others are done with these particles
         auto reduce = [&] {
             if (worldSize == 1) return;
+            PhaseTimer acc{tReduce, std::chrono::steady_clock::now()};
             rc = api.reduce_nccl(h, 0);
             if (rc != RFB200_OK) throw ProgramError(std::string("reduce failed: ") + api.last_error(h));
             if (rank != 0 && api.reset(h) != RFB200_OK) throw ProgramError(std::string("reset failed: ") + api.last_error(h));
         };
         auto finish = [&](const std::string& name) {
             if (rank != 0) return;
+            PhaseTimer acc{tFinish, std::chrono::steady_clock::now()};
             rc = api.finalize(h, vol.data());                                                   // RF.cpp:1056-1180
             if (rc != RFB200_OK) throw ProgramError(std::string("finalize failed: ") + api.last_error(h));
             writeVolume(name, vol.data(), N, N, N);                                             // RF.cpp:1179
@@ -734,6 +753,8 @@ void ProgRecFourierB200::run() {
             if (api.get_timings(h, &t) == RFB200_OK)
                 std::cout << " GPU time (ms): h2d " << t.h2d_ms << ", pad " << t.preprocess_ms << ", fft " << t.fft2d_ms << ", slices "
                           << t.slice_ms << ", gather " << t.gather_ms << ", edge " << t.edge_ms << ", finalize " << t.finalize_ms << "\n";
+            std::cout << " wall (s): load + insert " << tInsert << ", reduce (incl. waiting for the slowest rank and, the first time, NCCL's connection set-up) "
+                      << tReduce << ", finalize + write " << tFinish << "\n";
             std::cout << " " << n << " images in " << secs << " s (" << n / secs << " images/s including file I/O"
                       << (worldSize > 1 ? ", " + std::to_string(worldSize) + " GPUs" : std::string()) << ")" << std::endl;
         }
