@@ -167,12 +167,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def time_oracle(box, n_sample, threads, ctf=True, seed=100):
+def time_oracle(box, n_sample, threads, ctf=True, seed=100, sym="c1"):
     """Time the CPU oracle (port of ProgRecFourier, reference thread scheme) on n_sample particles."""
     from oracle import oracle as O
     img, cols = synth_batch_numpy(n_sample, box, seed, ctf)
     p = O.make_particles(n_sample, **cols)
-    o = O.Oracle(box, use_ctf=ctf, sampling=SAMPLING)
+    mats = None
+    if sym != "c1":
+        from xmipp3_b200 import geometry
+        mats = geometry.point_group_matrices(sym)
+    o = O.Oracle(box, use_ctf=ctf, sampling=SAMPLING, sym_matrices=mats)
     o.insert(img[: min(threads, n_sample)], p[: min(threads, n_sample)], threads=threads)   # touch pages, spin up
     t = time.perf_counter()
     o.insert(img, p, threads=threads)
@@ -638,6 +642,13 @@ def main():
         for cfg in OTHER_CONFIGS:
             try:
                 oc.append(measure_other_config(cfg, dev, local, rank, world, max_over_ranks, barrier_all))
+                if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                    # the CPU arm on a small sample of the same configuration (about 2-4 s each)
+                    cores = os.cpu_count() or 1
+                    n_s = {64: 1000, 128: 400, 256: 32, 512: 32}[cfg["box"]]
+                    rate, dt = time_oracle(cfg["box"], n_s, cores, ctf=cfg["ctf"], seed=300, sym=cfg["sym"])
+                    oc[-1]["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                              "sample": "%d particles in %.1f s (oracle port, reference thread scheme)" % (n_s, dt)}
             except Exception as e:      # one configuration failing must not take the headline line with it
                 oc.append({"workload": cfg["name"], "error": "%s: %s" % (type(e).__name__, e)})
         extra["other_configs"] = oc

@@ -100,6 +100,11 @@ struct rfb200_handle_s {
     std::string err;
 
     cudaStream_t compute = nullptr, copy = nullptr;
+    // side stream: the edge kernel and the damped-weight scatter of a chunk touch voxels / buffers the stick gather of the
+    // same chunk never touches, so they run beside it and soak up the tails of its launches
+    cudaStream_t aux = nullptr;
+    cudaEvent_t evSlices = nullptr, evAux = nullptr;
+    bool auxPending = false;
     // static device data
     float* dBlobTable = nullptr;
     int* dJmax = nullptr;
@@ -212,6 +217,16 @@ namespace {
 int fail(rfb200_handle h, int code, const std::string& msg) {
     h->err = msg;
     return code;
+}
+
+// make the compute stream wait for the side stream's kernels of the last chunk (before anything reads or overwrites what
+// they read or write: V, W, the damped-weight volume, the chunk's parameter and slice buffers)
+int join_aux(rfb200_handle h) {
+    if (h->auxPending) {
+        RF_CUDA(h, cudaStreamWaitEvent(h->compute, h->evAux, 0));
+        h->auxPending = false;
+    }
+    return RFB200_OK;
 }
 
 cudaEvent_t get_event(rfb200_handle h) {
@@ -365,6 +380,7 @@ int launch_fused_fft(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& 
 
 // W += weights of the CTF-damped pixels; must run before W is read, reduced or copied
 int flush_deficit(rfb200_handle h) {
+    if (int rj = join_aux(h)) return rj;
     if (h->fast && h->fastDirty) {      // --fast: fold the scratch accumulators into V and W
         k_fast_flush<<<2048, 256, 0, h->compute>>>(h->dFastAcc, h->dVb, h->dWb, h->nBlocked);
         RF_CUDA(h, cudaGetLastError());
@@ -425,6 +441,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
     ParamSlot& s = h->slots[h->slotIdx];
     h->slotIdx ^= 1;
     if (s.used) RF_CUDA(h, cudaEventSynchronize(s.done));
+    if (int rj = join_aux(h)) return rj;       // the previous chunk's side kernels still read its parameter buffers
     const Geometry& g = h->geo;
     const double pixPerVox = (double)g.P / (double)g.Z;
     int np = 0;
@@ -522,6 +539,41 @@ Slice2Args make_slice_args(rfb200_handle h) {
 int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
     const Geometry& g = h->geo;
     int rc = RFB200_OK;
+    // ---- side stream: edge voxels and damped-pixel weights.  They need this chunk's slices / masks / planes (ready on
+    // the compute stream at this point) and write where the stick gather never does (edge targets are exactly the voxels
+    // it does not own; the damped weights go to their own fixed-point volume), so they run beside the gather launches.
+    if (nPlanes && (h->nEdge || h->dDamped)) {
+        RF_CUDA(h, cudaEventRecord(h->evSlices, h->compute));
+        RF_CUDA(h, cudaStreamWaitEvent(h->aux, h->evSlices, 0));
+        if (h->nEdge) {
+            StageTimer t(h, Stage::EDGE, h->aux);
+            Edge2Args e{};
+            e.geo = g;
+            e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
+            e.planesD = h->dPlanesD; e.planeImg = h->dPlaneImg; e.img = h->dImg; e.nPlanes = nPlanes;
+            e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
+            e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
+            e.iDeltaD = h->tables.iDeltaSqrt;
+            k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->aux>>>(e);      // one warp per target voxel
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 1;
+        }
+        if (h->dDamped) {
+            StageTimer t(h, Stage::EDGE, h->aux);
+            DampedArgs d{};
+            d.geo = g;
+            d.mask = h->dDampedMask; d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
+            d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
+            d.D = h->dD; d.D2 = h->dD2;
+            const int nWords = ((g.R + 1 + 31) / 32) * (2 * g.R + 1);
+            k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, h->aux>>>(d);
+            RF_CUDA(h, cudaGetLastError());
+            h->nKernelLaunches += 1;
+            h->dampedDirty = true;
+        }
+        RF_CUDA(h, cudaEventRecord(h->evAux, h->aux));
+        h->auxPending = true;
+    }
     if (nPlanes) {
         RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, sizeof(int) * slot->launches.size(), h->compute));
         StageTimer t(h, Stage::GATHER, h->compute);
@@ -546,32 +598,6 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
             h->nKernelLaunches += 1;
             h->nGatherLaunches += 1;
         }
-    }
-    if (h->nEdge && nPlanes) {
-        StageTimer t(h, Stage::EDGE, h->compute);
-        Edge2Args e{};
-        e.geo = g;
-        e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
-        e.planesD = h->dPlanesD; e.planeImg = h->dPlaneImg; e.img = h->dImg; e.nPlanes = nPlanes;
-        e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
-        e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
-        e.iDeltaD = h->tables.iDeltaSqrt;
-        k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->compute>>>(e);      // one warp per target voxel
-        RF_CUDA(h, cudaGetLastError());
-        h->nKernelLaunches += 1;
-    }
-    if (h->dDamped && nPlanes) {
-        StageTimer t(h, Stage::EDGE, h->compute);
-        DampedArgs d{};
-        d.geo = g;
-        d.mask = h->dDampedMask; d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
-        d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
-        d.D = h->dD; d.D2 = h->dD2;
-        const int nWords = ((g.R + 1 + 31) / 32) * (2 * g.R + 1);
-        k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, h->compute>>>(d);
-        RF_CUDA(h, cudaGetLastError());
-        h->nKernelLaunches += 1;
-        h->dampedDirty = true;
     }
     return RFB200_OK;
 }
@@ -724,6 +750,7 @@ void free_all(rfb200_handle h) {
     cudaSetDevice(h->cfg.device);
     if (h->compute) cudaStreamSynchronize(h->compute);
     if (h->copy) cudaStreamSynchronize(h->copy);
+    if (h->aux) cudaStreamSynchronize(h->aux);
     resolve_timings(h);
     for (auto e : h->evPool) cudaEventDestroy(e);
     if (h->swStart) cudaEventDestroy(h->swStart);
@@ -753,6 +780,9 @@ void free_all(rfb200_handle h) {
 #endif
     if (h->compute) cudaStreamDestroy(h->compute);
     if (h->copy) cudaStreamDestroy(h->copy);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->evSlices) cudaEventDestroy(h->evSlices);
+    if (h->evAux) cudaEventDestroy(h->evAux);
     delete h;
 }
 
@@ -903,6 +933,9 @@ int do_create(rfb200_handle h) {
     // ---- streams / events
     RF_CUDA(h, cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     RF_CUDA(h, cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    RF_CUDA(h, cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    RF_CUDA(h, cudaEventCreateWithFlags(&h->evSlices, cudaEventDisableTiming));
+    RF_CUDA(h, cudaEventCreateWithFlags(&h->evAux, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         RF_CUDA(h, cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming));
         RF_CUDA(h, cudaEventCreateWithFlags(&h->evRawFree[i], cudaEventDisableTiming));
@@ -1122,6 +1155,8 @@ int rfb200_sync(rfb200_handle h) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    if (h->aux) RF_CUDA(h, cudaStreamSynchronize(h->aux));
+    h->auxPending = false;
     resolve_timings(h);
     return RFB200_OK;
 }
@@ -1331,6 +1366,7 @@ int rfb200_timer_start(rfb200_handle h) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     // make the compute stream wait for any copy still in flight so that the stopwatch starts "behind everything"
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
+    if (int rj = join_aux(h)) return rj;
     RF_CUDA(h, cudaEventRecord(h->swStart, h->compute));
     h->swStarted = true;
     return RFB200_OK;
@@ -1340,6 +1376,7 @@ int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms) {
     if (!h || !elapsed_ms) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
+    if (int rj = join_aux(h)) return rj;       // the stopwatch stops behind the side stream too
     RF_CUDA(h, cudaEventRecord(h->swStop, h->compute));
     RF_CUDA(h, cudaEventSynchronize(h->swStop));
     float ms = 0;
