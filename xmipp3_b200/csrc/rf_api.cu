@@ -539,26 +539,14 @@ Slice2Args make_slice_args(rfb200_handle h) {
 int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
     const Geometry& g = h->geo;
     int rc = RFB200_OK;
-    // ---- side stream: edge voxels and damped-pixel weights.  They need this chunk's slices / masks / planes (ready on
-    // the compute stream at this point) and write where the stick gather never does (edge targets are exactly the voxels
-    // it does not own; the damped weights go to their own fixed-point volume), so they run beside the gather launches.
-    if (nPlanes && (h->nEdge || h->dDamped)) {
+    // ---- side stream: the damped-pixel weights go to their own fixed-point volume and only need this chunk's masks and
+    // planes (ready on the compute stream at this point), so that scatter runs beside the gather launches.  (The edge
+    // kernel stays on the compute stream: the wrap-around aliases at the Nyquist faces add into voxels the stick gather
+    // owns, and the order of those additions must not depend on scheduling.)
+    if (nPlanes && h->dDamped) {
         RF_CUDA(h, cudaEventRecord(h->evSlices, h->compute));
         RF_CUDA(h, cudaStreamWaitEvent(h->aux, h->evSlices, 0));
-        if (h->nEdge) {
-            StageTimer t(h, Stage::EDGE, h->aux);
-            Edge2Args e{};
-            e.geo = g;
-            e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
-            e.planesD = h->dPlanesD; e.planeImg = h->dPlaneImg; e.img = h->dImg; e.nPlanes = nPlanes;
-            e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
-            e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
-            e.iDeltaD = h->tables.iDeltaSqrt;
-            k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->aux>>>(e);      // one warp per target voxel
-            RF_CUDA(h, cudaGetLastError());
-            h->nKernelLaunches += 1;
-        }
-        if (h->dDamped) {
+        {
             StageTimer t(h, Stage::EDGE, h->aux);
             DampedArgs d{};
             d.geo = g;
@@ -598,6 +586,19 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
             h->nKernelLaunches += 1;
             h->nGatherLaunches += 1;
         }
+    }
+    if (h->nEdge && nPlanes) {
+        StageTimer t(h, Stage::EDGE, h->compute);
+        Edge2Args e{};
+        e.geo = g;
+        e.items = h->dEdge; e.groupStart = h->dEdgeGroups; e.nGroups = h->nEdgeGroups;
+        e.planesD = h->dPlanesD; e.planeImg = h->dPlaneImg; e.img = h->dImg; e.nPlanes = nPlanes;
+        e.blobTable = h->dBlobTable; e.slices = h->dSlices2; e.col0 = h->dCol02; e.rimTab = h->dRimTab + g.Rp;
+        e.Vb = h->dVb; e.Wb = h->dWb; e.Wb2 = h->dWb2;
+        e.iDeltaD = h->tables.iDeltaSqrt;
+        k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->compute>>>(e);      // one warp per target voxel
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
     }
     return RFB200_OK;
 }
