@@ -125,8 +125,15 @@ def test_phantom_project_cli_argument_errors(tmp_path):
     r = subprocess.run([exe, "-i", str(tmp_path / "nope.vol"), "-o", "p.xmp", "--method", "fourier", "--angles", "0", "0", "0"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "XMIPP_ERROR" in r.stderr
-    r = subprocess.run([exe, "-i", "v.vol", "-o", "p.xmp", "--method", "fourier", "--params", "x.param"], capture_output=True, text=True)
-    assert r.returncode == 2 and "--params" in r.stderr
+    r = subprocess.run([exe, "-i", "v.vol", "-o", "p.xmp", "--method", "fourier", "--params", "x.param", "--angles", "0", "0", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "mutually exclusive" in r.stderr                     # message of project.cpp:65-66
+    # parameter files (project.cpp:220-388): random ranges and noise are refused, a missing file is an error
+    par = tmp_path / "noise.param"
+    par.write_text("# XMIPP_STAR_1 *\n#\ndata_block1\n_dimensions2D '32 32'\n_projRotRange '0 90 4'\n_projTiltRange '0'\n"
+                   "_projPsiRange '0'\n_noisePixelLevel '0.5 0'\n")
+    r = subprocess.run([exe, "-i", "v.vol", "-o", "p.stk", "--method", "fourier", "--params", str(par)], capture_output=True, text=True)
+    assert r.returncode == 1 and "noisePixelLevel" in r.stderr
 
 
 @gpu
@@ -160,3 +167,25 @@ def test_phantom_project_cli_matches_the_restatement(tmp_path, oracle_mod):
     for k in range(5):
         got = _host.read_image(names[k], N, N)
         assert synth.rel_l2(got, pl.project(rot[k], tilt[k], psi[k])) <= 2e-5
+    # --params (the reference's usual way to make a projection set, project.cpp:62-72, 220-388): deterministic ranges,
+    # projection number (i_rot * Ntilt + i_tilt) * Npsi + i_psi
+    par = tmp_path / "proj.param"
+    par.write_text("# XMIPP_STAR_1 *\n#\ndata_block1\n_dimensions2D '%d %d'\n_projRotRange '0 90 3'\n_projTiltRange '20 60 2'\n"
+                   "_projPsiRange '15'\n_noisePixelLevel '0 0'\n" % (N, N))
+    stack2 = str(tmp_path / "grid.stk")
+    r = subprocess.run([exe, "-i", str(tmp_path / "vol.vol"), "-o", stack2, "--method", "fourier", "2", "0.5", "linear",
+                        "--params", str(par)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p, names, _ = _host.read_particles(str(tmp_path / "grid.xmd"))
+    expect = [(ro, ti, 15.0) for ro in (0.0, 45.0, 90.0) for ti in (20.0, 60.0)]
+    assert len(names) == 6
+    for k, (ro, ti, ps) in enumerate(expect):
+        assert abs(p["rot"][k] - ro) < 1e-6 and abs(p["tilt"][k] - ti) < 1e-6 and abs(p["psi"][k] - ps) < 1e-6
+        assert synth.rel_l2(_host.read_image(names[k], N, N), pl.project(ro, ti, ps)) <= 2e-5
+    # ... and an angle file named in the parameter file
+    par.write_text("# XMIPP_STAR_1 *\n#\ndata_block1\n_dimensions2D '%d %d'\n_projAngleFile angles.xmd\n" % (N, N))
+    r = subprocess.run([exe, "-i", str(tmp_path / "vol.vol"), "-o", str(tmp_path / "fromfile.stk"), "--method", "fourier", "2", "0.5",
+                        "linear", "--params", str(par)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p, names, _ = _host.read_particles(str(tmp_path / "fromfile.xmd"))
+    assert len(names) == 5 and synth.rel_l2(_host.read_image(names[4], N, N), pl.project(rot[4], tilt[4], psi[4])) <= 2e-5

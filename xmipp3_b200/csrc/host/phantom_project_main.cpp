@@ -5,8 +5,11 @@
 //   xmipp_phantom_project_b200 -i volume.vol -o stack.stk --angles_md angles.xmd [...]      (extension: one projection per row of
 //                              angleRot / angleTilt / anglePsi; writes the stack and <stack root>.xmd)
 //
-// Only --method fourier is implemented (the reference defaults to real_space ray tracing; asking for it, or for --params /
-// shifted single projections, is refused with a message).  Like the reconstruction program the CUDA library is bound at
+//   xmipp_phantom_project_b200 -i volume.vol -o stack.stk --params proj.param [...]         (project.cpp:62-72, 220-388: metadata
+//                              flavour of the parameter file, angle file or deterministic ranges)
+//
+// Only --method fourier is implemented (the reference defaults to real_space ray tracing; asking for it, for random angle
+// ranges / noise in --params, or for shifted projections, is refused with a message).  Like the reconstruction program the CUDA library is bound at
 // run time; there is no CPU fallback.
 #include <dlfcn.h>
 
@@ -75,6 +78,9 @@ const char* kUsage =
     "  [--angles <rot> <tilt> <psi>]               : Angles for a single projection\n"
     "  [--angles_md <md_file>]                     : one projection per row (angleRot, angleTilt, anglePsi); writes a stack\n"
     "                                                and <output root>.xmd (extension of this implementation)\n"
+    "  [--params <parameters_file>]                : projection parameter file (metadata flavour): _dimensions2D, and\n"
+    "                                                _projAngleFile or deterministic _projRotRange / _projTiltRange /\n"
+    "                                                _projPsiRange; writes a stack and <output root>.xmd\n"
     "  [--device <dev=0>]                          : GPU device\n";
 
 bool isOpt(const std::string& t) { return t.size() > 1 && t[0] == '-' && !(isdigit((unsigned char)t[1]) || t[1] == '.'); }
@@ -115,8 +121,9 @@ int main(int argc, char** argv) {
         if (!has || fnIn.empty()) throw std::invalid_argument(std::string("-i <volume_file> is required\n") + kUsage);
         auto fnOut = values("-o", has);
         if (!has || fnOut.empty()) throw std::invalid_argument(std::string("-o <image_file> is required\n") + kUsage);
-        values("--params", has);
-        if (has) throw std::invalid_argument("--params (projection parameter files) is not implemented; use --angles or --angles_md");
+        auto fnParams = values("--params", has);
+        const bool doParams = has;
+        if (doParams && fnParams.empty()) throw std::invalid_argument("--params needs a parameter file");
         double pad = 2.0, maxFreq = 0.25;
         int degree = 3;
         auto method = values("--method", has);
@@ -137,18 +144,93 @@ int main(int argc, char** argv) {
         const bool doAngles = has;
         auto angMd = values("--angles_md", has);
         const bool doMd = has;
-        if (doAngles == doMd) throw std::invalid_argument("give exactly one of --angles <rot> <tilt> <psi> and --angles_md <md_file>");
+        if ((int)doAngles + (int)doMd + (int)doParams != 1)
+            throw std::invalid_argument(doAngles && doParams ? "--params and --angles are mutually exclusive"        // project.cpp:65-66
+                                                             : "You should provide --params or --angles (or --angles_md)");
         int device = 0;
         auto dv = values("--device", has);
         if (has && !dv.empty()) device = atoi(dv[0].c_str());
 
         std::vector<double> angles;
         MetaData md;
+        int paramXdim = -1, paramYdim = -1;
         if (doAngles) {
             if (ang.size() < 3) throw std::invalid_argument("--angles needs <rot> <tilt> <psi>");
             if (ang.size() > 3 && (atof(ang[3].c_str()) != 0.0 || (ang.size() > 4 && atof(ang[4].c_str()) != 0.0)))
                 throw std::invalid_argument("shifted single projections (--angles ... <x> <y>) are not implemented");
             for (int k = 0; k < 3; ++k) angles.push_back(atof(ang[k].c_str()));
+        } else if (doParams) {
+            // ParametersProjection::read, metadata flavour (project.cpp:220-388): one non-loop block with _dimensions2D,
+            // then either _projAngleFile (a metadata with the angles) or the three deterministic ranges
+            // _projRotRange / _projTiltRange / _projPsiRange '<ang0> [<angF> <samples>]'; projection number
+            // (i_rot * Ntilt + i_tilt) * Npsi + i_psi (generate_angles, project.cpp:560-703).  Random ranges, angular and pixel
+            // noise need the reference's random stream and are refused unless they are zero / absent.
+            MetaData pm;
+            pm.read(fnParams[0]);
+            if (pm.size() == 0) throw std::runtime_error("Prog_Project_Parameters::read: There is a problem opening the file " + fnParams[0]);
+            auto vec = [&](const char* label) {
+                std::vector<double> out;
+                std::string sv;
+                if (pm.getValue(label, 0, sv)) {
+                    char* c = const_cast<char*>(sv.c_str());
+                    for (;;) {
+                        char* end = nullptr;
+                        double x = strtod(c, &end);
+                        if (end == c) break;
+                        out.push_back(x);
+                        c = end;
+                    }
+                }
+                return out;
+            };
+            for (const char* l : {"noisePixelLevel", "noiseCoord", "projRotNoise", "projTiltNoise", "projPsiNoise"}) {
+                auto nv = vec(l);
+                for (double x : nv)
+                    if (x != 0.0) throw std::runtime_error(std::string("--params: _") + l + " with a non-zero value (random noise) is not implemented");
+            }
+            for (const char* l : {"projRotRandomness", "projTiltRandomness", "projPsiRandomness"}) {
+                std::string rs;
+                if (pm.getValue(l, 0, rs) && !rs.empty() && rs != "NULL" && rs != "even")
+                    throw std::runtime_error(std::string("--params: _") + l + " (random angle ranges) is not implemented");
+            }
+            auto dims = vec("dimensions2D");
+            if (dims.size() >= 2) paramXdim = (int)dims[0], paramYdim = (int)dims[1];
+            std::string fnAng;
+            if (pm.getValue("projAngleFile", 0, fnAng) && !fnAng.empty() && fnAng != "NULL") {
+                size_t slash = fnParams[0].rfind('/');
+                FILE* probe = fopen(fnAng.c_str(), "rb");
+                if (probe) fclose(probe);
+                else if (fnAng[0] != '/' && slash != std::string::npos) fnAng = fnParams[0].substr(0, slash + 1) + fnAng;
+                md.read(fnAng);
+                md.removeDisabled();
+                if (md.size() == 0) throw std::runtime_error("Prog_Project_Parameters::read: file " + fnAng + " doesn't exist");
+                for (size_t i = 0; i < md.size(); ++i) {
+                    if (md.getValueOrDefault("shiftX", i, 0) != 0.0 || md.getValueOrDefault("shiftY", i, 0) != 0.0)
+                        throw std::runtime_error("--params: shifted projections (shiftX / shiftY in the angle file) are not implemented");
+                    angles.push_back(md.getValueOrDefault("angleRot", i, 0));
+                    angles.push_back(md.getValueOrDefault("angleTilt", i, 0));
+                    angles.push_back(md.getValueOrDefault("anglePsi", i, 0));
+                }
+            } else {
+                struct Range { double a0 = 0, aF = 0; int n = 1; } rg[3];
+                const char* labels[3] = {"projRotRange", "projTiltRange", "projPsiRange"};
+                for (int k = 0; k < 3; ++k) {
+                    auto rv = vec(labels[k]);
+                    if (rv.empty()) throw std::runtime_error(std::string("--params: neither _projAngleFile nor _") + labels[k] + " given");
+                    rg[k].a0 = rv[0];
+                    if (rv.size() >= 3) { rg[k].aF = rv[1]; rg[k].n = (int)rv[2]; } else { rg[k].aF = rv[0]; rg[k].n = 1; }
+                    if (rg[k].a0 == rg[k].aF) rg[k].n = 1;                                  // project.cpp:274-275
+                    if (rg[k].n < 1) throw std::runtime_error(std::string("--params: bad sample count in _") + labels[k]);
+                }
+                auto at = [](const Range& r, int i) { return r.n > 1 ? r.a0 + (r.aF - r.a0) / (double)(r.n - 1) * i : r.a0; };
+                for (int i = 0; i < rg[0].n; ++i)
+                    for (int j = 0; j < rg[1].n; ++j)
+                        for (int k = 0; k < rg[2].n; ++k) {
+                            angles.push_back(at(rg[0], i));
+                            angles.push_back(at(rg[1], j));
+                            angles.push_back(at(rg[2], k));
+                        }
+            }
         } else {
             if (angMd.empty()) throw std::invalid_argument("--angles_md needs a metadata file");
             md.read(angMd[0]);
@@ -164,6 +246,9 @@ int main(int argc, char** argv) {
         ImageInfo info = readImageInfo(fnIn[0]);
         const int N = info.nx;
         if (info.ny != N || info.nz != N) throw std::runtime_error("the volume must be cubic (" + std::to_string(info.nx) + "x" + std::to_string(info.ny) + "x" + std::to_string(info.nz) + ")");
+        if (paramXdim > 0 && (paramXdim != N || paramYdim != N))
+            throw std::runtime_error("--params: _dimensions2D " + std::to_string(paramXdim) + " " + std::to_string(paramYdim) +
+                                     " differs from the volume size " + std::to_string(N) + " (resizing projections is not implemented)");
         std::vector<float> vol((size_t)N * N * N);
         for (int k = 0; k < N; ++k) {
             char idx[32];

@@ -5,6 +5,7 @@
 // Stream structure per handle: `copy` stream (H2D of raw particles, double buffered) and
 // `compute` stream (K1a -> cuFFT R2C -> K1b' -> K2' x3 classes -> K2e' -> K2r per chunk), linked by
 // events, so the PCIe transfer of chunk c+1 overlaps the kernels of chunk c.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <dlfcn.h>
@@ -168,6 +169,8 @@ struct rfb200_handle_s {
     PlaneS* dPlanesSStage = nullptr;
     int* dImgPlane0 = nullptr;
     int stickGrid = 0;
+    CUtensorMap sliceMap;           // TMA descriptor of dSlices2 (L2 prefetch of slice patches); zeroed when unavailable
+    bool haveSliceMap = false;
     // ---- fused FFT chain (power-of-two padded sizes, integer shifts); cuFFT is the general path
     bool fusedFft = false;
     float2* dTwiddle = nullptr;
@@ -543,24 +546,30 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
     // planes (ready on the compute stream at this point), so that scatter runs beside the gather launches.  (The edge
     // kernel stays on the compute stream: the wrap-around aliases at the Nyquist faces add into voxels the stick gather
     // owns, and the order of those additions must not depend on scheduling.)
+    static const bool noAux = getenv("RFB200_NO_AUX") != nullptr;      // developer switch: everything on the compute stream
+    cudaStream_t side = noAux ? h->compute : h->aux;
     if (nPlanes && h->dDamped) {
-        RF_CUDA(h, cudaEventRecord(h->evSlices, h->compute));
-        RF_CUDA(h, cudaStreamWaitEvent(h->aux, h->evSlices, 0));
+        if (!noAux) {
+            RF_CUDA(h, cudaEventRecord(h->evSlices, h->compute));
+            RF_CUDA(h, cudaStreamWaitEvent(h->aux, h->evSlices, 0));
+        }
         {
-            StageTimer t(h, Stage::EDGE, h->aux);
+            StageTimer t(h, Stage::EDGE, side);
             DampedArgs d{};
             d.geo = g;
             d.mask = h->dDampedMask; d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
             d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
             d.D = h->dD; d.D2 = h->dD2;
             const int nWords = ((g.R + 1 + 31) / 32) * (2 * g.R + 1);
-            k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, h->aux>>>(d);
+            k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, side>>>(d);
             RF_CUDA(h, cudaGetLastError());
             h->nKernelLaunches += 1;
             h->dampedDirty = true;
         }
-        RF_CUDA(h, cudaEventRecord(h->evAux, h->aux));
-        h->auxPending = true;
+        if (!noAux) {
+            RF_CUDA(h, cudaEventRecord(h->evAux, h->aux));
+            h->auxPending = true;
+        }
     }
     if (nPlanes) {
         RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, sizeof(int) * slot->launches.size(), h->compute));
@@ -579,6 +588,7 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
             a.planesSoA = h->dPlanesSoAp + gi * 9 * kLaunchPlanes;
             a.slices = h->dSlices2; a.rimTab = h->dRimTab + g.Rp;
             a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
+            L.sliceMap = h->sliceMap;
             std::memcpy(L.ps, slot->planesS + la.start, sizeof(PlaneS) * la.count);
             std::memcpy(L.pd, slot->planesDp + la.start, sizeof(PlaneD) * la.count);
             rc = launch_sticks(h, L, std::min(h->stickGrid, (h->nUnits[la.cls] + kStickWarps - 1) / kStickWarps));
@@ -1046,6 +1056,26 @@ int do_create(rfb200_handle h) {
             RF_CUDA(h, cudaMallocHost(&s.imgPlane0, sizeof(int) * CH + 16));
         }
         RF_CUDA(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    {
+        // TMA descriptor of the slices: floats of a row (pitch entries x 4), rows, images; box = 16 entries x 16 rows
+        std::memset(&h->sliceMap, 0, sizeof h->sliceMap);
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t dims[3] = {(cuuint64_t)g.pitch * 4, (cuuint64_t)g.side, (cuuint64_t)CH};
+            const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * 16, (cuuint64_t)g.planeStride * 16};
+            const cuuint32_t box[3] = {(cuuint32_t)kPfBoxCols * 4, (cuuint32_t)kPfBoxRows, 1}, es[3] = {1, 1, 1};
+            h->haveSliceMap = ((EncodeFn)fn)(&h->sliceMap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->dSlices2, dims, strides, box, es,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        } else
+            cudaGetLastError();
+#ifdef RF_L2_PREFETCH
+        if (!h->haveSliceMap) return fail(h, RFB200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the slice buffer");
+#endif
     }
     // persistent grid: one CTA per SM
     h->stickGrid = prop.multiProcessorCount;

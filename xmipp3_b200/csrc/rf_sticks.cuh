@@ -20,6 +20,8 @@
 //                           (order independent -> deterministic; only positive terms -> no cancellation)
 //        k_fold_damped      W += damped weights, once before W is consumed
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only: the map is encoded on the host through the driver entry point)
+
 #include "rf_kernels.cuh"
 
 namespace rfb200 {
@@ -358,6 +360,9 @@ struct StickLaunch {             // the whole parameter block of one launch (< 3
     StickArgs a;
     PlaneS ps[kLaunchPlanes];
     PlaneD pd[kLaunchPlanes];
+    // TMA descriptor of the chunk's slices as a 3-D tensor (floats of a row, rows, images), box = 16 entries x 16 rows:
+    // the patch of the next plane is requested into L2 with one UTMAPF per box while the current plane is processed
+    alignas(64) CUtensorMap sliceMap;
 };
 static_assert(sizeof(StickLaunch) <= 32764, "kernel parameter space");
 
@@ -456,6 +461,30 @@ __device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const Stick
         }
     }
     return touched;
+}
+
+// L2 prefetch of the slice patch a plane projects the stick onto: bounding box of the stick's slab crossing around the
+// projection of its centre (cA, cB, cD), in the coordinates of the stored half plane, as TMA box prefetches (16 entries x 16
+// rows each; everything here is warp-uniform, one lane issues).
+constexpr int kPfBoxCols = 16, kPfBoxRows = 16;
+__device__ __forceinline__ void d_prefetch_patch(const StickConsts& c, const PlaneS& pn, const CUtensorMap* map,
+                                                 const float cA, const float cB, const float cD, const float rSlab, const int lane) {
+    const float hc = cA * pn.na + cB * pn.nb + cD * pn.nd;            // height of the stick centre above the plane
+    const float dc = cD - hc * pn.invNd;                              // depth at which the central column crosses it
+    float al = cA * pn.e1a + cB * pn.e1b + dc * pn.e1d, be = cA * pn.e2a + cB * pn.e2b + dc * pn.e2d;
+    // half extents: the 4 x 4 footprint, the shift of the crossing depth across the footprint, the slab thickness, the blob
+    const float slope = 1.5f * (fabsf(pn.na) + fabsf(pn.nb)) * fabsf(pn.invNd) + rSlab * fabsf(pn.invNd);
+    const float ea = 1.5f * (fabsf(pn.e1a) + fabsf(pn.e1b)) + slope * fabsf(pn.e1d) + c.rho + 1.0f;
+    const float eb = 1.5f * (fabsf(pn.e2a) + fabsf(pn.e2b)) + slope * fabsf(pn.e2d) + c.rho + 1.0f;
+    if (al < 0.f) { al = -al; be = -be; }                             // the mirrored half is read at (-alpha, -beta)
+    const int j0 = max(__float2int_rd(al - ea), -c.colOff), j1 = min(__float2int_ru(al + ea), c.Rp);
+    const int i0 = max(__float2int_rd(be - eb), -c.Rp), i1 = min(__float2int_ru(be + eb), c.Rp);
+    if (lane == 0) {
+        for (int y = i0 + c.Rp; y <= i1 + c.Rp; y += kPfBoxRows)
+            for (int x = j0 + c.colOff; x <= j1 + c.colOff + 1; x += kPfBoxCols)
+                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(4 * x), "r"(y), "r"(pn.img)
+                             : "memory");
+    }
 }
 
 #ifdef RF_STICK_MAXREG
@@ -588,6 +617,12 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
             while (m) {
                 const int k = kb + __ffs(m) - 1;
                 m &= m - 1;
+#ifdef RF_L2_PREFETCH
+                // The patch of the NEXT plane that crosses this stick is requested into L2 now (one bulk-prefetch
+                // instruction, lane <-> slice row): first touches of slice data otherwise cost a DRAM round trip in the middle
+                // of a step, and a step waits for the slowest of its ~40 cache lines.
+                if (m) d_prefetch_patch(c, L.ps[kb + __ffs(m) - 1], &L.sliceMap, cA, cB, cD, rSlab, lane);
+#endif
                 // ---- set up task k
                 const PlaneS& pl = L.ps[k];
                 const PlaneD& pd = L.pd[k];
