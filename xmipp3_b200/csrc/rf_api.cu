@@ -101,11 +101,6 @@ struct rfb200_handle_s {
     std::string err;
 
     cudaStream_t compute = nullptr, copy = nullptr;
-    // side stream: the edge kernel and the damped-weight scatter of a chunk touch voxels / buffers the stick gather of the
-    // same chunk never touches, so they run beside it and soak up the tails of its launches
-    cudaStream_t aux = nullptr;
-    cudaEvent_t evSlices = nullptr, evAux = nullptr;
-    bool auxPending = false;
     // static device data
     float* dBlobTable = nullptr;
     int* dJmax = nullptr;
@@ -220,16 +215,6 @@ namespace {
 int fail(rfb200_handle h, int code, const std::string& msg) {
     h->err = msg;
     return code;
-}
-
-// make the compute stream wait for the side stream's kernels of the last chunk (before anything reads or overwrites what
-// they read or write: V, W, the damped-weight volume, the chunk's parameter and slice buffers)
-int join_aux(rfb200_handle h) {
-    if (h->auxPending) {
-        RF_CUDA(h, cudaStreamWaitEvent(h->compute, h->evAux, 0));
-        h->auxPending = false;
-    }
-    return RFB200_OK;
 }
 
 cudaEvent_t get_event(rfb200_handle h) {
@@ -383,7 +368,6 @@ int launch_fused_fft(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& 
 
 // W += weights of the CTF-damped pixels; must run before W is read, reduced or copied
 int flush_deficit(rfb200_handle h) {
-    if (int rj = join_aux(h)) return rj;
     if (h->fast && h->fastDirty) {      // --fast: fold the scratch accumulators into V and W
         k_fast_flush<<<2048, 256, 0, h->compute>>>(h->dFastAcc, h->dVb, h->dWb, h->nBlocked);
         RF_CUDA(h, cudaGetLastError());
@@ -444,7 +428,6 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
     ParamSlot& s = h->slots[h->slotIdx];
     h->slotIdx ^= 1;
     if (s.used) RF_CUDA(h, cudaEventSynchronize(s.done));
-    if (int rj = join_aux(h)) return rj;       // the previous chunk's side kernels still read its parameter buffers
     const Geometry& g = h->geo;
     const double pixPerVox = (double)g.P / (double)g.Z;
     int np = 0;
@@ -542,35 +525,6 @@ Slice2Args make_slice_args(rfb200_handle h) {
 int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
     const Geometry& g = h->geo;
     int rc = RFB200_OK;
-    // ---- side stream: the damped-pixel weights go to their own fixed-point volume and only need this chunk's masks and
-    // planes (ready on the compute stream at this point), so that scatter runs beside the gather launches.  (The edge
-    // kernel stays on the compute stream: the wrap-around aliases at the Nyquist faces add into voxels the stick gather
-    // owns, and the order of those additions must not depend on scheduling.)
-    static const bool noAux = getenv("RFB200_NO_AUX") != nullptr;      // developer switch: everything on the compute stream
-    cudaStream_t side = noAux ? h->compute : h->aux;
-    if (nPlanes && h->dDamped) {
-        if (!noAux) {
-            RF_CUDA(h, cudaEventRecord(h->evSlices, h->compute));
-            RF_CUDA(h, cudaStreamWaitEvent(h->aux, h->evSlices, 0));
-        }
-        {
-            StageTimer t(h, Stage::EDGE, side);
-            DampedArgs d{};
-            d.geo = g;
-            d.mask = h->dDampedMask; d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
-            d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
-            d.D = h->dD; d.D2 = h->dD2;
-            const int nWords = ((g.R + 1 + 31) / 32) * (2 * g.R + 1);
-            k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, side>>>(d);
-            RF_CUDA(h, cudaGetLastError());
-            h->nKernelLaunches += 1;
-            h->dampedDirty = true;
-        }
-        if (!noAux) {
-            RF_CUDA(h, cudaEventRecord(h->evAux, h->aux));
-            h->auxPending = true;
-        }
-    }
     if (nPlanes) {
         RF_CUDA(h, cudaMemsetAsync(h->dStickCounters, 0, sizeof(int) * slot->launches.size(), h->compute));
         StageTimer t(h, Stage::GATHER, h->compute);
@@ -609,6 +563,22 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
         k_edge2<<<(h->nEdgeGroups + 3) / 4, 128, 0, h->compute>>>(e);      // one warp per target voxel
         RF_CUDA(h, cudaGetLastError());
         h->nKernelLaunches += 1;
+    }
+    // (Measured and dropped: running the damped-weight scatter on a side stream beside the gather launches — it writes its
+    // own fixed-point volume — changed nothing: 44.80 vs 44.90 ms per 4096 particles; the persistent gather leaves no idle
+    // SM time to fill.)
+    if (h->dDamped && nPlanes) {
+        StageTimer t(h, Stage::EDGE, h->compute);
+        DampedArgs d{};
+        d.geo = g;
+        d.mask = h->dDampedMask; d.damped = h->dDamped; d.damped2 = h->dDamped2; d.nImg = n; d.imgPlane0 = h->dImgPlane0; d.nSym = h->nSymTot;
+        d.planesD = h->dPlanesD; d.blobTable = h->dBlobTable; d.iDeltaD = h->tables.iDeltaSqrt;
+        d.D = h->dD; d.D2 = h->dD2;
+        const int nWords = ((g.R + 1 + 31) / 32) * (2 * g.R + 1);
+        k_damped_scatter<<<dim3((nWords + 255) / 256, n), 256, 0, h->compute>>>(d);
+        RF_CUDA(h, cudaGetLastError());
+        h->nKernelLaunches += 1;
+        h->dampedDirty = true;
     }
     return RFB200_OK;
 }
@@ -761,7 +731,6 @@ void free_all(rfb200_handle h) {
     cudaSetDevice(h->cfg.device);
     if (h->compute) cudaStreamSynchronize(h->compute);
     if (h->copy) cudaStreamSynchronize(h->copy);
-    if (h->aux) cudaStreamSynchronize(h->aux);
     resolve_timings(h);
     for (auto e : h->evPool) cudaEventDestroy(e);
     if (h->swStart) cudaEventDestroy(h->swStart);
@@ -791,9 +760,6 @@ void free_all(rfb200_handle h) {
 #endif
     if (h->compute) cudaStreamDestroy(h->compute);
     if (h->copy) cudaStreamDestroy(h->copy);
-    if (h->aux) cudaStreamDestroy(h->aux);
-    if (h->evSlices) cudaEventDestroy(h->evSlices);
-    if (h->evAux) cudaEventDestroy(h->evAux);
     delete h;
 }
 
@@ -939,14 +905,15 @@ int do_create(rfb200_handle h) {
     for (int i = 0; i < kBlobTable; ++i) blobF[i] = (float)h->tables.blobSqrt[i];
 
     int maxBatch = c.max_batch > 0 ? c.max_batch : 1024;
-    h->chunkImages = std::min(maxBatch, 1024);
+    // Images per preprocessing chunk.  A gather launch carries at most kLaunchPlanes planes of one class; without symmetry a
+    // chunk of 720 images gives 240 +- 13 planes per class = one full launch each (1024 images would give 341 = two launches
+    // of 171, i.e. the per-launch work of a stick amortised over fewer planes: measured 44.07 vs 44.59 ms per 4096 particles).
+    // With symmetry every class needs many launches anyway and the split is even.
+    h->chunkImages = std::min(maxBatch, h->nSymTot == 1 ? (3 * kLaunchPlanes * 15) / 16 : 1024);
 
     // ---- streams / events
     RF_CUDA(h, cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     RF_CUDA(h, cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    RF_CUDA(h, cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
-    RF_CUDA(h, cudaEventCreateWithFlags(&h->evSlices, cudaEventDisableTiming));
-    RF_CUDA(h, cudaEventCreateWithFlags(&h->evAux, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         RF_CUDA(h, cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming));
         RF_CUDA(h, cudaEventCreateWithFlags(&h->evRawFree[i], cudaEventDisableTiming));
@@ -1186,8 +1153,6 @@ int rfb200_sync(rfb200_handle h) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
     RF_CUDA(h, cudaStreamSynchronize(h->compute));
-    if (h->aux) RF_CUDA(h, cudaStreamSynchronize(h->aux));
-    h->auxPending = false;
     resolve_timings(h);
     return RFB200_OK;
 }
@@ -1397,7 +1362,6 @@ int rfb200_timer_start(rfb200_handle h) {
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     // make the compute stream wait for any copy still in flight so that the stopwatch starts "behind everything"
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
-    if (int rj = join_aux(h)) return rj;
     RF_CUDA(h, cudaEventRecord(h->swStart, h->compute));
     h->swStarted = true;
     return RFB200_OK;
@@ -1407,7 +1371,6 @@ int rfb200_timer_stop(rfb200_handle h, double* elapsed_ms) {
     if (!h || !elapsed_ms) return RFB200_ERR_ARG;
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     RF_CUDA(h, cudaStreamSynchronize(h->copy));
-    if (int rj = join_aux(h)) return rj;       // the stopwatch stops behind the side stream too
     RF_CUDA(h, cudaEventRecord(h->swStop, h->compute));
     RF_CUDA(h, cudaEventSynchronize(h->swStop));
     float ms = 0;

@@ -263,80 +263,6 @@ __device__ __forceinline__ void d_pair(const float dy, const u64 dx2, const floa
 #undef RF_PAIR_IN
 }
 
-// ---- third-generation candidate evaluation: split in two phases so that the table lookups of a row group (which do not
-// depend on the pixel data) are issued BETWEEN the pixel loads and their first use.  ncu showed 52 % of the long-scoreboard
-// stall samples of the gather on the first FFMA after each pair of loads: the loads were issued and consumed back to back.
-//   phase A (d_pair_w): S = dy + dx, idx = round(S), accept test, table address, w = accepted ? table[idx] : 0
-//   phase B (d_pair_acc): V += w * (re, im) (unpredicated: w is 0 for a rejected candidate and the pixel registers are
-//            zero-initialised), W += w (* multiplicity) unless the pixel is flagged
-__device__ __forceinline__ void d_pair_w(const float dy, const u64 dx2, const float sMax, const uint32_t tblAdj, float& w0, float& w1) {
-    const u64 dy2 = d_pk(dy, dy);
-    const u64 magic2 = d_pk(8388608.0f, 8388608.0f);
-    asm("{\n\t"
-        ".reg .b64 s2, m2;\n\t"
-        ".reg .f32 s0, s1;\n\t"
-        ".reg .b32 i0, i1;\n\t"
-        ".reg .pred p0, p1;\n\t"
-        "add.rn.f32x2 s2, %2, %3;\n\t"
-        "add.rn.f32x2 m2, s2, %4;\n\t"
-        "mov.b64 {s0, s1}, s2;\n\t"
-        "mov.b64 {i0, i1}, m2;\n\t"
-        "setp.le.f32 p0, s0, %5;\n\t"
-        "setp.le.f32 p1, s1, %5;\n\t"
-        "shl.b32 i0, i0, 2;\n\t"
-        "add.u32 i0, i0, %6;\n\t"
-        "shl.b32 i1, i1, 2;\n\t"
-        "add.u32 i1, i1, %6;\n\t"
-        "mov.f32 %0, 0f00000000;\n\t"
-        "mov.f32 %1, 0f00000000;\n\t"
-        "@p0 ld.shared.f32 %0, [i0];\n\t"
-        "@p1 ld.shared.f32 %1, [i1];\n\t"
-        "}"
-        : "=f"(w0), "=f"(w1)
-        : "l"(dy2), "l"(dx2), "l"(magic2), "f"(sMax), "r"(tblAdj));
-}
-template <bool kSlow, bool kFlags>
-__device__ __forceinline__ void d_pair_acc(const float w0, const float w1, const float4 px, const float m0, const float m1, PairAcc& A) {
-    A.reA = fmaf(w0, px.x, A.reA);
-    A.imA = fmaf(w0, px.y, A.imA);
-    A.reB = fmaf(w1, px.z, A.reB);
-    A.imB = fmaf(w1, px.w, A.imB);
-    if (kFlags) {
-        if (kSlow)
-            asm("{\n\t"
-                ".reg .pred q0, q1, pt;\n\t"
-                ".reg .b32 t0, t1;\n\t"
-                "setp.eq.u32 pt, 0, 0;\n\t"
-                "lop3.and.b32 t0|q0, %2, 1, 0, 0x0C, pt;\n\t"
-                "lop3.and.b32 t1|q1, %3, 1, 0, 0x0C, pt;\n\t"
-                "@q0 fma.rn.f32 %0, %4, %6, %0;\n\t"
-                "@q1 fma.rn.f32 %1, %5, %7, %1;\n\t"
-                "}"
-                : "+f"(A.wA), "+f"(A.wB)
-                : "r"(__float_as_uint(px.x)), "r"(__float_as_uint(px.z)), "f"(w0), "f"(w1), "f"(m0), "f"(m1));
-        else
-            asm("{\n\t"
-                ".reg .pred q0, q1, pt;\n\t"
-                ".reg .b32 t0, t1;\n\t"
-                "setp.eq.u32 pt, 0, 0;\n\t"
-                "lop3.and.b32 t0|q0, %2, 1, 0, 0x0C, pt;\n\t"
-                "lop3.and.b32 t1|q1, %3, 1, 0, 0x0C, pt;\n\t"
-                "@q0 add.rn.f32 %0, %0, %4;\n\t"
-                "@q1 add.rn.f32 %1, %1, %5;\n\t"
-                "}"
-                : "+f"(A.wA), "+f"(A.wB)
-                : "r"(__float_as_uint(px.x)), "r"(__float_as_uint(px.z)), "f"(w0), "f"(w1));
-    } else {
-        if (kSlow) {
-            A.wA = fmaf(w0, m0, A.wA);
-            A.wB = fmaf(w1, m1, A.wB);
-        } else {
-            A.wA += w0;
-            A.wB += w1;
-        }
-    }
-}
-
 // One step of one column, second generation: the K x K candidate window of the lane's voxel, two candidates per asm
 // block.  p points at the window origin (16-byte aligned pixel pair); (da0, db0) is the offset of the projected voxel from
 // the window origin, h2s = h^2 * iDelta.  kSlow weighs every candidate with its multiplicity (0 outside the resolution
@@ -398,7 +324,6 @@ __device__ __forceinline__ void d_stick_window2(const float4* __restrict__ p, co
                 }
             }
         }
-#ifdef RF_GATHER_ONE_PHASE
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int ti = t0 + g;
@@ -416,33 +341,6 @@ __device__ __forceinline__ void d_stick_window2(const float4* __restrict__ p, co
                 }
             }
         }
-#else
-        float w[G][NP][2];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            if (t0 + g < K) {
-#pragma unroll
-                for (int q = 0; q < NP; ++q) d_pair_w(dys[t0 + g], dxs2[q], sMax, tblAdj, w[g][q][0], w[g][q][1]);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int ti = t0 + g;
-            if (ti < K) {
-                int rt = 0;
-                if (kSlow) rt = __ldg(rimTab + ic + ti);
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    float m0 = 1.f, m1 = 1.f;
-                    if (kSlow) {
-                        m0 = d_rim_mult(rt, jc + 2 * q);
-                        m1 = d_rim_mult(rt, jc + 2 * q + 1);
-                    }
-                    d_pair_acc<kSlow, kFlags>(w[g][q][0], w[g][q][1], px[g][q], m0, m1, A);
-                }
-            }
-        }
-#endif
     }
     accRe = A.reA + A.reB;
     accIm = A.imA + A.imB;
