@@ -510,6 +510,11 @@ def main():
                 "traffic_source": prof.get("source", "none: no ncu summary in profiles/gather_ncu.json") +
                                   " (one ncu --set full capture of this kernel, committed; NOT measured in this run)",
                 "ms_per_launch": g_ms, "particles_per_launch": imgs_per_launch,
+                "us_per_particle": 1e3 * g_ms / imgs_per_launch,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "frac_note": "algorithmic bytes per launch = particles x Npix x 8 B (slices) + 24 B x Nsphere (every launch reads and "
+                             "writes the touched volume once, SURVEY 8d); launches with more planes amortise the second term, so "
+                             "`achieved` falls when the kernel gets faster per particle by batching more planes per launch",
                 "bound_actual": "instruction issue + L1/shared-memory data pipe (ncu: l1_data_pipe); the contract's `bound` only admits hbm|tensor",
                 "note": "the gather is bound by the L1/shared-memory data pipe (per-pair pixel and blob-table fetches), "
                         "not by HBM or FP32: see l1_data_pipe (ncu) and fp32"}

@@ -40,11 +40,14 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def full_metrics(rep):
     txt = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
     rows = list(csv.reader(txt.splitlines()))
-    h, u, v = rows[0], rows[1], rows[2]
-    out = ["kernel: " + v[h.index("Kernel Name")]]
-    for i, n in enumerate(h):
-        if n in KEYS or ("issue_stalled" in n and n.endswith("per_issue_active.ratio")):
-            out.append("%-90s %-14s %s" % (n, u[i], v[i]))
+    h, u = rows[0], rows[1]
+    out = []
+    for v in rows[2:]:            # one block per captured launch
+        out.append("-" * 100)
+        out.append("kernel: " + v[h.index("Kernel Name")])
+        for i, n in enumerate(h):
+            if n in KEYS or ("issue_stalled" in n and n.endswith("per_issue_active.ratio")):
+                out.append("  %-88s %-14s %s" % (n, u[i], v[i]))
     return "\n".join(out)
 
 

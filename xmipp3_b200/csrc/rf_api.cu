@@ -542,7 +542,9 @@ int insert_planes_sticks(rfb200_handle h, ParamSlot* slot, int n, int nPlanes) {
             a.planesSoA = h->dPlanesSoAp + gi * 9 * kLaunchPlanes;
             a.slices = h->dSlices2; a.rimTab = h->dRimTab + g.Rp;
             a.Vb = h->dVb; a.Wb = h->dWb; a.Wb2 = h->dWb2;
+#ifdef RF_L2_PREFETCH
             L.sliceMap = h->sliceMap;
+#endif
             std::memcpy(L.ps, slot->planesS + la.start, sizeof(PlaneS) * la.count);
             std::memcpy(L.pd, slot->planesDp + la.start, sizeof(PlaneD) * la.count);
             rc = launch_sticks(h, L, std::min(h->stickGrid, (h->nUnits[la.cls] + kStickWarps - 1) / kStickWarps));
@@ -906,10 +908,11 @@ int do_create(rfb200_handle h) {
 
     int maxBatch = c.max_batch > 0 ? c.max_batch : 1024;
     // Images per preprocessing chunk.  A gather launch carries at most kLaunchPlanes planes of one class; without symmetry a
-    // chunk of 720 images gives 240 +- 13 planes per class = one full launch each (1024 images would give 341 = two launches
-    // of 171, i.e. the per-launch work of a stick amortised over fewer planes: measured 44.07 vs 44.59 ms per 4096 particles).
-    // With symmetry every class needs many launches anyway and the split is even.
-    h->chunkImages = std::min(maxBatch, h->nSymTot == 1 ? (3 * kLaunchPlanes * 15) / 16 : 1024);
+    // chunk of 720 images gives 240 +- 13 planes per class = one launch each, 3 % of the classes overflowing into a second
+    // one (1024 images would give 341 = two launches of 171, i.e. the per-launch work of a stick amortised over fewer planes:
+    // measured 44.07 vs 44.59 ms per 4096 particles).  With symmetry every class needs many launches anyway and the split
+    // is even.
+    h->chunkImages = std::min(maxBatch, h->nSymTot == 1 ? (3 * kLaunchPlanes * 10) / 11 : 1024);
 
     // ---- streams / events
     RF_CUDA(h, cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));

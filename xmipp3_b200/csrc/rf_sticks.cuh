@@ -360,9 +360,11 @@ struct StickLaunch {             // the whole parameter block of one launch (< 3
     StickArgs a;
     PlaneS ps[kLaunchPlanes];
     PlaneD pd[kLaunchPlanes];
-    // TMA descriptor of the chunk's slices as a 3-D tensor (floats of a row, rows, images), box = 16 entries x 16 rows:
-    // the patch of the next plane is requested into L2 with one UTMAPF per box while the current plane is processed
+#ifdef RF_L2_PREFETCH
+    // (measured variant) TMA descriptor of the chunk's slices as a 3-D tensor (floats of a row, rows, images), box = 16
+    // entries x 16 rows: the patch of the next plane is requested into L2 with one UTMAPF per box
     alignas(64) CUtensorMap sliceMap;
+#endif
 };
 static_assert(sizeof(StickLaunch) <= 32764, "kernel parameter space");
 
@@ -472,6 +474,15 @@ __device__ __forceinline__ void d_prefetch_patch(const StickConsts& c, const Pla
     const float hc = cA * pn.na + cB * pn.nb + cD * pn.nd;            // height of the stick centre above the plane
     const float dc = cD - hc * pn.invNd;                              // depth at which the central column crosses it
     float al = cA * pn.e1a + cB * pn.e1b + dc * pn.e1d, be = cA * pn.e2a + cB * pn.e2b + dc * pn.e2d;
+#if RF_L2_PREFETCH == 2
+    // cheap form: ONE box centred on the crossing point (covers the patch of all but the steepest planes)
+    if (al < 0.f) { al = -al; be = -be; }
+    if (lane == 0) {
+        const int x = max(__float2int_rn(al) - kPfBoxCols / 2 + c.colOff, 0), y = __float2int_rn(be) - kPfBoxRows / 2 + c.Rp;
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(4 * x), "r"(y), "r"(pn.img) : "memory");
+    }
+    return;
+#endif
     // half extents: the 4 x 4 footprint, the shift of the crossing depth across the footprint, the slab thickness, the blob
     const float slope = 1.5f * (fabsf(pn.na) + fabsf(pn.nb)) * fabsf(pn.invNd) + rSlab * fabsf(pn.invNd);
     const float ea = 1.5f * (fabsf(pn.e1a) + fabsf(pn.e1b)) + slope * fabsf(pn.e1d) + c.rho + 1.0f;

@@ -9,8 +9,8 @@ namespace rfb200 {
 // accumulators are contiguous (one coalesced warp access per brick).
 constexpr int kTileX = 16, kTileY = 16, kTileZ = 8;
 constexpr int kTileVox = kTileX * kTileY * kTileZ;   // 2048
-constexpr int kLaunchPlanes = 256;           // (image, symmetry) planes of ONE class per gather launch: their PlaneS + PlaneD
-                                             // tables travel as kernel parameters (30 KB of the 32,764-byte parameter space,
+constexpr int kLaunchPlanes = 264;           // (image, symmetry) planes of ONE class per gather launch: their PlaneS + PlaneD
+                                             // tables travel as kernel parameters (31 KB of the 32,764-byte parameter space,
                                              // i.e. constant bank 0), so every launch carries its own tables: handles and
                                              // streams on one device are independent
 constexpr int kBlobTable = 10000;            // BLOB_TABLE_SIZE_SQRT (reconstruct_fourier.h:41-44)
