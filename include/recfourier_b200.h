@@ -148,6 +148,12 @@ int rfb200_export_accumulators(rfb200_handle h, float* V, float* W);
  * FFT, crop and gridding correction.  out: N*N*N float32 in HOST memory, [z][y][x].
  * The accumulators are left untouched, so more batches may follow. */
 int rfb200_finalize(rfb200_handle h, float* out);
+/* Optional: pay the one-off set-up costs of the END of a run while particles are still being inserted.  Creates the 3-D
+ * inverse-FFT plan and the finalisation buffers and, when a communicator is attached, runs a 4-byte collective on a
+ * private stream so that NCCL's connection set-up (about a second) does not land on the first rfb200_reduce_nccl.  The
+ * only entry point that may run on a second thread while another thread inserts into the same handle; it must have
+ * returned before rfb200_reduce_nccl / rfb200_finalize are called, and every rank must call it (or none). */
+int rfb200_warmup(rfb200_handle h);
 
 /* Half-set support for --prepare_fsc (RF.cpp:991-1053): push saves the current accumulators aside and zeroes
  * them (so the next particles form an independent half set); merge adds the saved half back. */

@@ -302,3 +302,25 @@ def test_two_handles_on_one_device_run_concurrently(oracle_mod):
     b.close()
     assert np.array_equal(Va, ref[0][0]) and np.array_equal(Wa, ref[0][1])
     assert np.array_equal(Vb, ref[1][0]) and np.array_equal(Wb, ref[1][1])
+
+
+def test_warmup_on_a_second_thread_while_inserting():
+    """rfb200_warmup (finalisation plan + buffers, NCCL connection set-up) is the one entry point that may run beside an
+    insert on the same handle (the CLI hides ~1.5 s of one-off set-up behind the particle loop that way)."""
+    import threading
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    N, n = 64, 400
+    d = synth.make_dataset(n, N, seed=81, ctf=True)
+    p = make_particles(n, **_cols(d, True))
+    a = Reconstructor(N, use_ctf=True, sampling=d["sampling"], max_batch=40)
+    a.insert(d["images"], p)
+    ref = a.finalize()
+    a.close()
+    b = Reconstructor(N, use_ctf=True, sampling=d["sampling"], max_batch=40)
+    t = threading.Thread(target=b.warmup)
+    t.start()
+    b.insert(d["images"], p)
+    t.join()
+    vol = b.finalize()
+    b.close()
+    assert np.array_equal(vol, ref)

@@ -2,7 +2,8 @@
 particle counts the single-thread oracle could not finish in a test run.  The oracle runs in its race-free parallel mode
 (scheme="slabs": every slab of the volume owned by one task, bit-identical to threads = 1, tests/test_oracle_kat.py).
 
-  * config 3 geometry: 2000 x 256^2 particles with CTF, padding 2, C1
+  * config 2 in full:  10,000 x 128^2 particles with CTF and integer shifts, C1
+  * config 3 geometry: 2000 x 256^2 particles with CTF, padding 2, C1 (100,000: tools/parity_at_scale.py, profiles/)
   * config 4:          200 x 256^2 particles, D7 (14 insertions per image = 2800 planes)
   * config 5 geometry: 200 x 512^2 particles, padding 2 (Z = 1024, FFT<1024>, 6.5 GB of accumulators)
   * FP32 accumulation: 20,000 x 256^2 particles accumulated in one go (FP32) against the FP64 sum of the per-1000
@@ -74,6 +75,22 @@ def _gate(res):
         assert res["acc_V"] <= ACC_TOL and res["acc_W"] <= ACC_TOL, res
     assert res["rel_l2"] <= REL_L2_GATE, res
     assert res["min_fsc"] >= FSC_GATE, res
+
+
+def test_config2_in_full_10k_particles_box128_ctf_shifts(oracle_mod):
+    """BASELINE config 2 as stated: 10,000 x 128^2 particles with CTF and random integer shifts, C1."""
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    N, n = 128, 10000
+    d = synth.make_dataset(n, N, seed=54, ctf=True, shifts=True)
+    cols = _cols(d, True)
+    r = Reconstructor(N, use_ctf=True, sampling=d["sampling"])
+    r.insert(d["images"], make_particles(n, **cols))
+    v = r.finalize()
+    r.close()
+    o = oracle_mod.Oracle(N, use_ctf=True, sampling=d["sampling"])
+    o.insert(d["images"], oracle_mod.make_particles(n, **cols), threads=CORES, scheme="slabs")
+    vo = o.finalize()
+    _gate({"rel_l2": float(synth.rel_l2(v, vo)), "min_fsc": float(np.nanmin(synth.fsc(v, vo)[1:])), "particles": n})
 
 
 def test_config3_2000_particles_box256_ctf(oracle_mod):

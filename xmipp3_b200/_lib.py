@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
-    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count", "rfb200_measure_fp32_peak", "rfb200_debug_fast_fourier",
+    "rfb200_host_alloc", "rfb200_host_free", "rfb200_device_count", "rfb200_measure_fp32_peak", "rfb200_warmup", "rfb200_debug_fast_fourier",
     "rfb200_projector_create", "rfb200_projector_project", "rfb200_projector_project_device", "rfb200_projector_last_error",
     "rfb200_projector_destroy",
 ]
@@ -108,6 +108,7 @@ def load(build=True):
     L.rfb200_accumulator_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.rfb200_export_accumulators.argtypes = [H, C.c_void_p, C.c_void_p]
     L.rfb200_finalize.argtypes = [H, C.c_void_p]
+    L.rfb200_warmup.argtypes = [H]
     L.rfb200_get_timings.argtypes = [H, C.POINTER(Timings)]
     L.rfb200_halfset_push.argtypes = [H]
     L.rfb200_halfset_merge.argtypes = [H]
@@ -272,6 +273,11 @@ class Reconstructor:
         out = np.empty((self.N,) * 3, dtype=np.float32)
         self._check(self._L.rfb200_finalize(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def warmup(self):
+        """Create the finalisation plan / buffers (and run NCCL's connection set-up) ahead of time; may run on a second
+        thread while another one inserts."""
+        self._check(self._L.rfb200_warmup(self._h))
 
     def finalize_into(self, host_ptr):
         """finalize() into caller-owned host memory of N^3 float32 (e.g. page-locked: the 4 N^3-byte read-back then runs

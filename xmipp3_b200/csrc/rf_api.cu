@@ -334,8 +334,8 @@ int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs
     const int threads = kFftSeqs * P / 8;
     const size_t smem = sizeof(float2) * (P + kFftSeqs * kFftBuf<P>);
     constexpr int NC = kColsPerCta<P>;
-    const int threadsC = (NC + 1) * P / 8;
-    const size_t smemC = sizeof(float2) * (P + (NC + 1) * kFftBuf<P> + (P + 2));      // twiddles, NC + 1 sequences, halo values
+    const int threadsC = (NC + kK1cHalo) * P / 8;
+    const size_t smemC = sizeof(float2) * (P + (NC + kK1cHalo) * kFftBuf<P> + (P + 2));      // twiddles, the sequences, halo values
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1271,12 +1271,9 @@ int rfb200_export_accumulators(rfb200_handle h, float* V, float* W) {
     return RFB200_OK;
 }
 
-int rfb200_finalize(rfb200_handle h, float* out) {
-    if (!h || !out) return RFB200_ERR_ARG;
-    RF_CUDA(h, cudaSetDevice(h->cfg.device));
-    if (h->fast) return finalize_fast(h, out);
+// plan and buffers of the finalisation (created on first use, or ahead of time by rfb200_warmup)
+static int prepare_finalize(rfb200_handle h) {
     const Geometry& g = h->geo;
-    const rfb200_config& c = h->cfg;
     size_t nHalf = (size_t)g.Z * g.Z * g.X, nVol = (size_t)g.Z * g.Z * g.Z, nOut = (size_t)g.N * g.N * g.N;
     if (!h->havePlan3d) {
         RF_CUFFT(h, cufftPlan3d(&h->plan3d, g.Z, g.Z, g.Z, CUFFT_C2R));
@@ -1286,6 +1283,41 @@ int rfb200_finalize(rfb200_handle h, float* out) {
     if (!h->dNorm) RF_CUDA(h, cudaMalloc(&h->dNorm, sizeof(float2) * nHalf));
     if (!h->dVol) RF_CUDA(h, cudaMalloc(&h->dVol, sizeof(float) * nVol));
     if (!h->dOut) RF_CUDA(h, cudaMalloc(&h->dOut, sizeof(float) * nOut));
+    return RFB200_OK;
+}
+
+int rfb200_warmup(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!h->fast)
+        if (int rc = prepare_finalize(h)) return rc;
+#if RFB200_HAVE_NCCL_H
+    if (h->comm && g_nccl.ok) {
+        // a 4-byte reduce on a private stream: every rank calls this once, before its first real reduce
+        cudaStream_t s = nullptr;
+        float* d = nullptr;
+        RF_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        cudaError_t e = cudaMalloc(&d, 16);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d, 0, 16, s);
+        ncclResult_t r = e == cudaSuccess ? g_nccl.Reduce(d, d, 1, ncclFloat, ncclSum, 0, h->comm, s) : ncclSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (d) cudaFree(d);
+        cudaStreamDestroy(s);
+        if (e != cudaSuccess) return fail(h, RFB200_ERR_CUDA, std::string("warm-up failed: ") + cudaGetErrorString(e));
+        if (r != ncclSuccess) return fail(h, RFB200_ERR_NCCL, "warm-up ncclReduce failed");
+    }
+#endif
+    return RFB200_OK;
+}
+
+int rfb200_finalize(rfb200_handle h, float* out) {
+    if (!h || !out) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (h->fast) return finalize_fast(h, out);
+    const Geometry& g = h->geo;
+    const rfb200_config& c = h->cfg;
+    size_t nHalf = (size_t)g.Z * g.Z * g.X, nOut = (size_t)g.N * g.N * g.N;
+    if (int rcp = prepare_finalize(h)) return rcp;
     if (int rcf = flush_deficit(h)) return rcf;
     {
         StageTimer t(h, Stage::FINALIZE, h->compute);

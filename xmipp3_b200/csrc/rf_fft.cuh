@@ -215,9 +215,14 @@ template <int P> constexpr int kColsPerCta = (P >= 1024) ? 4 : 8;
 // side, E(-r, -j) = (conj p(r,j), conj p(r,j-1))), so a row piece of a CTA is NC consecutive entries = full 32-byte sectors
 // and one store request.  (Round 1 stored the full plane: every pixel four times, 4.3 GB of DRAM writes per 1024
 // particles at box 256; the half-plane format halves that.)
+#ifdef RF_K1C_NO_HALO
+constexpr int kK1cHalo = 0;     // variant: no halo column; the two entry halves at a CTA's column boundary are 8-byte stores
+#else
+constexpr int kK1cHalo = 1;
+#endif
 template <int P>
-__global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
-    constexpr int NC = kColsPerCta<P>, NS = NC + 1;
+__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
+    constexpr int NC = kColsPerCta<P>, NS = NC + kK1cHalo;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float2* W = reinterpret_cast<float2*>(smemRaw);
     float2* bufs = W + P;
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slice
     if (sp.useCtf && tid == 32) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
     float2* buf = bufs + seq * kFftBuf<P>;
     const int j0 = blockIdx.x * NC;                   // first own column; sequence 0 transforms column j0 - 1
-    const int kx = j0 + seq - 1;
+    const int kx = j0 + seq - kK1cHalo;
     const float2* col = (kx >= 0 && kx <= sp.R) ? a.T + ((size_t)img * Xh + kx) * N : nullptr;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slice
     // ---- halo pass: the slice value (flag in the LSB of re) of pixel (j0 - 1, ip) for every row; its weights, mask bits
     // and column-0 extras belong to the CTA that owns the column
     const int nRows = 2 * sp.R + 1;
-    if (j0 >= 2) {
+    if (kK1cHalo && j0 >= 2) {
         for (int r = tid; r < nRows; r += NT) {
             const int ipx = r - sp.R, jh = j0 - 1;
             const float2 F = bufs[fft_phys(ipx & (P - 1))];
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slice
         bool flag = false;
         float wDamped = 0.f, wUnmod = 0.f;
         if (own) {
-            const float2* b = bufs + (c + 1) * kFftBuf<P>;
+            const float2* b = bufs + (c + kK1cHalo) * kFftBuf<P>;
             const float2 F = b[fft_phys(ipx & (P - 1))];
             float4 cc = d_contrib_from_F(F, d_pixel_valid(a.s.jmax, sp, j, ipx), sp, ctf, sCtfF, weight, j, ipx);
             flag = cc.w != 0.f;
@@ -301,14 +306,23 @@ __global__ void __launch_bounds__((kColsPerCta<P> + 1) * P / 8) k_fft_cols_slice
         prv.x = __shfl_up_sync(0xffffffffu, pv.x, 1, NC);
         prv.y = __shfl_up_sync(0xffffffffu, pv.y, 1, NC);
         if (!act) continue;
-        if (c == 0) prv = (j0 >= 2) ? sHalo[r] : make_float2(0.f, 0.f);
+        if (kK1cHalo && c == 0) prv = (j0 >= 2) ? sHalo[r] : make_float2(0.f, 0.f);
         if (j > 0) {
             const size_t o1 = (size_t)(ipx + sp.Rp) * a.s.pitch + (j + a.s.colOff);
-            S4[o1 - 1] = make_float4(prv.x, prv.y, pv.x, pv.y);            // E(r, j-1)
+            if (kK1cHalo || c > 0) {
+                S4[o1 - 1] = make_float4(prv.x, prv.y, pv.x, pv.y);            // E(r, j-1)
+            } else {
+                // first column of the CTA: the left neighbour belongs to the previous CTA, which writes its half itself
+                reinterpret_cast<float2*>(S4 + (o1 - 1))[1] = pv;              // second half of E(r, j-1)
+            }
+            if (!kK1cHalo && c == NC - 1 && j <= sp.R) reinterpret_cast<float2*>(S4 + o1)[0] = pv;   // first half of E(r, j): the next CTA adds the second
             if (j <= a.s.colOff) {                                         // half-plane format: the first colOff mirrored columns only
                 const size_t o2 = (size_t)(-ipx + sp.Rp) * a.s.pitch + (-j + a.s.colOff);
-                S4[o2] = make_float4(pv.x, -pv.y, prv.x, -prv.y);         // E(-r, -j)
+                if (kK1cHalo || c > 0) S4[o2] = make_float4(pv.x, -pv.y, prv.x, -prv.y);         // E(-r, -j)
+                else reinterpret_cast<float2*>(S4 + o2)[0] = make_float2(pv.x, -pv.y);
             }
+            if (!kK1cHalo && c == NC - 1 && j + 1 <= a.s.colOff)          // second half of E(-r, -(j+1)), owned by the next CTA
+                reinterpret_cast<float2*>(S4 + ((size_t)(-ipx + sp.Rp) * a.s.pitch + (-(j + 1) + a.s.colOff)))[1] = make_float2(pv.x, -pv.y);
         }
         if (flag) {
             if (a.s.damped) a.s.damped[dOff + (size_t)r * (sp.R + 1) + j] = wDamped;
