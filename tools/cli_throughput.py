@@ -52,7 +52,7 @@ def main():
                               "--bufferSize", str(a.buffer), "-v", "1"] + (["--gpus", a.gpus] if a.gpus != "1" else []),
                              capture_output=True, text=True)
         dt = time.perf_counter() - t0
-        tail = [l for l in out.stdout.replace("\r", "\n").splitlines() if "images in" in l or "GPU time" in l or "wall (s)" in l]
+        tail = [l for l in out.stdout.replace("\r", "\n").splitlines() if ("images in" in l and "inserted" not in l) or "GPU time" in l or "wall (s)" in l]
         print("thr=%d wall %.2f s (%.0f images/s incl. process start) rc=%d | %s" % (thr, dt, a.n / dt, out.returncode, " | ".join(t.strip() for t in tail)), flush=True)
         if out.returncode:
             print(out.stderr[-500:])

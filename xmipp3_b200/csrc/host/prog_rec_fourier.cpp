@@ -619,8 +619,13 @@ void ProgRecFourierB200::run() {
     // is paid on a second thread while the particles are loaded and inserted; joined before the first reduce / finalize.
     int warmRc = RFB200_OK;
     std::thread warm;                           // started inside the try block below: it must be joined on every path
+    double tWarmWait = 0;
     auto joinWarm = [&] {
-        if (warm.joinable()) warm.join();
+        if (warm.joinable()) {
+            const auto tw = std::chrono::steady_clock::now();
+            warm.join();
+            tWarmWait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
+        }
         if (warmRc != RFB200_OK) throw ProgramError(std::string("warm-up failed: ") + api.last_error(h));
     };
     std::string loadError;
@@ -767,7 +772,8 @@ void ProgRecFourierB200::run() {
                 std::cout << " GPU time (ms): h2d " << t.h2d_ms << ", pad " << t.preprocess_ms << ", fft " << t.fft2d_ms << ", slices "
                           << t.slice_ms << ", gather " << t.gather_ms << ", edge " << t.edge_ms << ", finalize " << t.finalize_ms << "\n";
             std::cout << " wall (s): load + insert " << tInsert << ", reduce (incl. waiting for the slowest rank and, the first time, NCCL's connection set-up) "
-                      << tReduce << ", finalize + write " << tFinish << "\n";
+                      << tReduce << ", finalize + write " << tFinish << ", waiting for the set-up thread (FFT plan, NCCL connections) "
+                      << tWarmWait << "\n";
             std::cout << " " << n << " images in " << secs << " s (" << n / secs << " images/s including file I/O"
                       << (worldSize > 1 ? ", " + std::to_string(worldSize) + " GPUs" : std::string()) << ")" << std::endl;
         }
