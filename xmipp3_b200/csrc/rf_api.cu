@@ -335,7 +335,7 @@ int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs
     const size_t smem = sizeof(float2) * (P + kFftSeqs * kFftBuf<P>);
     constexpr int NC = kColsPerCta<P>;
     const int threadsC = (NC + kK1cHalo) * P / 8;
-    const size_t smemC = sizeof(float2) * (P + (NC + kK1cHalo) * kFftBuf<P> + (P + 2));      // twiddles, the sequences, halo values
+    const size_t smemC = sizeof(float2) * (P + (NC + kK1cHalo) * kFftBuf<P> + (P + 2)) + sizeof(int) * (P + 2);   // twiddles, the sequences, halo values, cut-off table
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

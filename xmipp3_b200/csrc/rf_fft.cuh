@@ -220,13 +220,17 @@ constexpr int kK1cHalo = 0;     // variant: no halo column; the two entry halves
 #else
 constexpr int kK1cHalo = 1;
 #endif
+#ifndef RF_K1C_CTAS
+#define RF_K1C_CTAS 1          // CTAs per SM the register budget of K1c is sized for (P <= 512)
+#endif
 template <int P>
-__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
+__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P <= 512) ? RF_K1C_CTAS : 1) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
     constexpr int NC = kColsPerCta<P>, NS = NC + kK1cHalo;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float2* W = reinterpret_cast<float2*>(smemRaw);
     float2* bufs = W + P;
     float2* sHalo = bufs + NS * kFftBuf<P>;          // slice value of the halo pixel of every row (P + 1 entries)
+    int* sJmax = reinterpret_cast<int*>(sHalo + (P + 2));   // resolution cut-off per row: read by every pixel, staged once per CTA
     __shared__ CtfConsts sCtf;
     __shared__ CtfFloat sCtfF;
     constexpr int TPS = P / 8, Xh = P / 2 + 1, NT = NS * TPS;
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8) k_fft_col
     const int N = a.N, img = blockIdx.y;
     const int tid = threadIdx.x, seq = tid / TPS, t = tid % TPS;
     for (int i = tid; i < P; i += NT) W[i] = __ldg(a.twiddle + i);
+    for (int i = tid; i <= sp.iHi - sp.iLo; i += NT) sJmax[i] = __ldg(a.s.jmax + i);
     if (sp.useCtf && tid < (int)(sizeof(CtfConsts) / 8))
         reinterpret_cast<double*>(&sCtf)[tid] = reinterpret_cast<const double*>(a.s.ctfs + img)[tid];
     if (sp.useCtf && tid == 32) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8) k_fft_col
         for (int r = tid; r < nRows; r += NT) {
             const int ipx = r - sp.R, jh = j0 - 1;
             const float2 F = bufs[fft_phys(ipx & (P - 1))];
-            const float4 cc = d_contrib_from_F(F, d_pixel_valid(a.s.jmax, sp, jh, ipx), sp, ctf, sCtfF, weight, jh, ipx);
+            const float4 cc = d_contrib_from_F(F, d_pixel_valid(sJmax, sp, jh, ipx), sp, ctf, sCtfF, weight, jh, ipx);
             sHalo[r] = make_float2(d_set_flag(cc.x, cc.w != 0.f), cc.y);
         }
     }
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8) k_fft_col
         if (own) {
             const float2* b = bufs + (c + kK1cHalo) * kFftBuf<P>;
             const float2 F = b[fft_phys(ipx & (P - 1))];
-            float4 cc = d_contrib_from_F(F, d_pixel_valid(a.s.jmax, sp, j, ipx), sp, ctf, sCtfF, weight, j, ipx);
+            float4 cc = d_contrib_from_F(F, d_pixel_valid(sJmax, sp, j, ipx), sp, ctf, sCtfF, weight, j, ipx);
             flag = cc.w != 0.f;
             wDamped = cc.z;
             wUnmod = (cc.z != 0.f || flag) ? weight : 0.f;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8) k_fft_col
             } else {
                 // column 0: original (0,ip) plus the mirror of original (0,-ip) (see k_make_slices2)
                 const float2 Fm = b[fft_phys((-ipx) & (P - 1))];
-                float4 m = d_contrib_from_F(Fm, d_pixel_valid(a.s.jmax, sp, 0, -ipx), sp, ctf, sCtfF, weight, 0, -ipx);
+                float4 m = d_contrib_from_F(Fm, d_pixel_valid(sJmax, sp, 0, -ipx), sp, ctf, sCtfF, weight, 0, -ipx);
                 flag = flag || (m.w != 0.f);
                 pv = make_float2(d_set_flag(cc.x + m.x, flag), cc.y - m.y);
                 a.s.col0[(size_t)img * sp.side + (ipx + sp.Rp)] = make_float2(d_set_flag(cc.x, flag), cc.y);

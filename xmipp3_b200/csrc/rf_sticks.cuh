@@ -187,6 +187,34 @@ __device__ __forceinline__ u64 d_mul2(u64 a, u64 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ u64 d_fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// Address of 16-byte entry `off` of a (warp-uniform) slice: one IMAD.WIDE.U32 instead of the sign extension + 64-bit
+// shift/add chain a signed index costs.
+__device__ __forceinline__ u64 d_entry_addr(const float4* base, unsigned off) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(off), "l"(base));
+    return r;
+}
+// Pixel pair at row + kByteOff, fetched only if dy <= lim, zero otherwise.  (The zeroing costs two CS2R per pair.  Declaring the
+// registers as plain outputs of a predicated load would save them - a skipped pair is only read by predicated-off
+// candidates - but then the 32 pixel registers are live across the whole step loop and the kernel spills: measured at
+// compile time, 350 bytes of spill traffic in the hot loop.)
+template <int kByteOff>
+__device__ __forceinline__ float4 d_load_pair_if(u64 row, float dy, float lim) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.le.f32 p, %5, %6;\n\t"
+        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%7];\n\t"
+        "}"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(row), "f"(dy), "f"(lim), "n"(kByteOff));
+    return v;
+}
 
 // Two adjacent candidates (tj = 2q, 2q+1) of one window row, fully predicated:
 //   S = dy + dx (one FADD2 with dy broadcast); idx = round(S) by the 2^23 trick (one FADD2); per candidate: accept test,
@@ -264,26 +292,32 @@ __device__ __forceinline__ void d_pair(const float dy, const u64 dx2, const floa
 }
 
 // One step of one column, second generation: the K x K candidate window of the lane's voxel, two candidates per asm
-// block.  p points at the window origin (16-byte aligned pixel pair); (da0, db0) is the offset of the projected voxel from
-// the window origin, h2s = h^2 * iDelta.  kSlow weighs every candidate with its multiplicity (0 outside the resolution
-// disc, 2 on column j = 0), looked up per window row.
+// block.  `off` is the entry index of the window origin inside the image's slice `sl` (warp-uniform base, 32-bit per-lane
+// offset: a row address is one IMAD.WIDE.U32); (da0, db0) is the offset of the projected voxel from the window origin,
+// h2s = h^2 * iDelta.  kSlow weighs every candidate with its multiplicity (0 outside the resolution disc, 2 on column
+// j = 0), looked up per window row.
 template <int K, bool kSlow, bool kFlags>
-__device__ __forceinline__ void d_stick_window2(const float4* __restrict__ p, const int pitch, const float da0, const float db0, const float h2s,
-                                                const float kI, const float sMax, const uint32_t tblAdj, const int jc, const int ic,
+__device__ __forceinline__ void d_stick_window2(const float4* __restrict__ sl, const unsigned off, const unsigned pitch, const float da0, const float db0,
+                                                const float h2s, const float kI, const float sMax, const uint32_t tblAdj, const int jc, const int ic,
                                                 const int* __restrict__ rimTab, float& accRe, float& accIm, float& accW) {
     constexpr int NP = (K + 1) / 2;
-    float dys[K];
+    const u64 kI2 = d_pk(kI, kI);
+    // squared row offsets + h^2, two per register pair: dys[q] = (kI * db) * db + h2s with db = db0 - q
+    float dys[2 * NP];
+    {
+        const u64 db2 = d_pk(db0, db0), h2 = d_pk(h2s, h2s);
 #pragma unroll
-    for (int q = 0; q < K; ++q) {
-        const float db = db0 - (float)q;
-        dys[q] = fmaf(kI * db, db, h2s);
+        for (int q = 0; q < NP; ++q) {
+            const u64 d = d_add2(db2, d_pk(-(float)(2 * q), -(float)(2 * q + 1)));
+            d_upk(d_fma2(d_mul2(kI2, d), d, h2), dys[2 * q], dys[2 * q + 1]);
+        }
     }
     // squared column offsets, two per register pair; lim[q]: a pair is needed iff dys <= sMax - min(dxs of the pair).  The
     // load predicate carries a slack of 0.02 table steps, so that it can never be false for an accepted candidate whatever
     // the rounding of dy + dx (S < 10^4, one ulp = 10^-3)
     u64 dxs2[NP];
     float lim[NP];
-    const u64 da2 = d_pk(da0, da0), kI2 = d_pk(kI, kI);
+    const u64 da2 = d_pk(da0, da0);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         const u64 d = d_add2(da2, d_pk(-(float)(2 * q), -(float)(2 * q + 1)));
@@ -310,16 +344,18 @@ __device__ __forceinline__ void d_stick_window2(const float4* __restrict__ p, co
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             if (t0 + g < K) {
+                const u64 row = d_entry_addr(sl, off + (unsigned)(t0 + g) * pitch);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
 #ifdef RF_STICK_UNCOND_LOADS
-                    px[g][q] = __ldg(p + (t0 + g) * pitch + 2 * q);
+                    px[g][q] = __ldg(reinterpret_cast<const float4*>(row) + 2 * q);
 #else
                     // A pixel pair is fetched only if one of its two candidates can be accepted: fewer lanes per load
-                    // instruction means fewer cache lines (L1 wavefronts) per instruction.  The registers are zeroed
-                    // first: a conditionally written register is live across the whole step loop otherwise.
-                    px[g][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (dys[t0 + g] <= lim[q]) px[g][q] = __ldg(p + (t0 + g) * pitch + 2 * q);
+                    // instruction means fewer cache lines (L1 wavefronts) per instruction.
+                    if (q == 0) px[g][q] = d_load_pair_if<0>(row, dys[t0 + g], lim[q]);
+                    else if (q == 1) px[g][q] = d_load_pair_if<32>(row, dys[t0 + g], lim[q]);
+                    else if (q == 2) px[g][q] = d_load_pair_if<64>(row, dys[t0 + g], lim[q]);
+                    else px[g][q] = d_load_pair_if<96>(row, dys[t0 + g], lim[q]);
 #endif
                 }
             }
@@ -437,6 +473,8 @@ __device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const Stick
     const float4* sl = slices + (size_t)pl.img * imgStride;
     const float weight = pl.weight;
     uint32_t touched = 0;          // bit b <-> depths 2b, 2b + 1 of the stick hold something
+    if (!kChecked && t.tauLo <= t.tauHi)       // every step of the lane's walk is taken: the bits are known up front
+        touched = ((2u << ((t.tauHi - t.tauLo) >> 1)) - 1u) << (t.tauLo >> 1);
     for (int s = 0; s < nIter; ++s) {
         const int tau = t.tauLo + 2 * s;
         const StickStep q = d_step<K, kChecked>(c, t, pl.nd, tau);
@@ -447,19 +485,19 @@ __device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const Stick
             const float da0 = q.ar - __int2float_rn(q.jw), db0 = q.br - __int2float_rn(q.iw);
             const float h2s = q.h * q.h * c.iDelta;
             const int jc = q.ja + q.jw, ic = q.jb + q.iw;
-            const float4* p = sl + ((ic + c.Rp) * c.pitch + (jc + c.colOff));
+            const unsigned off = (unsigned)((ic + c.Rp) * c.pitch + (jc + c.colOff));       // in bounds: >= 0
             float accRe = 0.f, accIm = 0.f, accWt = 0.f;
             if (kChecked && anySlow)
-                d_stick_window2<K, true, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
+                d_stick_window2<K, true, kFlags>(sl, off, (unsigned)c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
             else
-                d_stick_window2<K, false, kFlags>(p, c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
+                d_stick_window2<K, false, kFlags>(sl, off, (unsigned)c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
             const int o = tau * kStickCols + col;
             float2 v = accV[o];
             v.x += accRe;
             v.y = fmaf(q.sg, accIm, v.y);
             accV[o] = v;
             accW[o] = fmaf(weight, accWt, accW[o]);
-            touched |= 1u << (tau >> 1);
+            if (kChecked) touched |= 1u << (tau >> 1);
         }
     }
     return touched;
@@ -570,6 +608,7 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
     const float hA = 0.5f * (kStickA - 1), hB = 0.5f * (kStickB - 1), hD = 0.5f * (kStickL - 1);
     const float inLim = geo.inplane_reach + sqrtf(hA * hA + hB * hB + hD * hD) * sqrtf(1.0f / geo.s2) + 1.0f;
     const float inLim2 = inLim * inLim;
+    const float pxPerVox = sqrtf(1.0f / geo.s2), rimInR = geo.rimIn2 > 0.f ? sqrtf(geo.rimIn2) : -1.f;
     const int imgStride = geo.planeStride;
 
     for (;;) {
@@ -611,7 +650,8 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
         const float cA = (float)A0c + hA, cB = (float)B0c + hB, cD = (float)T0c + hD;
         for (int kb = 0; kb < a.nPlanes; kb += 32) {
             const int kk = kb + lane;
-            bool hit = false;
+            bool hit = false, hint = false;
+            float alc = 0.f;
             if (kk < a.nPlanes) {
                 const float* s = a.planesSoA + kk;
                 constexpr int kMaxPlanes = kLaunchPlanes;
@@ -619,12 +659,26 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
                 const float hc = cA * na + cB * nb + cD * nd;
                 const float supp = hA * fabsf(na) + hB * fabsf(nb) + hD * fabsf(nd);
                 if (fabsf(hc) <= rSlab + supp + 1e-2f) {
-                    const float ac = cA * __ldg(s) + cB * __ldg(s + kMaxPlanes) + cD * __ldg(s + 2 * kMaxPlanes);
-                    const float bc = cA * __ldg(s + 3 * kMaxPlanes) + cB * __ldg(s + 4 * kMaxPlanes) + cD * __ldg(s + 5 * kMaxPlanes);
+                    const float e1d = __ldg(s + 2 * kMaxPlanes), e2d = __ldg(s + 5 * kMaxPlanes);
+                    const float ac = cA * __ldg(s) + cB * __ldg(s + kMaxPlanes) + cD * e1d;
+                    const float bc = cA * __ldg(s + 3 * kMaxPlanes) + cB * __ldg(s + 4 * kMaxPlanes) + cD * e2d;
                     hit = ac * ac + bc * bc <= inLim2;
+                    // Plain-task hint, decided here for 32 planes at once: every voxel this stick can have inside the slab
+                    // of the plane lies within F pixels (in the image) of the point where the stick's centre column crosses
+                    // the plane.  If that disc is inside the all-valid radius and on one side of the strip around column 0,
+                    // every step of every lane takes the unchecked path with the same mirror sign, and the per-lane test
+                    // of both walk ends (two checked step evaluations per task) is skipped.
+                    const float inv = __frcp_rn(nd), sh = hc * inv;
+                    alc = ac - sh * e1d;
+                    const float bec = bc - sh * e2d;
+                    const float dd = (hA * fabsf(na) + hB * fabsf(nb) + rSlab) * fabsf(inv);
+                    const float F = sqrtf(hA * hA + hB * hB + dd * dd) * pxPerVox + 0.5f;
+                    const float lim = rimInR - F;
+                    hint = hit && lim > 0.f && alc * alc + bec * bec <= lim * lim && fabsf(alc) > c.rhoCol0 + F;
                 }
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
+            const unsigned mHint = __ballot_sync(0xffffffffu, hint), mNeg = __ballot_sync(0xffffffffu, alc < 0.f);
             while (m) {
                 const int k = kb + __ffs(m) - 1;
                 m &= m - 1;
@@ -660,20 +714,25 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
                 const int nIter = __reduce_max_sync(0xffffffffu, max((t.tauHi - colLo + 2) >> 1, 0));
                 if (nIter == 0) continue;
                 // both ends of the lane's walk in bounds and free of special pixels -> unchecked loop
-                bool plain = true;
-                float aFirst = 1.f;
-                if (t.tauLo <= t.tauHi) {
-                    const int last = t.tauLo + ((t.tauHi - t.tauLo) & ~1);
-                    const StickStep q0 = d_step<K, true>(c, t, pl.nd, t.tauLo), q1 = d_step<K, true>(c, t, pl.nd, last);
-                    // "away from column 0" is the union of two half planes: both ends must lie in the SAME one (a steep
-                    // column can enter the strip |alpha| <= rho between two ends that are outside it on opposite sides)
-                    plain = q0.inb && q1.inb && !q0.special && !q1.special && (q0.sg == q1.sg);
-                    aFirst = q0.sg;
+                bool allPlain = true;
+                float aFirst = ((mNeg >> (k - kb)) & 1u) ? -1.f : 1.f;
+                if (!((mHint >> (k - kb)) & 1u)) {         // warp-uniform: no hint from the culling pass, test the lane's walk
+                    bool plain = true;
+                    aFirst = 1.f;
+                    if (t.tauLo <= t.tauHi) {
+                        const int last = t.tauLo + ((t.tauHi - t.tauLo) & ~1);
+                        const StickStep q0 = d_step<K, true>(c, t, pl.nd, t.tauLo), q1 = d_step<K, true>(c, t, pl.nd, last);
+                        // "away from column 0" is the union of two half planes: both ends must lie in the SAME one (a steep
+                        // column can enter the strip |alpha| <= rho between two ends that are outside it on opposite sides)
+                        plain = q0.inb && q1.inb && !q0.special && !q1.special && (q0.sg == q1.sg);
+                        aFirst = q0.sg;
+                    }
+                    allPlain = __all_sync(0xffffffffu, plain);
                 }
                 // which of a column's two lanes owns an accumulator depends on the parity of the column's first depth in
                 // THIS plane, so consecutive tasks may touch the same shared address from different lanes: order them
                 __syncwarp();
-                if (__all_sync(0xffffffffu, plain)) {
+                if (allPlain) {
                     if (aFirst < 0.f) {        // the lane's whole walk lies in the mirrored half: flip it once
                         t.sg = -1.f;
                         t.ja0 = -t.ja0; t.jb0 = -t.jb0;
