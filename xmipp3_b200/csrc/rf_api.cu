@@ -129,6 +129,16 @@ struct rfb200_handle_s {
     int* dPlaneImg = nullptr;
     ParamSlot slots[2];
     int slotIdx = 0;
+    // Device copies of a chunk's parameter tables, one set per slot.  dImg, dCtf, dPlanesD, dPlaneImg, dPlanesSoAp, dImgPlane0 and
+    // dFastSpaces above are the CURRENT set (the launches of a chunk capture the pointers); the next chunk's set is filled
+    // by DMA on the copy stream while this chunk computes, so no parameter traffic sits between two chunks on the compute
+    // stream (it used to: six small kernels reading pinned memory through a PCIe link busy with the next image batch).
+    struct DevParams {
+        ImgParams* img = nullptr; CtfConsts* ctf = nullptr; PlaneD* planesD = nullptr; int* planeImg = nullptr;
+        float* soaP = nullptr; int* imgPlane0 = nullptr; FastSpace* fast = nullptr;
+        size_t nImg = 0, nCtf = 0, nPlanesD = 0, nPlaneImg = 0, nSoaP = 0, nImgPlane0 = 0, nFast = 0;   // bytes
+        cudaEvent_t up = nullptr;
+    } dpar[2];
     std::map<int, cufftHandle> plans2d;
     // finalize
     cufftHandle plan3d = 0;
@@ -283,13 +293,38 @@ void resolve_timings(rfb200_handle h) {
     h->pending.clear();
 }
 
-// copy `bytes` (rounded up to 16) from pinned host memory to device memory with a kernel on the compute stream
+// Parameter tables of a chunk: DMA from the slot's pinned staging arrays into the slot's device set on the COPY stream (the
+// slot's previous user has finished: upload_chunk_params waited for its `done` event), one event, and the compute stream
+// waits for that event before the chunk's first kernel.
 int fetch_params(rfb200_handle h, void* dst, const void* srcPinned, size_t bytes) {
-    size_t n16 = (bytes + 15) / 16;
-    if (!n16) return RFB200_OK;
-    int blocks = (int)std::min<size_t>(64, (n16 + 255) / 256);
-    k_fetch_params<<<blocks, 256, 0, h->compute>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(srcPinned), n16);
-    RF_CUDA(h, cudaGetLastError());
+    if (!bytes) return RFB200_OK;
+    RF_CUDA(h, cudaMemcpyAsync(dst, srcPinned, bytes, cudaMemcpyHostToDevice, h->copy));
+    return RFB200_OK;
+}
+void use_param_set(rfb200_handle h, int si) {
+    const rfb200_handle_s::DevParams& d = h->dpar[si];
+    h->dImg = d.img; h->dCtf = d.ctf; h->dPlanesD = d.planesD; h->dPlaneImg = d.planeImg;
+    h->dPlanesSoAp = d.soaP; h->dImgPlane0 = d.imgPlane0; h->dFastSpaces = d.fast;
+}
+int params_uploaded(rfb200_handle h, int si) {
+    RF_CUDA(h, cudaEventRecord(h->dpar[si].up, h->copy));
+    RF_CUDA(h, cudaStreamWaitEvent(h->compute, h->dpar[si].up, 0));
+    return RFB200_OK;
+}
+// second device set with the sizes of the first (the cudaMalloc calls of do_create fill set 0 through the h->d* members)
+int make_param_sets(rfb200_handle h, size_t nImg, size_t nCtf, size_t nPlanesD, size_t nPlaneImg, size_t nSoaP, size_t nImgPlane0, size_t nFast) {
+    rfb200_handle_s::DevParams& a = h->dpar[0];
+    a.img = h->dImg; a.ctf = h->dCtf; a.planesD = h->dPlanesD; a.planeImg = h->dPlaneImg; a.soaP = h->dPlanesSoAp;
+    a.imgPlane0 = h->dImgPlane0; a.fast = h->dFastSpaces;
+    rfb200_handle_s::DevParams& b = h->dpar[1];
+    if (nImg) RF_CUDA(h, cudaMalloc(&b.img, nImg));
+    if (nCtf) RF_CUDA(h, cudaMalloc(&b.ctf, nCtf));
+    if (nPlanesD) RF_CUDA(h, cudaMalloc(&b.planesD, nPlanesD));
+    if (nPlaneImg) RF_CUDA(h, cudaMalloc(&b.planeImg, nPlaneImg));
+    if (nSoaP) RF_CUDA(h, cudaMalloc(&b.soaP, nSoaP));
+    if (nImgPlane0) RF_CUDA(h, cudaMalloc(&b.imgPlane0, nImgPlane0));
+    if (nFast) RF_CUDA(h, cudaMalloc(&b.fast, nFast));
+    for (int i = 0; i < 2; ++i) RF_CUDA(h, cudaEventCreateWithFlags(&h->dpar[i].up, cudaEventDisableTiming));
     return RFB200_OK;
 }
 
@@ -446,6 +481,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
             ++np;
         }
     }
+    use_param_set(h, &s == &h->slots[0] ? 0 : 1);
     int rcf = fetch_params(h, h->dImg, s.img, sizeof(ImgParams) * n);
     if (!rcf && h->cfg.use_ctf) rcf = fetch_params(h, h->dCtf, s.ctf, sizeof(CtfConsts) * n);
     if (!rcf && np) {
@@ -488,6 +524,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         if (!s.launches.empty()) rcf = fetch_params(h, h->dPlanesSoAp, s.soaP, sizeof(float) * 9 * kLaunchPlanes * s.launches.size());
         if (!rcf) rcf = fetch_params(h, h->dImgPlane0, s.imgPlane0, sizeof(int) * n);
     }
+    if (!rcf) rcf = params_uploaded(h, &s == &h->slots[0] ? 0 : 1);
     if (rcf) return rcf;
     s.used = true;
     *anySplineOut = anySpline;
@@ -634,9 +671,11 @@ int process_chunk_fast(rfb200_handle h, const float* dRaw, const rfb200_particle
         for (int sIdx = 0; sIdx < h->nSymTot; ++sIdx)
             host::make_fast_space(fg, &h->sym[9 * sIdx], p.rot, p.tilt, p.psi, i, q.weight, s.fast[np++]);
     }
+    use_param_set(h, &s == &h->slots[0] ? 0 : 1);
     int rc = fetch_params(h, h->dImg, s.img, sizeof(ImgParams) * n);
     if (!rc && h->cfg.use_ctf) rc = fetch_params(h, h->dCtf, s.ctf, sizeof(CtfConsts) * n);
     if (!rc && np) rc = fetch_params(h, h->dFastSpaces, s.fast, sizeof(FastSpace) * np);
+    if (!rc) rc = params_uploaded(h, &s == &h->slots[0] ? 0 : 1);
     if (rc) return rc;
     s.used = true;
     rc = pad_and_fft(h, dRaw, n, anySpline);
@@ -743,11 +782,20 @@ void free_all(rfb200_handle h) {
     for (auto& kv : h->plans2d) cufftDestroy(kv.second);
     if (h->havePlan3d) cufftDestroy(h->plan3d);
     void* dev[] = {h->dBlobTable, h->dJmax, h->dEdge, h->dEdgeGroups, h->dG, h->dVb, h->dWb, h->dWb2, h->dVsaved, h->dWsaved, h->dW2saved, h->dRaw[0], h->dRaw[1],
-                   h->dPad, h->dCoef, h->dFft, h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dNorm,
+                   h->dPad, h->dCoef, h->dFft, h->dNorm,
                    h->dVol, h->dOut, h->dSlices2, h->dCol02, h->dDamped, h->dDamped2, h->dDampedMask, h->dD, h->dD2, h->dRimTab, h->dUnits[0], h->dUnits[1], h->dUnits[2],
-                   h->dStickCounters, h->dTwiddle, h->dPlanesDp, h->dPlanesSoAp, h->dPlanesSStage, h->dImgPlane0,
-                   h->dFastPix, h->dFastSpaces, h->dFastVh, h->dFastVc, h->dFastWh, h->dFastWc, h->dFastAcc};
+                   h->dStickCounters, h->dTwiddle, h->dPlanesDp, h->dPlanesSStage,
+                   h->dFastPix, h->dFastVh, h->dFastVc, h->dFastWh, h->dFastWc, h->dFastAcc};
     for (void* p : dev) if (p) cudaFree(p);
+    if (!h->dpar[0].up) {        // creation failed before the parameter sets existed: the members still own set 0
+        void* own[] = {h->dImg, h->dCtf, h->dPlanesD, h->dPlaneImg, h->dPlanesSoAp, h->dImgPlane0, h->dFastSpaces};
+        for (void* p : own) if (p) cudaFree(p);
+    }
+    for (auto& d : h->dpar) {
+        void* dp[] = {d.img, d.ctf, d.planesD, d.planeImg, d.soaP, d.imgPlane0, d.fast};
+        for (void* p : dp) if (p) cudaFree(p);
+        if (d.up) cudaEventDestroy(d.up);
+    }
     for (auto& s : h->slots) {
         void* hp[] = {s.img, s.ctf, s.planesD, s.planeImg, s.planesDp, s.planesS, s.soaP, s.imgPlane0, s.fast};
         for (void* p : hp) if (p) cudaFreeHost(p);
@@ -816,6 +864,7 @@ int do_create_fast(rfb200_handle h) {
     RF_CUDA(h, cudaMalloc(&h->dFastSpaces, sizeof(FastSpace) * maxSpaces + 16));
     RF_CUDA(h, cudaMalloc(&h->dImg, sizeof(ImgParams) * CH));
     RF_CUDA(h, cudaMalloc(&h->dCtf, sizeof(CtfConsts) * CH));
+    if (int rcp = make_param_sets(h, sizeof(ImgParams) * CH, sizeof(CtfConsts) * CH, 0, 0, 0, 0, sizeof(FastSpace) * maxSpaces + 16)) return rcp;
     for (auto& s : h->slots) {
         RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
         RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));
@@ -1014,6 +1063,8 @@ int do_create(rfb200_handle h) {
         RF_CUDA(h, cudaMalloc(&h->dPlanesSoAp, sizeof(float) * 9 * kLaunchPlanes * maxLaunches));
         RF_CUDA(h, cudaMalloc(&h->dImgPlane0, sizeof(int) * CH + 16));
     }
+    if (int rcp = make_param_sets(h, sizeof(ImgParams) * CH, sizeof(CtfConsts) * CH, sizeof(PlaneD) * maxPlanes + 16, sizeof(int) * maxPlanes + 16,
+                                  sizeof(float) * 9 * kLaunchPlanes * maxLaunches, sizeof(int) * CH + 16, 0)) return rcp;
     for (auto& s : h->slots) {
         RF_CUDA(h, cudaMallocHost(&s.img, sizeof(ImgParams) * CH));
         RF_CUDA(h, cudaMallocHost(&s.ctf, sizeof(CtfConsts) * CH));

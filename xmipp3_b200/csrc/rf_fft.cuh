@@ -57,24 +57,42 @@ __device__ __forceinline__ void dft_small<8>(float2* v, float2* x) {
     x[0] = v[0]; x[1] = v[4]; x[2] = v[2]; x[3] = v[6]; x[4] = v[1]; x[5] = v[5]; x[6] = v[3]; x[7] = v[7];
 }
 
+// Barrier among the P/8 threads that transform ONE sequence (`seq` = index of the sequence inside the CTA).  Sequences are
+// independent, so a CTA-wide barrier would only make them wait for each other: sequences of >= 64 threads use their own
+// named barrier (ids 1..15; id 0 is __syncthreads), a sequence of <= 32 threads lives inside one warp.
+template <int P>
+__device__ __forceinline__ void fft_seq_barrier(int seq) {
+    constexpr int TPS = P / 8;
+    if (TPS >= 64) asm volatile("bar.sync %0, %1;" ::"r"(seq + 1), "n"(TPS) : "memory");
+    else __syncwarp();
+}
+
 // One Stockham stage of radix R over a sequence of P points held in the padded shared buffer `buf`; the P/8 threads
 // of the sequence (index t) each handle 8 points = 8/R butterflies.  W[k] = exp(-2 pi i k / P).  All threads of
-// the CTA call this together (two CTA barriers).
+// the sequence call this together (two sequence barriers).
 template <int P, int R, int Ns>
-__device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ W, int t) {
+__device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ W, int t, int seq) {
     constexpr int NB = 8 / R;               // butterflies per thread
     float2 v[8];
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
         const int j = t * NB + q, k = j % Ns;
+        // twiddles W^(r k P/(Ns R)), r = 1..R-1: one table load, the powers by multiplication (the stages are bound by the
+        // shared-memory instruction queue, the FP32 pipe has room; 6 complex products replace 6 loads for radix 8)
+        float2 tw[8];
+        if (Ns > 1) {
+            tw[1] = W[(k * (P / (Ns * R))) & (P - 1)];
+            if (R > 2) { tw[2] = cmul(tw[1], tw[1]); tw[3] = cmul(tw[2], tw[1]); }
+            if (R > 4) { tw[4] = cmul(tw[2], tw[2]); tw[5] = cmul(tw[4], tw[1]); tw[6] = cmul(tw[3], tw[3]); tw[7] = cmul(tw[4], tw[3]); }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float2 a = buf[fft_phys(j + r * (P / R))];
-            if (Ns > 1 && r > 0) a = cmul(a, W[(r * k * (P / (Ns * R))) & (P - 1)]);
+            if (Ns > 1 && r > 0) a = cmul(a, tw[r]);
             v[q * R + r] = a;
         }
     }
-    __syncthreads();
+    fft_seq_barrier<P>(seq);
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
         const int j = t * NB + q, k = j % Ns;
@@ -84,41 +102,41 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 #pragma unroll
         for (int r = 0; r < R; ++r) buf[fft_phys(j0 + r * Ns)] = x[r];
     }
-    __syncthreads();
+    fft_seq_barrier<P>(seq);
 }
 
 // forward FFT (e^{-i...}, unnormalised) of the P points in buf, natural order in and out
 template <int P>
-__device__ __forceinline__ void fft_block(float2* buf, const float2* __restrict__ W, int t);
+__device__ __forceinline__ void fft_block(float2* buf, const float2* __restrict__ W, int t, int seq);
 template <>
-__device__ __forceinline__ void fft_block<64>(float2* buf, const float2* __restrict__ W, int t) {
-    fft_stage<64, 8, 1>(buf, W, t);
-    fft_stage<64, 8, 8>(buf, W, t);
+__device__ __forceinline__ void fft_block<64>(float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_stage<64, 8, 1>(buf, W, t, seq);
+    fft_stage<64, 8, 8>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<128>(float2* buf, const float2* __restrict__ W, int t) {
-    fft_stage<128, 8, 1>(buf, W, t);
-    fft_stage<128, 8, 8>(buf, W, t);
-    fft_stage<128, 2, 64>(buf, W, t);
+__device__ __forceinline__ void fft_block<128>(float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_stage<128, 8, 1>(buf, W, t, seq);
+    fft_stage<128, 8, 8>(buf, W, t, seq);
+    fft_stage<128, 2, 64>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<256>(float2* buf, const float2* __restrict__ W, int t) {
-    fft_stage<256, 8, 1>(buf, W, t);
-    fft_stage<256, 8, 8>(buf, W, t);
-    fft_stage<256, 4, 64>(buf, W, t);
+__device__ __forceinline__ void fft_block<256>(float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_stage<256, 8, 1>(buf, W, t, seq);
+    fft_stage<256, 8, 8>(buf, W, t, seq);
+    fft_stage<256, 4, 64>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<512>(float2* buf, const float2* __restrict__ W, int t) {
-    fft_stage<512, 8, 1>(buf, W, t);
-    fft_stage<512, 8, 8>(buf, W, t);
-    fft_stage<512, 8, 64>(buf, W, t);
+__device__ __forceinline__ void fft_block<512>(float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_stage<512, 8, 1>(buf, W, t, seq);
+    fft_stage<512, 8, 8>(buf, W, t, seq);
+    fft_stage<512, 8, 64>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<1024>(float2* buf, const float2* __restrict__ W, int t) {
-    fft_stage<1024, 8, 1>(buf, W, t);
-    fft_stage<1024, 8, 8>(buf, W, t);
-    fft_stage<1024, 8, 64>(buf, W, t);
-    fft_stage<1024, 2, 512>(buf, W, t);
+__device__ __forceinline__ void fft_block<1024>(float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_stage<1024, 8, 1>(buf, W, t, seq);
+    fft_stage<1024, 8, 8>(buf, W, t, seq);
+    fft_stage<1024, 8, 64>(buf, W, t, seq);
+    fft_stage<1024, 2, 512>(buf, W, t, seq);
 }
 
 #ifndef RF_FFT_SEQS
@@ -165,7 +183,8 @@ __global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_rows(const __grid_const
         buf[fft_phys(x)] = z;
     }
     __syncthreads();
-    fft_block<P>(buf, W, t);
+    fft_block<P>(buf, W, t, seq);
+    __syncthreads();              // the untangling reads every sequence of the CTA
     // untangle the two real transforms and write T[kx][row], 16 consecutive rows per kx
     const int nOut = Xh * 2 * kFftSeqs;
     for (int o = tid; o < nOut; o += kFftSeqs * TPS) {
@@ -206,19 +225,25 @@ __device__ __forceinline__ bool d_pixel_valid(const int* __restrict__ jmax, cons
     return ip >= sp.iLo && ip <= sp.iHi && j <= jmax[ip - sp.iLo];
 }
 
-// Columns per CTA of K1c (plus one halo column on the left): 8 for P <= 512, 4 for P = 1024 (thread limit)
-template <int P> constexpr int kColsPerCta = (P >= 1024) ? 4 : 8;
+// Columns per CTA of K1c: 8 for P <= 512, 4 for P = 1024 (thread limit).
+#ifndef RF_K1C_COLS
+#define RF_K1C_COLS 8
+#endif
+template <int P> constexpr int kColsPerCta = (P >= 1024) ? 4 : RF_K1C_COLS;
 
-// grid (ceil((R+2) / NC), nImg), block (NC+1) * P/8 threads: columns kx = NC*blockIdx.x .. +NC-1 and the halo column
-// NC*blockIdx.x - 1.  With the left neighbour's pixel at hand every lane writes a WHOLE 16-byte entry,
-// E(r, j-1) = (p(r,j-1), p(r,j)) (and, for the few columns next to j = 0 that the half-plane format keeps on the mirrored
-// side, E(-r, -j) = (conj p(r,j), conj p(r,j-1))), so a row piece of a CTA is NC consecutive entries = full 32-byte sectors
-// and one store request.  (Round 1 stored the full plane: every pixel four times, 4.3 GB of DRAM writes per 1024
-// particles at box 256; the half-plane format halves that.)
-#ifdef RF_K1C_NO_HALO
-constexpr int kK1cHalo = 0;     // variant: no halo column; the two entry halves at a CTA's column boundary are 8-byte stores
-#else
+// grid (ceil((R+2) / NC), nImg), block (NC + halo) * P/8 threads: columns kx = NC*blockIdx.x .. +NC-1.  A slice entry is
+// a pixel PAIR, E(r, j-1) = (p(r,j-1), p(r,j)) (and, for the few columns next to j = 0 that the half-plane format keeps on
+// the mirrored side, E(-r, -j) = (conj p(r,j), conj p(r,j-1))): inside a CTA the left neighbour comes by shuffle and a
+// lane writes the whole 16-byte entry; at the CTA's first and last column the two halves of an entry belong to two CTAs
+// and are written as 8-byte stores.
+// Variant -DRF_K1C_HALO (round 1 / early round 2 default): the CTA also transforms the column on its left (a ninth
+// sequence) and evaluates its pixels, so that every store is a whole entry.  Measured on B200 (profiles/r2b_ab_k1c.txt):
+// 9.25 ms per 4096 particles with the halo, 8.44 ms without - the extra FFT and CTF evaluations (1/8 more work, and 576
+// threads do not divide the 513 x 8 pixels of a CTA as well as 512 do) cost more than the split stores.
+#ifdef RF_K1C_HALO
 constexpr int kK1cHalo = 1;
+#else
+constexpr int kK1cHalo = 0;
 #endif
 #ifndef RF_K1C_CTAS
 #define RF_K1C_CTAS 1          // CTAs per SM the register budget of K1c is sized for (P <= 512)
@@ -255,7 +280,8 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P <= 512
         buf[fft_phys(y)] = z;
     }
     __syncthreads();
-    fft_block<P>(buf, W, t);
+    fft_block<P>(buf, W, t, seq);
+    if (kK1cHalo) __syncthreads();   // the halo pass reads sequence 0
 
     const CtfConsts* ctf = sp.useCtf ? &sCtf : nullptr;
     const float weight = a.s.ip[img].weight;
@@ -278,6 +304,11 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P <= 512
     const int wordsPerRow = (sp.R + 1 + 31) / 32;
     const int nElem = nRows * NC;
     const int nIter = (nElem + NT - 1) / NT;
+#ifndef RF_K1C_UNROLL
+#define RF_K1C_UNROLL 1
+#endif
+    constexpr int kUnroll = RF_K1C_UNROLL;
+#pragma unroll kUnroll
     for (int it = 0; it < nIter; ++it) {
         const int o = tid + it * NT;
         const int c = o & (NC - 1), r = o / NC;

@@ -26,9 +26,10 @@ __device__ __forceinline__ int d_tile_slot(int vx, int vy, int vz) {
     return brick * 32 + lane;
 }
 __device__ __forceinline__ int64_t d_blocked_index(const Geometry& geo, int ux, int uy, int uz) {
-    int x = ux, y = uy - geo.lo, z = uz - geo.lo;
-    int64_t tile = ((int64_t)(z / kTileZ) * geo.ty + (y / kTileY)) * geo.tx + (x / kTileX);
-    return tile * kTileVox + d_tile_slot(x % kTileX, y % kTileY, z % kTileZ);
+    // stored-offset coordinates are non-negative: unsigned arithmetic turns the divisions into plain shifts and masks
+    const unsigned x = (unsigned)ux, y = (unsigned)(uy - geo.lo), z = (unsigned)(uz - geo.lo);
+    const unsigned tile = ((z / kTileZ) * (unsigned)geo.ty + (y / kTileY)) * (unsigned)geo.tx + (x / kTileX);
+    return (int64_t)tile * kTileVox + d_tile_slot((int)(x % kTileX), (int)(y % kTileY), (int)(z % kTileZ));
 }
 // natural lattice point owned by the tile gather? (host twin: host::main_owns)
 __device__ __forceinline__ bool d_main_owns(const Geometry& geo, int ux, int uy) {
@@ -392,13 +393,6 @@ __global__ void __launch_bounds__(256) k_export(const __grid_constant__ Geometry
     if (x == 0 && uy <= c_geo.yHalf) { v.x *= 0.5f; v.y *= 0.5f; w *= 0.5f; }
     V[idx] = v;
     W[idx] = w;
-}
-
-// Parameter upload by the SMs: reads the chunk's (small) parameter blocks straight from pinned, mapped host
-// memory.  A DMA copy would queue behind the 268 MB particle transfers of the copy stream in the single
-// host-to-device engine and stall the compute stream for milliseconds (seen in the stage timeline).
-__global__ void __launch_bounds__(256) k_fetch_params(uint4* __restrict__ dst, const uint4* __restrict__ srcHost, size_t n16) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = srcHost[i];
 }
 
 // y += x (merging a saved half-set into the current accumulators)

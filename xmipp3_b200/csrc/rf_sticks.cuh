@@ -910,34 +910,34 @@ struct DampedArgs {
 };
 
 // grid (ceil(words/256), nImg).  Every thread reads one word of the flag mask (32 pixels); the warp then walks the
-// flagged pixels one at a time (they are rare), the 32 lanes sharing the (floor(2r)+1)^3 candidate lattice points
-// of the pixel.  This is the reference's scatter (RF.cpp:628-792) restricted to W of those pixels.
+// flagged pixels one at a time (they are rare).  The (floor(2r)+1)^3 candidate lattice points of a pixel are tested 64 at
+// a time (two per lane) and the ACCEPTED ones (about 45 %) are compacted through shared memory, so the weight / index /
+// atomic part runs once per 32 accepted candidates instead of once per 32 candidates.  The pixel position and the window
+// origin are double precision (the reference's decisions, RF.cpp:628-650); from the origin on, offsets are < 2r + 1 and
+// the distance, the table index and the weight are single precision like everything in the main gather.  This is the
+// reference's scatter (RF.cpp:628-792) restricted to W of those pixels.
 __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ DampedArgs a) {
     const Geometry& geo = a.geo;
     const int R = geo.R, Z = geo.Z;
     const int img = blockIdx.y;
     const int cols = R + 1, total = cols * (2 * R + 1);
     const int wordsPerRow = (cols + 31) / 32, nWords = wordsPerRow * (2 * R + 1);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int widx0 = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t sList[8][64];      // per warp: packed offsets of the accepted candidates of one group of 64
     uint32_t word = 0;
     if (widx0 < nWords) word = __ldg(a.mask + (size_t)img * nWords + widx0);
     unsigned any = __ballot_sync(0xffffffffu, word != 0);
     if (!any) return;
     const int p0 = a.imgPlane0[img];
     if (p0 < 0) return;
-    const double r = geo.r, r2 = r * r;
+    const double r = geo.r;
+    const float r2F = geo.r * geo.r, iDeltaF = (float)a.iDeltaD;
     const double voxPerPix = (double)Z / (double)geo.P;
     const double sc = voxPerPix * voxPerPix;
-    // candidate lattice points of a pixel: a cube of edge E = floor(2r)+1 from ceil(p - r); the lane's share of the
-    // cube is fixed, so its offsets are computed once (no integer division in the loops when E^3 <= 128)
+    // candidate lattice points of a pixel: a cube of edge E = floor(2r)+1 from ceil(p - r)
     const int E = (int)floor(2.0 * r) + 1, E3 = E * E * E;
-    int ox[4], oy[4], oz[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int cidx = lane + 32 * i;
-        ox[i] = cidx % E; oy[i] = (cidx / E) % E; oz[i] = cidx / (E * E);
-    }
+    const unsigned ltMask = (1u << lane) - 1u;
     // |u| <= Z/2 + r + 1, so one conditional add wraps an index into [0, Z)
     auto wrap1 = [Z](int x) { return x < 0 ? x + Z : (x >= Z ? x - Z : x); };
     while (any) {
@@ -950,8 +950,8 @@ __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ 
         const int j = jBase + __ffs(w) - 1;
         w &= w - 1;
         const size_t e = (size_t)img * total + (size_t)row * cols + j;
-        const float dd = __ldg(a.damped + e);
-        const float dd2 = a.damped2 ? __ldg(a.damped2 + e) : 0.f;
+        const float dd = __ldg(a.damped + e) * 4294967296.0f;
+        const float dd2 = a.damped2 ? __ldg(a.damped2 + e) * 4294967296.0f : 0.f;
         for (int s = 0; s < a.nSym; ++s) {
             const PlaneD& pl = a.planesD[p0 + s];
             // position of the pixel in voxel units: e1/e2 carry pixel-per-voxel, so p = (j*e1 + ip*e2) * (Z/P)^2
@@ -960,37 +960,54 @@ __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ 
             const double py = (j * pl.e1[1] + ip * pl.e2[1]) * sc;
             const double pz = (j * pl.e1[2] + ip * pl.e2[2]) * sc;
             const int x0 = (int)ceil(px - r), y0 = (int)ceil(py - r), z0 = (int)ceil(pz - r);
-            auto process = [&](int cx, int cy3, int cz3) {
-                const int ux = x0 + cx, uy = y0 + cy3, uz = z0 + cz3;
-                const double dx = ux - px, dy = uy - py, dz = uz - pz;
-                const double dist2 = dx * dx + dy * dy + dz * dz;
-                if (dist2 > r2) return;
-                const int ti = (int)(dist2 * a.iDeltaD + 0.5);                 // RF.cpp:725
-                const double tw = (double)__ldg(a.blobTable + ti);
-                const unsigned long long q = (unsigned long long)__double2ll_rn(tw * (double)dd * kFixedScale);
-                const unsigned long long q2 = (unsigned long long)__double2ll_rn(tw * (double)dd2 * kFixedScale);
-                const int wx = wrap1(ux), wy = wrap1(uy), wz = wrap1(uz);
-                // original at u
-                if (wx <= Z / 2) {
-                    const int cy = wy <= Z / 2 ? wy : wy - Z, cz = wz <= Z / 2 ? wz : wz - Z;
-                    const int64_t o = d_blocked_index(geo, wx, cy, cz);
-                    if (q) atomicAdd(a.D + o, q);
-                    if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
-                }
-                // Hermitian mirror at -u
-                const int sx = wx ? Z - wx : 0, sy = wy ? Z - wy : 0, sz = wz ? Z - wz : 0;
-                const int cy = sy <= Z / 2 ? sy : sy - Z, cz = sz <= Z / 2 ? sz : sz - Z;
-                const bool mirr = wx > Z / 2;                                       // cond_mirr(-u)
-                if (sx <= Z / 2 && (mirr || (sx == 0 && cy <= geo.yHalf))) {
-                    const int64_t o = d_blocked_index(geo, sx, cy, cz);
-                    if (q) atomicAdd(a.D + o, q);
-                    if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
-                }
-            };
+            const float fx = (float)((double)x0 - px), fy = (float)((double)y0 - py), fz = (float)((double)z0 - pz);
+            for (int g0 = 0; g0 < E3; g0 += 64) {
+                bool acc[2];
+                uint32_t pk[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (lane + 32 * i < E3) process(ox[i], oy[i], oz[i]);
-            for (int c = lane + 128; c < E3; c += 32) process(c % E, (c / E) % E, c / (E * E));
+                for (int i = 0; i < 2; ++i) {
+                    const int c = g0 + 32 * i + lane;
+                    int cx, cy, cz;
+                    if (E == 4) { cx = c & 3; cy = (c >> 2) & 3; cz = c >> 4; }
+                    else { cx = c % E; cy = (c / E) % E; cz = c / (E * E); }
+                    const float dx = fx + (float)cx, dy = fy + (float)cy, dz = fz + (float)cz;
+                    acc[i] = c < E3 && dx * dx + dy * dy + dz * dz <= r2F;
+                    pk[i] = (uint32_t)cx | ((uint32_t)cy << 8) | ((uint32_t)cz << 16);
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, acc[0]), m1 = __ballot_sync(0xffffffffu, acc[1]);
+                const int n0 = __popc(m0), n = n0 + __popc(m1);
+                if (acc[0]) sList[warp][__popc(m0 & ltMask)] = pk[0];
+                if (acc[1]) sList[warp][n0 + __popc(m1 & ltMask)] = pk[1];
+                __syncwarp();
+                for (int k = lane; k < n; k += 32) {
+                    const uint32_t q3 = sList[warp][k];
+                    const int cx = q3 & 255, cy = (q3 >> 8) & 255, cz = q3 >> 16;
+                    const float dx = fx + (float)cx, dy = fy + (float)cy, dz = fz + (float)cz;
+                    const float dist2 = dx * dx + dy * dy + dz * dz;
+                    const int ti = (int)(dist2 * iDeltaF + 0.5f);                     // RF.cpp:725
+                    const float tw = __ldg(a.blobTable + ti);
+                    const unsigned long long q = (unsigned long long)__float2ll_rn(tw * dd);      // 2^32 fixed point
+                    const unsigned long long q2 = (unsigned long long)__float2ll_rn(tw * dd2);
+                    const int wx = wrap1(x0 + cx), wy = wrap1(y0 + cy), wz = wrap1(z0 + cz);
+                    // original at u
+                    if (wx <= Z / 2) {
+                        const int oy = wy <= Z / 2 ? wy : wy - Z, oz = wz <= Z / 2 ? wz : wz - Z;
+                        const int64_t o = d_blocked_index(geo, wx, oy, oz);
+                        if (q) atomicAdd(a.D + o, q);
+                        if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
+                    }
+                    // Hermitian mirror at -u
+                    const int sx = wx ? Z - wx : 0, sy = wy ? Z - wy : 0, sz = wz ? Z - wz : 0;
+                    const int my = sy <= Z / 2 ? sy : sy - Z, mz = sz <= Z / 2 ? sz : sz - Z;
+                    const bool mirr = wx > Z / 2;                                       // cond_mirr(-u)
+                    if (sx <= Z / 2 && (mirr || (sx == 0 && my <= geo.yHalf))) {
+                        const int64_t o = d_blocked_index(geo, sx, my, mz);
+                        if (q) atomicAdd(a.D + o, q);
+                        if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
+                    }
+                }
+                __syncwarp();
+            }
         }
       }
     }
