@@ -225,11 +225,14 @@ __device__ __forceinline__ bool d_pixel_valid(const int* __restrict__ jmax, cons
     return ip >= sp.iLo && ip <= sp.iHi && j <= jmax[ip - sp.iLo];
 }
 
-// Columns per CTA of K1c: 8 for P <= 512, 4 for P = 1024 (thread limit).
+// Columns per CTA of K1c: 8 for P <= 256, 4 for P = 1024 (thread limit) and for P = 512, where a CTA of 4 x 64 threads at
+// <= 128 registers lets TWO CTAs share an SM: the FFT phase of one (shared-memory queue bound) overlaps the slice phase
+// of the other (ALU / latency bound).  Measured: 7.77 ms per 4096 particles with 8 columns and one CTA per SM, 7.41 ms
+// with 4 columns and two (profiles/r2b_ab_k1c.txt).
 #ifndef RF_K1C_COLS
-#define RF_K1C_COLS 8
+#define RF_K1C_COLS 4          // columns per CTA at P = 512
 #endif
-template <int P> constexpr int kColsPerCta = (P >= 1024) ? 4 : RF_K1C_COLS;
+template <int P> constexpr int kColsPerCta = (P >= 1024) ? 4 : (P == 512 ? RF_K1C_COLS : 8);
 
 // grid (ceil((R+2) / NC), nImg), block (NC + halo) * P/8 threads: columns kx = NC*blockIdx.x .. +NC-1.  A slice entry is
 // a pixel PAIR, E(r, j-1) = (p(r,j-1), p(r,j)) (and, for the few columns next to j = 0 that the half-plane format keeps on
@@ -246,10 +249,10 @@ constexpr int kK1cHalo = 1;
 constexpr int kK1cHalo = 0;
 #endif
 #ifndef RF_K1C_CTAS
-#define RF_K1C_CTAS 1          // CTAs per SM the register budget of K1c is sized for (P <= 512)
+#define RF_K1C_CTAS 2          // CTAs per SM the register budget of K1c is sized for at P = 512
 #endif
 template <int P>
-__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P <= 512) ? RF_K1C_CTAS : 1) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
+__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512) ? RF_K1C_CTAS : 1) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
     constexpr int NC = kColsPerCta<P>, NS = NC + kK1cHalo;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float2* W = reinterpret_cast<float2*>(smemRaw);
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P <= 512
     for (int i = tid; i <= sp.iHi - sp.iLo; i += NT) sJmax[i] = __ldg(a.s.jmax + i);
     if (sp.useCtf && tid < (int)(sizeof(CtfConsts) / 8))
         reinterpret_cast<double*>(&sCtf)[tid] = reinterpret_cast<const double*>(a.s.ctfs + img)[tid];
-    if (sp.useCtf && tid == 32) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
+    if (sp.useCtf && tid == NT - 1) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
     float2* buf = bufs + seq * kFftBuf<P>;
     const int j0 = blockIdx.x * NC;                   // first own column; sequence 0 transforms column j0 - 1
     const int kx = j0 + seq - kK1cHalo;

@@ -35,6 +35,9 @@ namespace rfb200 {
 #ifndef RF_STICK_WARPS
 #define RF_STICK_WARPS 16
 #endif
+#ifndef RF_STICK_LANEMAP
+#define RF_STICK_LANEMAP 1     // lane <-> (column, depth parity) map of the gather, see k_gather_sticks (measured: 0: 29.62, 1: 29.27, 2: 29.43 ms)
+#endif
 constexpr int kStickWarps = RF_STICK_WARPS;
 constexpr int kStickThreads = kStickWarps * 32;
 constexpr size_t kStickSmem = (size_t)kStickWarps * kStickL * kStickCols * (sizeof(float2) + sizeof(float));
@@ -464,6 +467,16 @@ __device__ __forceinline__ StickStep d_step(const StickConsts& c, const StickTas
     return q;
 }
 
+// Slot of (depth tau, column col) in the warp's complex accumulators.  With lane maps that put both lanes of a column
+// into the same half warp the two depth parities of a column must sit in different banks.
+__device__ __forceinline__ int d_accv_slot(int tau, int col) {
+#if RF_STICK_LANEMAP != 0
+    return (tau >> 1) * (2 * kStickCols) + 2 * col + (tau & 1);
+#else
+    return tau * kStickCols + col;
+#endif
+}
+
 // Walk the columns of one task, two depths per column and iteration.  kChecked = false: every step of every
 // active lane is known to be in bounds, on one side of column 0 and to need no multiplicity handling (both ends of
 // each column were tested; the conditions are convex along it).
@@ -491,11 +504,11 @@ __device__ __forceinline__ uint32_t d_task_run(const StickConsts& c, const Stick
                 d_stick_window2<K, true, kFlags>(sl, off, (unsigned)c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
             else
                 d_stick_window2<K, false, kFlags>(sl, off, (unsigned)c.pitch, da0, db0, h2s, c.kI, c.sMax, c.tblAdj, jc, ic, rimTab, accRe, accIm, accWt);
-            const int o = tau * kStickCols + col;
-            float2 v = accV[o];
+            const int o = tau * kStickCols + col, ov = d_accv_slot(tau, col);
+            float2 v = accV[ov];
             v.x += accRe;
             v.y = fmaf(q.sg, accIm, v.y);
-            accV[o] = v;
+            accV[ov] = v;
             accW[o] = fmaf(weight, accWt, accW[o]);
             if (kChecked) touched |= 1u << (tau >> 1);
         }
@@ -600,8 +613,17 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
     const int lo = geo.lo, hi = geo.hi;
     const float reach2 = geo.reach * geo.reach + 1.0f;
     const float rSlab = geo.r + 1e-3f;
-    const int col = lane & (kStickCols - 1), par = lane >> 4;       // two lanes per column: even / odd depth
-    const int la = col & (kStickA - 1), lb = col / kStickA;
+    // two lanes per column: even / odd depth.  Which 8 lanes form a quarter warp matters: a 128-bit warp load is served
+    // in four quarter-warp passes, each costing one L1 tag request per cache line its 8 lanes touch (measured 1.0 - 1.5).
+#if RF_STICK_LANEMAP == 1      // quarter = 2 x 2 columns x both depths
+    const int la = (lane & 1) | (((lane >> 3) & 1) << 1), lb = ((lane >> 1) & 1) | (((lane >> 4) & 1) << 1), par = (lane >> 2) & 1;
+#elif RF_STICK_LANEMAP == 2    // quarter = 4 columns along a x both depths
+    const int la = lane & 3, par = (lane >> 2) & 1, lb = lane >> 3;
+#else                          // quarter = 4 x 2 columns of one depth parity
+    const int la = lane & 3, lb = (lane >> 2) & 3, par = lane >> 4;
+#endif
+    static_assert(kStickA == 4 && kStickB == 4, "lane maps are written for 4 x 4 columns");
+    const int col = la + kStickA * lb;
     const float laf = (float)la, lbf = (float)lb;
     const int offA = (cls == 0) ? lo : 0, offB = lo, offD = (cls == 0) ? 0 : lo;
     // culling: half extents of the stick's lattice box around its centre, in (a,b,d) order
@@ -763,8 +785,8 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
 #pragma unroll
                     for (int ba = 0; ba < nBa; ++ba) {
                         const int av = ba * 4 + da, bv = bb * spanB + db, tau = bt * spanT + dt;
-                        const int o = tau * kStickCols + av + kStickA * bv;
-                        const float2 v = accV[o];
+                        const int o = tau * kStickCols + av + kStickA * bv, ov = d_accv_slot(tau, av + kStickA * bv);
+                        const float2 v = accV[ov];
                         const float w = accW[o];
                         if (w != 0.f || v.x != 0.f || v.y != 0.f) {
                             int X, Y, Zc;   // stored-offset coordinates
@@ -776,7 +798,7 @@ __global__ void RF_STICK_BOUNDS k_gather_sticks(const __grid_constant__ StickLau
                             d_red_add2(a.Vb + g, v.x, v.y);
                             d_red_add(a.Wb + g, w);
                             if (a.Wb2) d_red_add(a.Wb2 + g, w);
-                            accV[o] = make_float2(0.f, 0.f);
+                            accV[ov] = make_float2(0.f, 0.f);
                             accW[o] = 0.f;
                         }
                     }
