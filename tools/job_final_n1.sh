@@ -8,7 +8,7 @@ smi=$!
 python bench.py > $o/${tag}_bench_n1_final.json 2> $o/${tag}_bench_n1_final.err
 kill $smi
 tail -c 600 $o/${tag}_bench_n1_final.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $o/${tag}_launches_final.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 800 --csv --log-file $o/${tag}_launches_final.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $o/${tag}_bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_gather_sticks|k_fft_cols_slices|k_fft_rows|k_damped_scatter|k_edge2' -s 21 -c 8 \
     -o $o/${tag}_final_full python bench.py --steps 1 --warmup 3 --batch 720 --no-cpu-baseline --no-e2e --no-extras > $o/${tag}_ncu_full.log 2>&1

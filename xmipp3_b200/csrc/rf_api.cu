@@ -363,8 +363,18 @@ int launch_sticks(rfb200_handle h, const StickLaunch& a, int grid) {
     return fail(h, RFB200_ERR_ARG, "blob radius / padding ratio gives an unsupported interpolation window");
 }
 
+template <int P, int kCtf>
+int launch_k1c(rfb200_handle h, const FftColsArgs& ca, int n, int threadsC, size_t smemC) {
+    constexpr int NC = kColsPerCta<P>;
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P, kCtf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P, kCtf>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    k_fft_cols_slices<P, kCtf><<<dim3((h->geo.R + 2 + NC - 1) / NC, n), threadsC, smemC, h->compute>>>(ca);
+    RF_CUDA(h, cudaGetLastError());
+    return RFB200_OK;
+}
+// ctfMode: 0 = no CTF, 1 = every image of the chunk takes the fixed-point phase path, 2 = general (envelope / phase plate)
 template <int P>
-int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& ca, int n) {
+int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& ca, int n, int ctfMode) {
     const Geometry& g = h->geo;
     const int threads = kFftSeqs * P / 8;
     const size_t smem = sizeof(float2) * (P + kFftSeqs * kFftBuf<P>);
@@ -372,9 +382,7 @@ int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs
     const int threadsC = (NC + kK1cHalo) * P / 8;
     const size_t smemC = sizeof(float2) * (P + (NC + kK1cHalo) * kFftBuf<P> + (P + 2)) + sizeof(int) * (P + 2);   // twiddles, the sequences, halo values, cut-off table
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     RF_CUDA(h, cudaFuncSetAttribute(k_fft_rows<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    RF_CUDA(h, cudaFuncSetAttribute(k_fft_cols_slices<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     {
         StageTimer t(h, Stage::FFT2D, h->compute);
         k_fft_rows<P><<<dim3((g.N + 2 * kFftSeqs - 1) / (2 * kFftSeqs), n), threads, smem, h->compute>>>(ra);
@@ -384,19 +392,20 @@ int launch_fused_fft_p(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs
         StageTimer t(h, Stage::SLICE, h->compute);
         if (h->dDampedMask)
             RF_CUDA(h, cudaMemsetAsync(h->dDampedMask, 0, sizeof(uint32_t) * (size_t)n * (2 * g.R + 1) * ((g.R + 1 + 31) / 32), h->compute));
-        k_fft_cols_slices<P><<<dim3((g.R + 2 + NC - 1) / NC, n), threadsC, smemC, h->compute>>>(ca);
-        RF_CUDA(h, cudaGetLastError());
+        const int rck = ctfMode == 0 ? launch_k1c<P, 0>(h, ca, n, threadsC, smemC)
+                      : ctfMode == 1 ? launch_k1c<P, 1>(h, ca, n, threadsC, smemC) : launch_k1c<P, 2>(h, ca, n, threadsC, smemC);
+        if (rck) return rck;
     }
     h->nKernelLaunches += 2;
     return RFB200_OK;
 }
-int launch_fused_fft(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& ca, int n) {
+int launch_fused_fft(rfb200_handle h, const FftRowsArgs& ra, const FftColsArgs& ca, int n, int ctfMode) {
     switch (h->geo.P) {
-        case 64: return launch_fused_fft_p<64>(h, ra, ca, n);
-        case 128: return launch_fused_fft_p<128>(h, ra, ca, n);
-        case 256: return launch_fused_fft_p<256>(h, ra, ca, n);
-        case 512: return launch_fused_fft_p<512>(h, ra, ca, n);
-        case 1024: return launch_fused_fft_p<1024>(h, ra, ca, n);
+        case 64: return launch_fused_fft_p<64>(h, ra, ca, n, ctfMode);
+        case 128: return launch_fused_fft_p<128>(h, ra, ca, n, ctfMode);
+        case 256: return launch_fused_fft_p<256>(h, ra, ca, n, ctfMode);
+        case 512: return launch_fused_fft_p<512>(h, ra, ca, n, ctfMode);
+        case 1024: return launch_fused_fft_p<1024>(h, ra, ca, n, ctfMode);
     }
     return fail(h, RFB200_ERR_STATE, "fused FFT chain selected for an unsupported padded size");
 }
@@ -490,7 +499,7 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
     }
     if (!rcf) {
         // stable sort of the chunk's planes by class (axis dominating the normal), components permuted to the (a,b,d)
-        // order of the class; every class is then cut into launches of <= kLaunchPlanes planes of (nearly) equal size
+        // order of the class; every class is then cut into launches of <= kLaunchPlanes planes
         int start[4] = {0, 0, 0, 0};
         for (int k = 0; k < np; ++k) start[host::plane_class(s.planesD[k]) + 1]++;
         for (int c = 0; c < 3; ++c) start[c + 1] += start[c];
@@ -505,12 +514,14 @@ int upload_chunk_params(rfb200_handle h, const rfb200_particle* meta, int n, Par
         for (int c = 0; c < 3; ++c) {
             const int nc = start[c + 1] - start[c];
             if (!nc) continue;
-            const int nl = (nc + kLaunchPlanes - 1) / kLaunchPlanes, base = nc / nl, rem = nc % nl;
+            // full launches first, the remainder last: every launch reads and writes all the sticks its planes touch, so an
+            // overflow of a few planes is cheap as a small launch (few sticks) and expensive as two half-full ones
             int at = start[c];
-            for (int l = 0; l < nl; ++l) {
-                const int cnt = base + (l < rem ? 1 : 0);
+            for (int left = nc; left > 0;) {
+                const int cnt = std::min(left, kLaunchPlanes);
                 s.launches.push_back({c, at, cnt});
                 at += cnt;
+                left -= cnt;
             }
         }
         for (size_t g = 0; g < s.launches.size(); ++g) {
@@ -730,7 +741,14 @@ int process_chunk(rfb200_handle h, const float* dRaw, const rfb200_particle* met
         ra.raw = dRaw; ra.ip = h->dImg; ra.twiddle = h->dTwiddle; ra.T = h->dFft; ra.N = g.N;
         FftColsArgs ca{};
         ca.s = make_slice_args(h); ca.twiddle = h->dTwiddle; ca.T = h->dFft; ca.N = g.N;
-        rc = launch_fused_fft(h, ra, ca, n);
+        // which CTF code the slice pass needs: none, the fixed-point phase path only, or the general one
+        int ctfMode = 0;
+        if (h->cfg.use_ctf) {
+            ctfMode = ca.s.sp.a >= 1e-6f ? 1 : 2;
+            for (int i = 0; i < n && ctfMode == 1; ++i)
+                if (slot->ctf[i].has_envelope || slot->ctf[i].has_vpp) ctfMode = 2;
+        }
+        rc = launch_fused_fft(h, ra, ca, n, ctfMode);
         if (rc) return rc;
     } else {
     rc = pad_and_fft(h, dRaw, n, anySpline);

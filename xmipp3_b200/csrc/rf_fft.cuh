@@ -209,11 +209,14 @@ struct FftColsArgs {
 };
 
 // value and weights of pixel (j, ip) from its transform value F (as d_pixel_contrib2)
+// kCtf: 0 = the run has no CTF, 1 = every image of the launch takes the fixed-point phase path, 2 = general
+template <int kCtf>
 __device__ __forceinline__ float4 d_contrib_from_F(float2 F, bool valid, const SliceParams& sp, const CtfConsts* ctf, const CtfFloat& cf, float weight, int j, int ip) {
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!valid) return out;
     float wc = 1.f, wm = 1.f;
-    if (sp.useCtf) d_ctf_weights(*ctf, cf, sp, j, ip, wc, wm);
+    if (kCtf == 1) d_ctf_weights<false>(*ctf, cf, sp, j, ip, wc, wm);
+    if (kCtf == 2) d_ctf_weights<true>(*ctf, cf, sp, j, ip, wc, wm);
     const float s = weight * wm * wc * sp.invP2;
     out.x = F.x * s;
     out.y = F.y * s;
@@ -249,10 +252,10 @@ constexpr int kK1cHalo = 1;
 constexpr int kK1cHalo = 0;
 #endif
 #ifndef RF_K1C_CTAS
-#define RF_K1C_CTAS 2          // CTAs per SM the register budget of K1c is sized for at P = 512
+#define RF_K1C_CTAS 4          // CTAs per SM the register budget of K1c is sized for at P = 512 (2 with the general CTF path)
 #endif
-template <int P>
-__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512) ? RF_K1C_CTAS : 1) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
+template <int P, int kCtf>
+__global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512) ? (kCtf == 2 ? 2 : RF_K1C_CTAS) : 1) k_fft_cols_slices(const __grid_constant__ FftColsArgs a) {
     constexpr int NC = kColsPerCta<P>, NS = NC + kK1cHalo;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float2* W = reinterpret_cast<float2*>(smemRaw);
@@ -267,9 +270,9 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512
     const int tid = threadIdx.x, seq = tid / TPS, t = tid % TPS;
     for (int i = tid; i < P; i += NT) W[i] = __ldg(a.twiddle + i);
     for (int i = tid; i <= sp.iHi - sp.iLo; i += NT) sJmax[i] = __ldg(a.s.jmax + i);
-    if (sp.useCtf && tid < (int)(sizeof(CtfConsts) / 8))
+    if (kCtf && tid < (int)(sizeof(CtfConsts) / 8))
         reinterpret_cast<double*>(&sCtf)[tid] = reinterpret_cast<const double*>(a.s.ctfs + img)[tid];
-    if (sp.useCtf && tid == NT - 1) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
+    if (kCtf && tid == NT - 1) d_ctf_prepare(a.s.ctfs[img], sp, sCtfF);
     float2* buf = bufs + seq * kFftBuf<P>;
     const int j0 = blockIdx.x * NC;                   // first own column; sequence 0 transforms column j0 - 1
     const int kx = j0 + seq - kK1cHalo;
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512
     fft_block<P>(buf, W, t, seq);
     if (kK1cHalo) __syncthreads();   // the halo pass reads sequence 0
 
-    const CtfConsts* ctf = sp.useCtf ? &sCtf : nullptr;
+    const CtfConsts* ctf = kCtf ? &sCtf : nullptr;
     const float weight = a.s.ip[img].weight;
     // ---- halo pass: the slice value (flag in the LSB of re) of pixel (j0 - 1, ip) for every row; its weights, mask bits
     // and column-0 extras belong to the CTA that owns the column
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512
         for (int r = tid; r < nRows; r += NT) {
             const int ipx = r - sp.R, jh = j0 - 1;
             const float2 F = bufs[fft_phys(ipx & (P - 1))];
-            const float4 cc = d_contrib_from_F(F, d_pixel_valid(sJmax, sp, jh, ipx), sp, ctf, sCtfF, weight, jh, ipx);
+            const float4 cc = d_contrib_from_F<kCtf>(F, d_pixel_valid(sJmax, sp, jh, ipx), sp, ctf, sCtfF, weight, jh, ipx);
             sHalo[r] = make_float2(d_set_flag(cc.x, cc.w != 0.f), cc.y);
         }
     }
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512
         if (own) {
             const float2* b = bufs + (c + kK1cHalo) * kFftBuf<P>;
             const float2 F = b[fft_phys(ipx & (P - 1))];
-            float4 cc = d_contrib_from_F(F, d_pixel_valid(sJmax, sp, j, ipx), sp, ctf, sCtfF, weight, j, ipx);
+            float4 cc = d_contrib_from_F<kCtf>(F, d_pixel_valid(sJmax, sp, j, ipx), sp, ctf, sCtfF, weight, j, ipx);
             flag = cc.w != 0.f;
             wDamped = cc.z;
             wUnmod = (cc.z != 0.f || flag) ? weight : 0.f;
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512
             } else {
                 // column 0: original (0,ip) plus the mirror of original (0,-ip) (see k_make_slices2)
                 const float2 Fm = b[fft_phys((-ipx) & (P - 1))];
-                float4 m = d_contrib_from_F(Fm, d_pixel_valid(sJmax, sp, 0, -ipx), sp, ctf, sCtfF, weight, 0, -ipx);
+                float4 m = d_contrib_from_F<kCtf>(Fm, d_pixel_valid(sJmax, sp, 0, -ipx), sp, ctf, sCtfF, weight, 0, -ipx);
                 flag = flag || (m.w != 0.f);
                 pv = make_float2(d_set_flag(cc.x + m.x, flag), cc.y - m.y);
                 a.s.col0[(size_t)img * sp.side + (ipx + sp.Rp)] = make_float2(d_set_flag(cc.x, flag), cc.y);

@@ -273,9 +273,12 @@ __device__ __forceinline__ void d_sincos_quadrant(float x, int q, float& sn, flo
 // wCTF / wModulator of half-plane pixel (j, ip) — RF.cpp:600-625.  Fast path: exact fixed-point phase (see CtfFloat).
 // General path (envelope or phase plate): the phase argument is formed in double from exact integer frequencies and
 // reduced to [-pi/4, pi/4] in double.  sin/cos, the amplitude and the minCTF rules run in FP32.
+// kGeneral = false: the caller guarantees f.fast (no image of the launch has envelope or phase-plate terms), and the
+// double-precision general path is not even compiled into the kernel (registers).
+template <bool kGeneral = true>
 __device__ __forceinline__ void d_ctf_weights(const CtfConsts& c, const CtfFloat& f, const SliceParams& sp, int j, int ip, float& wCTF, float& wMod) {
     float sn, cs, E = 1.0f;
-    if (f.fast) {
+    if (!kGeneral || f.fast) {
         const int jj = j * j, ii = ip * ip;
         typedef unsigned long long u64;                      // all products wrap modulo 2^64 = one turn
         const u64 r2 = (u64)(jj + ii);
