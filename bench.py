@@ -515,7 +515,9 @@ def main():
                 "frac_note": "algorithmic bytes per launch = particles x Npix x 8 B (slices) + 24 B x Nsphere (every launch reads and "
                              "writes the touched volume once, SURVEY 8d); launches with more planes amortise the second term, so "
                              "`achieved` falls when the kernel gets faster per particle by batching more planes per launch",
-                "bound_actual": "instruction issue + L1/shared-memory data pipe (ncu: l1_data_pipe); the contract's `bound` only admits hbm|tensor",
+                "bound_actual": "L1/shared-memory data pipe: about 75 wavefronts per warp step-iteration (42 tag requests of the window loads, 27 of "
+                                "the blob-table lookups, 5.5 of the stick accumulators) against about 60 issue cycles (profiles/r2b_gather_hot_loop.txt); "
+                                "the contract's `bound` only admits hbm|tensor",
                 "note": "the gather is bound by the L1/shared-memory data pipe (per-pair pixel and blob-table fetches), "
                         "not by HBM or FP32: see l1_data_pipe (ncu) and fp32"}
     fp32 = {"achieved": alg_flops / (g_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
