@@ -105,35 +105,47 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
     fft_seq_barrier<P>(seq);
 }
 
-// forward FFT (e^{-i...}, unnormalised) of the P points in buf, natural order in and out
+// First stage (radix 8, Ns = 1) with the inputs already in registers: thread t of the sequence holds points t + r P/8,
+// r = 0..7 - exactly what the kernels' load loops read, so the loaded values never make the round trip through shared
+// memory (8 stores, 8 loads and one barrier less per thread; the transforms are bound by the shared-memory queue).
 template <int P>
-__device__ __forceinline__ void fft_block(float2* buf, const float2* __restrict__ W, int t, int seq);
+__device__ __forceinline__ void fft_first_stage(float2* v, float2* buf, int t, int seq) {
+    float2 x[8];
+    dft_small<8>(v, x);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) buf[fft_phys(8 * t + r)] = x[r];
+    fft_seq_barrier<P>(seq);
+}
+
+// forward FFT (e^{-i...}, unnormalised) of P points, natural order; v[r] = point t + r P/8 on entry, result in buf
+template <int P>
+__device__ __forceinline__ void fft_block(float2* v, float2* buf, const float2* __restrict__ W, int t, int seq);
 template <>
-__device__ __forceinline__ void fft_block<64>(float2* buf, const float2* __restrict__ W, int t, int seq) {
-    fft_stage<64, 8, 1>(buf, W, t, seq);
+__device__ __forceinline__ void fft_block<64>(float2* v, float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_first_stage<64>(v, buf, t, seq);
     fft_stage<64, 8, 8>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<128>(float2* buf, const float2* __restrict__ W, int t, int seq) {
-    fft_stage<128, 8, 1>(buf, W, t, seq);
+__device__ __forceinline__ void fft_block<128>(float2* v, float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_first_stage<128>(v, buf, t, seq);
     fft_stage<128, 8, 8>(buf, W, t, seq);
     fft_stage<128, 2, 64>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<256>(float2* buf, const float2* __restrict__ W, int t, int seq) {
-    fft_stage<256, 8, 1>(buf, W, t, seq);
+__device__ __forceinline__ void fft_block<256>(float2* v, float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_first_stage<256>(v, buf, t, seq);
     fft_stage<256, 8, 8>(buf, W, t, seq);
     fft_stage<256, 4, 64>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<512>(float2* buf, const float2* __restrict__ W, int t, int seq) {
-    fft_stage<512, 8, 1>(buf, W, t, seq);
+__device__ __forceinline__ void fft_block<512>(float2* v, float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_first_stage<512>(v, buf, t, seq);
     fft_stage<512, 8, 8>(buf, W, t, seq);
     fft_stage<512, 8, 64>(buf, W, t, seq);
 }
 template <>
-__device__ __forceinline__ void fft_block<1024>(float2* buf, const float2* __restrict__ W, int t, int seq) {
-    fft_stage<1024, 8, 1>(buf, W, t, seq);
+__device__ __forceinline__ void fft_block<1024>(float2* v, float2* buf, const float2* __restrict__ W, int t, int seq) {
+    fft_first_stage<1024>(v, buf, t, seq);
     fft_stage<1024, 8, 8>(buf, W, t, seq);
     fft_stage<1024, 8, 64>(buf, W, t, seq);
     fft_stage<1024, 2, 512>(buf, W, t, seq);
@@ -170,6 +182,7 @@ __global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_rows(const __grid_const
     const int rowA = blockIdx.x * 2 * kFftSeqs + 2 * seq, rowB = rowA + 1;
     const float* ra = rowA < N ? src + (size_t)d_wrap(rowA + q.my, N) * N : nullptr;
     const float* rb = rowB < N ? src + (size_t)d_wrap(rowB + q.my, N) * N : nullptr;
+    float2 v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int x = t + TPS * e;                        // padded column
@@ -180,10 +193,10 @@ __global__ void __launch_bounds__(kFftSeqs* P / 8) k_fft_rows(const __grid_const
             if (ra) z.x = __ldg(ra + sj);
             if (rb) z.y = __ldg(rb + sj);
         }
-        buf[fft_phys(x)] = z;
+        v[e] = z;
     }
-    __syncthreads();
-    fft_block<P>(buf, W, t, seq);
+    __syncthreads();              // twiddle table
+    fft_block<P>(v, buf, W, t, seq);
     __syncthreads();              // the untangling reads every sequence of the CTA
     // untangle the two real transforms and write T[kx][row], 16 consecutive rows per kx
     const int nOut = Xh * 2 * kFftSeqs;
@@ -277,16 +290,17 @@ __global__ void __launch_bounds__((kColsPerCta<P> + kK1cHalo) * P / 8, (P == 512
     const int j0 = blockIdx.x * NC;                   // first own column; sequence 0 transforms column j0 - 1
     const int kx = j0 + seq - kK1cHalo;
     const float2* col = (kx >= 0 && kx <= sp.R) ? a.T + ((size_t)img * Xh + kx) * N : nullptr;
+    float2 v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int y = t + TPS * e;                        // padded row
         const int ii = (y + N / 2) & (P - 1);             // destination row before padding
         float2 z = make_float2(0.f, 0.f);
         if (col && ii < N) z = __ldg(col + ii);
-        buf[fft_phys(y)] = z;
+        v[e] = z;
     }
-    __syncthreads();
-    fft_block<P>(buf, W, t, seq);
+    __syncthreads();              // twiddle, cut-off and CTF tables
+    fft_block<P>(v, buf, W, t, seq);
     if (kK1cHalo) __syncthreads();   // the halo pass reads sequence 0
 
     const CtfConsts* ctf = kCtf ? &sCtf : nullptr;
