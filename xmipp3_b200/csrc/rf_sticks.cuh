@@ -1011,24 +1011,21 @@ __global__ void __launch_bounds__(256) k_damped_scatter(const __grid_constant__ 
                     const unsigned long long q = (unsigned long long)__float2ll_rn(tw * dd);      // 2^32 fixed point
                     const unsigned long long q2 = (unsigned long long)__float2ll_rn(tw * dd2);
                     const int wx = wrap1(x0 + cx), wy = wrap1(y0 + cy), wz = wrap1(z0 + cz);
-                    // The original lands at u when u is in the stored half (wx <= Z/2), its Hermitian mirror at -u when it is
-                    // not: one target, except on the plane wx = 0, which holds both (second target below).
-                    const bool neg = wx > Z / 2;
-                    const int tx = neg ? Z - wx : wx;
-                    const int ty = neg ? (wy ? Z - wy : 0) : wy, tz = neg ? (wz ? Z - wz : 0) : wz;
-                    {
-                        const int64_t o = d_blocked_index(geo, tx, ty <= Z / 2 ? ty : ty - Z, tz <= Z / 2 ? tz : tz - Z);
+                    // original at u
+                    if (wx <= Z / 2) {
+                        const int oy = wy <= Z / 2 ? wy : wy - Z, oz = wz <= Z / 2 ? wz : wz - Z;
+                        const int64_t o = d_blocked_index(geo, wx, oy, oz);
                         if (q) atomicAdd(a.D + o, q);
                         if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
                     }
-                    if (wx == 0) {                                                      // mirror of a point of the x = 0 plane
-                        const int sy = wy ? Z - wy : 0, sz = wz ? Z - wz : 0;
-                        const int my = sy <= Z / 2 ? sy : sy - Z, mz = sz <= Z / 2 ? sz : sz - Z;
-                        if (my <= geo.yHalf) {
-                            const int64_t o = d_blocked_index(geo, 0, my, mz);
-                            if (q) atomicAdd(a.D + o, q);
-                            if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
-                        }
+                    // Hermitian mirror at -u
+                    const int sx = wx ? Z - wx : 0, sy = wy ? Z - wy : 0, sz = wz ? Z - wz : 0;
+                    const int my = sy <= Z / 2 ? sy : sy - Z, mz = sz <= Z / 2 ? sz : sz - Z;
+                    const bool mirr = wx > Z / 2;                                       // cond_mirr(-u)
+                    if (sx <= Z / 2 && (mirr || (sx == 0 && my <= geo.yHalf))) {
+                        const int64_t o = d_blocked_index(geo, sx, my, mz);
+                        if (q) atomicAdd(a.D + o, q);
+                        if (a.D2 && q2) atomicAdd(a.D2 + o, q2);
                     }
                 }
                 __syncwarp();
