@@ -269,7 +269,7 @@ def measure_other_config(cfg, dev, local, rank, world, max_over_ranks, barrier_a
             "stage_ms_per_step": {k: tm[k] / K for k in ("preprocess_ms", "fft2d_ms", "slice_ms", "gather_ms", "edge_ms")}}
 
 
-def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_over_ranks, vol_ptr):
+def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_over_ranks, vol_ptr, p2p=False):
     """Config 3 AS STATED: `total` particles in all, sharded over the ranks, end to end (pinned host batches -> H2D ->
     insertion -> one NCCL reduce -> normalisation + 3-D inverse FFT + D2H of the map on rank 0).  The two pinned batches
     are cycled: the bytes moved and the work done are those of `total` distinct particles."""
@@ -287,7 +287,7 @@ def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_ov
         done += n
         i += 1
     if world > 1:
-        r.reduce(0)
+        do_reduce(r, p2p)
     if rank == 0:
         r.finalize_into(vol_ptr)
     else:
@@ -296,7 +296,43 @@ def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_ov
     dt = max_over_ranks(time.perf_counter() - t0)
     return {"workload": "config[2] as stated: %d particles %dx%d with CTF in total, sharded over %d GPU(s)" % (total, box, box, world),
             "scaling": "strong", "particles_total": total, "particles_per_gpu": int(mine), "seconds": dt, "value": total / dt, "unit": UNIT,
-            "includes": "H2D from pinned host memory, insertion, NCCL reduce (N>1), normalise + 3-D IFFT + D2H of the map"}
+            "includes": "H2D from pinned host memory, insertion, reduce onto rank 0 (N>1: %s), normalise + 3-D IFFT + D2H of the map" % ("peer-memory kernel over NVLink" if p2p else "ncclReduce")}
+
+
+def setup_p2p(r, dev, world, rank):
+    """Peer-memory reduce: every rank exports the IPC handles of its accumulators, all ranks import all others.  True when
+    every rank succeeded (then rfb200_reduce_p2p replaces the two ncclReduce calls); RFB200_BENCH_REDUCE=nccl disables it."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1 or os.environ.get("RFB200_BENCH_REDUCE", "p2p") == "nccl":
+        return False
+    ok = 1
+    try:
+        blob = r.ipc_export()
+    except Exception:
+        blob, ok = None, 0
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob)
+    if ok and all(b is not None for b in blobs):
+        try:
+            for k, b in enumerate(blobs):
+                if k != rank:
+                    r.ipc_import(k, b)
+        except Exception as e:
+            print("bench.py: rank %d cannot map peer memory (%s); using the NCCL reduce" % (rank, e), file=sys.stderr)
+            ok = 0
+    else:
+        ok = 0
+    t = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def do_reduce(r, p2p):
+    if p2p:
+        r.reduce_p2p(0)
+    else:
+        r.reduce(0)
 
 
 def reduce_check(dev, local, rank, world):
@@ -314,12 +350,25 @@ def reduce_check(dev, local, rank, world):
     ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     r.nccl_init(ids[0], world, rank)
+    p2p = setup_p2p(r, dev, world, rank)
     img, p = data(rank)
     r.insert_device_ptr(img.data_ptr(), p)
     mine = r.weight_sum()
     t = torch.tensor([mine], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    r.reduce(0)
+    after_nccl = None
+    if p2p:
+        # both collectives on the same partial volumes: the NCCL reduce first (rank 0's accumulators then hold the sum, the
+        # others are unchanged), the result noted, rank 0 re-inserts its own particles into zeroed accumulators, then the
+        # peer-memory reduce, whose result is the one checked against the single-rank reconstruction below
+        r.reduce(0)
+        if rank == 0:
+            after_nccl = r.weight_sum()
+            r.reset()
+            r.insert_device_ptr(img.data_ptr(), p)
+        r.sync()
+        dist.barrier()
+    do_reduce(r, p2p)
     out = None
     if rank == 0:
         after = r.weight_sum()
@@ -331,7 +380,9 @@ def reduce_check(dev, local, rank, world):
         solo_sum = solo.weight_sum()
         ref = solo.finalize()
         solo.close()
-        out = {"ranks": world, "particles_per_rank": n, "weight_sum_after_reduce": after, "sum_of_rank_weight_sums": float(t.item()),
+        out = {"ranks": world, "particles_per_rank": n, "collective": "rfb200_reduce_p2p (peer memory over NVLink)" if p2p else "rfb200_reduce_nccl",
+               "weight_sum_after_nccl_reduce": after_nccl,
+               "weight_sum_after_reduce": after, "sum_of_rank_weight_sums": float(t.item()),
                "weight_sum_rel_err": abs(after - float(t.item())) / abs(float(t.item())),
                "weight_sum_one_rank_all_particles": solo_sum,
                "map_rel_l2_vs_one_rank": float(np.linalg.norm(vol - ref) / np.linalg.norm(ref))}
@@ -439,6 +490,7 @@ def main():
         ids = [Reconstructor.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         r.nccl_init(ids[0], world, rank)
+    p2p = setup_p2p(r, dev, world, rank) if world > 1 else False
 
     def barrier():
         if world > 1:
@@ -578,6 +630,8 @@ def main():
         r.weight_sum()
         if world > 1:
             r.reduce(0)          # warm-up of the communicator (connection set-up happens on the first collective)
+            if p2p:
+                r.reduce_p2p(0)  # and of the peer mappings
         vol_pinned = torch.empty((box, box, box), dtype=torch.float32, pin_memory=True) if rank == 0 else None
         if rank == 0:
             r.finalize_into(vol_pinned.data_ptr())      # creates the 3-D FFT plan and the finalisation buffers
@@ -604,7 +658,7 @@ def main():
         assert len(results) == K and all(b > a for a, b in zip(results, results[1:])), "per-step results must grow"
         t_ins = time.perf_counter()
         if world > 1:
-            r.reduce(0)
+            do_reduce(r, p2p)
             r.sync()
         t_red = time.perf_counter()
         vol = None
@@ -633,7 +687,20 @@ def main():
     headline = box == 256 and args.sym.lower() == "c1" and not args.no_ctf and not args.fast
     if not args.no_extras and not args.no_e2e and headline:
         vol_ptr = vol_pinned.data_ptr() if rank == 0 else 0
-        extra["strong_scaling"] = measure_strong_scaling(r, host, box, world, rank, args.strong_total, barrier, max_over_ranks, vol_ptr)
+        if world > 1:
+            # the two collectives side by side on the headline accumulators (content does not matter for the time)
+            cmp_ms = {}
+            for name, fn in (("nccl", lambda: r.reduce(0)),) + ((("p2p", lambda: r.reduce_p2p(0)),) if p2p else ()):
+                ts = []
+                for _ in range(3):
+                    barrier()
+                    tq = time.perf_counter()
+                    fn()
+                    r.sync()
+                    ts.append(max_over_ranks(time.perf_counter() - tq))
+                cmp_ms[name] = 1e3 * min(ts)
+            extra["reduce_ms"] = dict(cmp_ms, used="p2p" if p2p else "nccl", bytes_per_rank=int(12 * r.accumulator_ptrs()[2]))
+        extra["strong_scaling"] = measure_strong_scaling(r, host, box, world, rank, args.strong_total, barrier, max_over_ranks, vol_ptr, p2p)
     r.close()
     r = None
     del batches
@@ -686,7 +753,7 @@ def main():
             "config": {"workload": "config[2]: %dx%d Gaussian-phantom projections %s, padding 2, %s, blob 1.9/0/15, max_resolution 0.5%s" % (box, box, "without CTF" if args.no_ctf else "with CTF", args.sym.upper(), ", --fast arithmetic" if args.fast else ""),
                        "box": box, "padding": 2, "sym": args.sym.lower(), "insertions_per_particle": n_ops, "ctf": not args.no_ctf, "particles_per_step_per_gpu": B,
                        "l2": "inputs larger than L2: each step reads a %.2f GB batch, two batches alternate" % (B * box * box * 4 / 1e9),
-                       "parallelism": "particle sharding, %d rank(s), one ncclReduce of V and W before normalisation" % world,
+                       "parallelism": "particle sharding, %d rank(s), one reduce of V and W onto rank 0 before normalisation" % world,
                        "stage_ms_per_step": stage_ms},
             "clocks": cs, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "per_kernel_roofline": per_kernel, "fp32": fp32, "l1_data_pipe": l1_pipe, "cpu_baseline": cpu_baseline,
         }

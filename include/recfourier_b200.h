@@ -133,6 +133,19 @@ int rfb200_reset(rfb200_handle h);   /* zero the accumulators and the timings */
 int rfb200_nccl_unique_id(void* id128);
 int rfb200_nccl_init(rfb200_handle h, const void* id128, int32_t n_ranks, int32_t rank);
 int rfb200_reduce_nccl(rfb200_handle h, int32_t root);
+/* Peer-memory alternative to rfb200_reduce_nccl for the ranks of ONE node (NVLink / NVSwitch): every rank exports the
+ * CUDA IPC handles of its accumulators (rfb200_ipc_export fills RFB200_IPC_BYTES bytes), the host program hands every
+ * rank's blob to every other rank (rfb200_ipc_import, once per peer), and rfb200_reduce_p2p then runs ONE kernel per
+ * rank that reads its 1/n_ranks slice of V and W from the memory of all ranks, adds the copies in rank order and stores
+ * the sums into the root's accumulators - a reduce-scatter and a gather to the root in one pass, every link carrying
+ * 1/n_ranks of the data.  The communicator of rfb200_nccl_init is still required: two 4-byte all-reduces order the
+ * ranks before and after the kernel.  Same call discipline as rfb200_reduce_nccl (every rank calls it, same root);
+ * the accumulators of the other ranks are left unchanged.  Replaces the MPI_Reduce per row of
+ * mpi_reconstruct_fourier_gpu.cpp:250-268 like rfb200_reduce_nccl does. */
+#define RFB200_IPC_BYTES 256
+int rfb200_ipc_export(rfb200_handle h, void* out_blob);
+int rfb200_ipc_import(rfb200_handle h, int32_t rank, const void* peer_blob);
+int rfb200_reduce_p2p(rfb200_handle h, int32_t root);
 /* Raw device pointers of the blocked accumulators (for a host program that wants to run
  * its own collective on them): V = n_blocked float2, W = n_blocked float. */
 int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_blocked);

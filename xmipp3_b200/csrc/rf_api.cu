@@ -65,6 +65,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
@@ -81,6 +82,7 @@ void load_nccl() {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
     g_nccl.Reduce = (decltype(g_nccl.Reduce))dlsym(g_nccl.lib, "ncclReduce");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
     g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Reduce && g_nccl.CommDestroy;
@@ -156,6 +158,10 @@ struct rfb200_handle_s {
     ncclComm_t comm = nullptr;
 #endif
     int nRanks = 1, rank = 0;
+    // peer-memory reduce (rfb200_reduce_p2p): accumulators of the other ranks' handles, opened through CUDA IPC
+    struct Peer { float2* V = nullptr; float* W = nullptr; float* W2 = nullptr; bool open = false; };
+    std::vector<Peer> peers;
+    float* dBarrier = nullptr;      // 4 bytes for the stream-ordered rank barrier (a tiny all-reduce)
     // ---- stick gather
     float4* dSlices2 = nullptr;     // per image side x pitch entries (pixel(i,j), pixel(i,j+1))
     float2* dCol02 = nullptr;
@@ -823,6 +829,13 @@ void free_all(rfb200_handle h) {
         if (h->evH2D[i]) cudaEventDestroy(h->evH2D[i]);
         if (h->evRawFree[i]) cudaEventDestroy(h->evRawFree[i]);
     }
+    for (auto& p : h->peers) {
+        if (!p.open) continue;
+        cudaIpcCloseMemHandle(p.V);
+        cudaIpcCloseMemHandle(p.W);
+        if (p.W2) cudaIpcCloseMemHandle(p.W2);
+    }
+    if (h->dBarrier) cudaFree(h->dBarrier);
 #if RFB200_HAVE_NCCL_H
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
 #endif
@@ -1296,6 +1309,113 @@ int rfb200_reduce_nccl(rfb200_handle h, int32_t root) {
         if (r1 != ncclSuccess || r2 != ncclSuccess) return fail(h, RFB200_ERR_NCCL, "ncclReduce failed");
     }
     return RFB200_OK;
+#else
+    (void)root;
+    return h ? fail(h, RFB200_ERR_NCCL, "built without nccl.h") : RFB200_ERR_NCCL;
+#endif
+}
+
+// ---- peer-memory reduce
+namespace {
+struct IpcBlob {                      // RFB200_IPC_BYTES = 256
+    cudaIpcMemHandle_t V, W, W2;      // 3 x 64 bytes
+    int64_t nBlocked;
+    int32_t hasW2, device;
+    char pad[256 - 3 * 64 - 16];
+};
+static_assert(sizeof(IpcBlob) == 256, "IPC blob layout");
+
+int launch_p2p(rfb200_handle h, const P2PArgs& a) {
+    const long long n = a.hi - a.lo;
+    if (n <= 0) return RFB200_OK;
+    const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    switch (h->nRanks) {
+        case 2: k_reduce_p2p<2><<<grid, 256, 0, h->compute>>>(a, 2); break;
+        case 4: k_reduce_p2p<4><<<grid, 256, 0, h->compute>>>(a, 4); break;
+        case 8: k_reduce_p2p<8><<<grid, 256, 0, h->compute>>>(a, 8); break;
+        default: k_reduce_p2p<0><<<grid, 256, 0, h->compute>>>(a, h->nRanks); break;
+    }
+    RF_CUDA(h, cudaGetLastError());
+    h->nKernelLaunches += 1;
+    return RFB200_OK;
+}
+// stream-ordered barrier over the ranks of the communicator: a 4-byte all-reduce on the compute stream
+int rank_barrier(rfb200_handle h) {
+#if RFB200_HAVE_NCCL_H
+    if (!h->dBarrier) {
+        RF_CUDA(h, cudaMalloc(&h->dBarrier, 16));
+        RF_CUDA(h, cudaMemsetAsync(h->dBarrier, 0, 16, h->compute));
+    }
+    if (g_nccl.AllReduce(h->dBarrier, h->dBarrier, 1, ncclFloat, ncclSum, h->comm, h->compute) != ncclSuccess)
+        return fail(h, RFB200_ERR_NCCL, "ncclAllReduce (rank barrier) failed");
+    return RFB200_OK;
+#else
+    return fail(h, RFB200_ERR_NCCL, "built without nccl.h");
+#endif
+}
+}  // namespace
+
+int rfb200_ipc_export(rfb200_handle h, void* out256) {
+    if (!h || !out256) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    IpcBlob b;
+    std::memset(&b, 0, sizeof b);
+    RF_CUDA(h, cudaIpcGetMemHandle(&b.V, h->dVb));
+    RF_CUDA(h, cudaIpcGetMemHandle(&b.W, h->dWb));
+    if (h->dWb2) RF_CUDA(h, cudaIpcGetMemHandle(&b.W2, h->dWb2));
+    b.nBlocked = (int64_t)h->nBlocked;
+    b.hasW2 = h->dWb2 ? 1 : 0;
+    b.device = h->cfg.device;
+    std::memcpy(out256, &b, sizeof b);
+    return RFB200_OK;
+}
+
+int rfb200_ipc_import(rfb200_handle h, int32_t rank, const void* in256) {
+    if (!h || !in256 || rank < 0 || rank >= kMaxP2PRanks) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    IpcBlob b;
+    std::memcpy(&b, in256, sizeof b);
+    if (b.nBlocked != (int64_t)h->nBlocked || (b.hasW2 != 0) != (h->dWb2 != nullptr))
+        return fail(h, RFB200_ERR_ARG, "rfb200_ipc_import: the peer's handle has a different geometry");
+    if ((int)h->peers.size() <= rank) h->peers.resize(rank + 1);
+    rfb200_handle_s::Peer& p = h->peers[rank];
+    if (p.open) return fail(h, RFB200_ERR_STATE, "rfb200_ipc_import: this rank has been imported already");
+    void *v = nullptr, *w = nullptr, *w2 = nullptr;
+    RF_CUDA(h, cudaIpcOpenMemHandle(&v, b.V, cudaIpcMemLazyEnablePeerAccess));
+    RF_CUDA(h, cudaIpcOpenMemHandle(&w, b.W, cudaIpcMemLazyEnablePeerAccess));
+    if (b.hasW2) RF_CUDA(h, cudaIpcOpenMemHandle(&w2, b.W2, cudaIpcMemLazyEnablePeerAccess));
+    p.V = (float2*)v; p.W = (float*)w; p.W2 = (float*)w2; p.open = true;
+    return RFB200_OK;
+}
+
+int rfb200_reduce_p2p(rfb200_handle h, int32_t root) {
+#if RFB200_HAVE_NCCL_H
+    if (!h) return RFB200_ERR_ARG;
+    if (!h->comm) return fail(h, RFB200_ERR_STATE, "rfb200_nccl_init has not been called (its communicator orders the ranks)");
+    if (!g_nccl.AllReduce) return fail(h, RFB200_ERR_NCCL, "ncclAllReduce not found in libnccl");
+    if (root < 0 || root >= h->nRanks || h->nRanks > kMaxP2PRanks) return RFB200_ERR_ARG;
+    for (int k = 0; k < h->nRanks; ++k)
+        if (k != h->rank && ((int)h->peers.size() <= k || !h->peers[k].open))
+            return fail(h, RFB200_ERR_STATE, "rfb200_reduce_p2p: rfb200_ipc_import has not been called for every other rank");
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
+    StageTimer t(h, Stage::REDUCE, h->compute);
+    // every rank has finished inserting (and folding its damped weights) before anybody reads its accumulators
+    if (int rcb = rank_barrier(h)) return rcb;
+    auto one = [&](auto member, void* mine, size_t nFloat4) -> int {
+        P2PArgs a{};
+        for (int k = 0; k < h->nRanks; ++k) a.src[k] = reinterpret_cast<const float4*>(k == h->rank ? mine : (void*)(h->peers[k].*member));
+        a.dst = reinterpret_cast<float4*>(root == h->rank ? mine : (void*)(h->peers[root].*member));
+        a.lo = (long long)(nFloat4 * (size_t)h->rank / (size_t)h->nRanks);
+        a.hi = (long long)(nFloat4 * (size_t)(h->rank + 1) / (size_t)h->nRanks);
+        return launch_p2p(h, a);
+    };
+    int rc = one(&rfb200_handle_s::Peer::V, h->dVb, h->nBlocked / 2);
+    if (!rc) rc = one(&rfb200_handle_s::Peer::W, h->dWb, h->nBlocked / 4);
+    if (!rc && h->dWb2) rc = one(&rfb200_handle_s::Peer::W2, h->dWb2, h->nBlocked / 4);
+    if (rc) return rc;
+    // the root may use the sums, and nobody may change its accumulators, once every rank's slice has been written
+    return rank_barrier(h);
 #else
     (void)root;
     return h ? fail(h, RFB200_ERR_NCCL, "built without nccl.h") : RFB200_ERR_NCCL;

@@ -398,6 +398,41 @@ __global__ void __launch_bounds__(256) k_export(const __grid_constant__ Geometry
     W[idx] = w;
 }
 
+// ---- peer-memory reduce over NVLink (rfb200_reduce_p2p).  Every rank owns the slice [lo, hi) of the accumulators: it
+// reads that slice from the memory of ALL ranks (its own locally, the others through their IPC-mapped pointers, 16-byte
+// loads), adds them in rank order (so the sum does not depend on who computes it or on timing) and stores the result
+// into the root's memory.  In NCCL terms a reduce-scatter and a gather to the root in one kernel, with every link of the
+// switch carrying 1/N of the data instead of the root's links carrying all of it.
+constexpr int kMaxP2PRanks = 16;
+struct P2PArgs {
+    const float4* src[kMaxP2PRanks];   // the same array of every rank (as float4)
+    float4* dst;                       // the root's array
+    long long lo, hi;                  // float4 range this rank reduces
+};
+template <int NR>
+__global__ void __launch_bounds__(256) k_reduce_p2p(const __grid_constant__ P2PArgs a, int nRanksRt) {
+    const int nr = NR > 0 ? NR : nRanksRt;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = a.lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi; i += stride) {
+        float4 v[NR > 0 ? NR : 1];
+        float4 acc;
+        if (NR > 0) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) v[k] = a.src[k][i];          // all loads in flight before the first add
+            acc = v[0];
+#pragma unroll
+            for (int k = 1; k < NR; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+        } else {
+            acc = a.src[0][i];
+            for (int k = 1; k < nr; ++k) {
+                const float4 t = a.src[k][i];
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+        }
+        a.dst[i] = acc;
+    }
+}
+
 // y += x (merging a saved half-set into the current accumulators)
 __global__ void __launch_bounds__(256) k_axpy(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
