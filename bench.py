@@ -296,15 +296,18 @@ def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_ov
     dt = max_over_ranks(time.perf_counter() - t0)
     return {"workload": "config[2] as stated: %d particles %dx%d with CTF in total, sharded over %d GPU(s)" % (total, box, box, world),
             "scaling": "strong", "particles_total": total, "particles_per_gpu": int(mine), "seconds": dt, "value": total / dt, "unit": UNIT,
-            "includes": "H2D from pinned host memory, insertion, reduce onto rank 0 (N>1: %s), normalise + 3-D IFFT + D2H of the map" % ("peer-memory kernel over NVLink" if p2p else "ncclReduce")}
+            "includes": "H2D from pinned host memory, insertion, reduce onto rank 0 (N>1: %s), normalise + 3-D IFFT + D2H of the map" % ("peer-memory kernel over NVLink" if (p2p and os.environ.get("RFB200_BENCH_REDUCE") == "p2p") else "ncclReduce")}
 
 
 def setup_p2p(r, dev, world, rank):
     """Peer-memory reduce: every rank exports the IPC handles of its accumulators, all ranks import all others.  True when
-    every rank succeeded (then rfb200_reduce_p2p replaces the two ncclReduce calls); RFB200_BENCH_REDUCE=nccl disables it."""
+    every rank succeeded.  Opt-in: RFB200_BENCH_REDUCE=p2p uses rfb200_reduce_p2p wherever the bench reduces, =both keeps
+    ncclReduce for the measured paths and reports the two collectives side by side (`reduce_ms`, `reduce_check`).  The
+    default is NCCL alone: measured on 2 and 4 B200s the NVLS reduce of NCCL is as fast or faster (profiles/
+    r2c_bench_n*_p2p_reduce.json: 1.32 vs 1.36 ms at N = 2, 1.43 vs 2.00 ms at N = 4 for 856 MB per rank)."""
     import torch
     import torch.distributed as dist
-    if world <= 1 or os.environ.get("RFB200_BENCH_REDUCE", "p2p") == "nccl":
+    if world <= 1 or os.environ.get("RFB200_BENCH_REDUCE", "nccl") == "nccl":
         return False
     ok = 1
     try:
@@ -329,7 +332,7 @@ def setup_p2p(r, dev, world, rank):
 
 
 def do_reduce(r, p2p):
-    if p2p:
+    if p2p and os.environ.get("RFB200_BENCH_REDUCE") == "p2p":
         r.reduce_p2p(0)
     else:
         r.reduce(0)
@@ -368,7 +371,9 @@ def reduce_check(dev, local, rank, world):
             r.insert_device_ptr(img.data_ptr(), p)
         r.sync()
         dist.barrier()
-    do_reduce(r, p2p)
+        r.reduce_p2p(0)
+    else:
+        r.reduce(0)
     out = None
     if rank == 0:
         after = r.weight_sum()
@@ -380,7 +385,7 @@ def reduce_check(dev, local, rank, world):
         solo_sum = solo.weight_sum()
         ref = solo.finalize()
         solo.close()
-        out = {"ranks": world, "particles_per_rank": n, "collective": "rfb200_reduce_p2p (peer memory over NVLink)" if p2p else "rfb200_reduce_nccl",
+        out = {"ranks": world, "particles_per_rank": n, "collective": "rfb200_reduce_nccl, then rfb200_reduce_p2p (peer memory over NVLink) on re-inserted particles" if p2p else "rfb200_reduce_nccl",
                "weight_sum_after_nccl_reduce": after_nccl,
                "weight_sum_after_reduce": after, "sum_of_rank_weight_sums": float(t.item()),
                "weight_sum_rel_err": abs(after - float(t.item())) / abs(float(t.item())),
@@ -389,6 +394,9 @@ def reduce_check(dev, local, rank, world):
         out["ok"] = bool(out["weight_sum_rel_err"] <= 1e-6 and out["map_rel_l2_vs_one_rank"] <= 1e-5)
     else:
         r.sync()
+    if p2p:
+        r.ipc_release()
+        dist.barrier()      # every rank has unmapped its peers before anybody frees
     r.close()
     dist.barrier()
     return out
@@ -699,8 +707,12 @@ def main():
                     r.sync()
                     ts.append(max_over_ranks(time.perf_counter() - tq))
                 cmp_ms[name] = 1e3 * min(ts)
-            extra["reduce_ms"] = dict(cmp_ms, used="p2p" if p2p else "nccl", bytes_per_rank=int(12 * r.accumulator_ptrs()[2]))
+            extra["reduce_ms"] = dict(cmp_ms, used="p2p" if (p2p and os.environ.get("RFB200_BENCH_REDUCE") == "p2p") else "nccl",
+                                      bytes_per_rank=int(12 * r.accumulator_ptrs()[2]))
         extra["strong_scaling"] = measure_strong_scaling(r, host, box, world, rank, args.strong_total, barrier, max_over_ranks, vol_ptr, p2p)
+    if p2p:
+        r.ipc_release()
+        barrier()           # every rank has unmapped its peers before anybody frees
     r.close()
     r = None
     del batches

@@ -146,6 +146,10 @@ int rfb200_reduce_nccl(rfb200_handle h, int32_t root);
 int rfb200_ipc_export(rfb200_handle h, void* out_blob);
 int rfb200_ipc_import(rfb200_handle h, int32_t rank, const void* peer_blob);
 int rfb200_reduce_p2p(rfb200_handle h, int32_t root);
+/* Unmaps the peers' accumulators (after the last rfb200_reduce_p2p).  A process must not destroy a handle whose
+ * accumulators another process still has mapped: every rank calls this, the host program makes the ranks wait for
+ * each other, then the handles may be destroyed in any order. */
+int rfb200_ipc_release(rfb200_handle h);
 /* Raw device pointers of the blocked accumulators (for a host program that wants to run
  * its own collective on them): V = n_blocked float2, W = n_blocked float. */
 int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_blocked);

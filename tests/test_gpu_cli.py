@@ -108,9 +108,12 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-def test_cli_two_gpus_prepare_fsc(tmp_path, oracle_mod):
-    """--gpus 2: the program forks one rank per GPU, each inserts a contiguous shard, one NCCL reduce per map;
-    full map and both half-set maps must equal the oracle's (and hence the single-GPU program's)."""
+@pytest.mark.parametrize("collective", ["nccl", "p2p"])
+def test_cli_two_gpus_prepare_fsc(tmp_path, oracle_mod, monkeypatch, collective):
+    """--gpus 2: the program forks one rank per GPU, each inserts a contiguous shard, one reduce per map (ncclReduce, or
+    with RFB200_REDUCE=p2p the peer-memory kernel over CUDA IPC mappings); full map and both half-set maps must equal the
+    oracle's (and hence the single-GPU program's)."""
+    monkeypatch.setenv("RFB200_REDUCE", collective)
     N, n = 32, 61
     d, md = _dataset(tmp_path, N, n, True, True, ".stk", seed=11)
     out = str(tmp_path / "full.vol")

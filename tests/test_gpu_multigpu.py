@@ -66,7 +66,9 @@ def _worker(rank, world, N, n, tmp, p2p=False):
     r.sync()
     if rank == 0:
         np.save(os.path.join(tmp, "vol.npy"), r.finalize())
-    _exchange(tmp, "done", rank, world, b"1")     # nobody frees memory a peer has mapped before everybody is done
+    if p2p:
+        r.ipc_release()
+    _exchange(tmp, "done", rank, world, b"1")     # nobody frees memory a peer has mapped before everybody has unmapped it
     r.close()
 
 

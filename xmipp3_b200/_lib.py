@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_create", "rfb200_destroy", "rfb200_last_error", "rfb200_get_info",
     "rfb200_insert_batch", "rfb200_insert_batch_device", "rfb200_sync", "rfb200_reset",
     "rfb200_nccl_unique_id", "rfb200_nccl_init", "rfb200_reduce_nccl", "rfb200_accumulator_ptrs",
-    "rfb200_ipc_export", "rfb200_ipc_import", "rfb200_reduce_p2p",
+    "rfb200_ipc_export", "rfb200_ipc_import", "rfb200_reduce_p2p", "rfb200_ipc_release",
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
@@ -109,6 +109,7 @@ def load(build=True):
     L.rfb200_ipc_export.argtypes = [H, C.c_void_p]
     L.rfb200_ipc_import.argtypes = [H, C.c_int32, C.c_void_p]
     L.rfb200_reduce_p2p.argtypes = [H, C.c_int32]
+    L.rfb200_ipc_release.argtypes = [H]
     L.rfb200_accumulator_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.rfb200_export_accumulators.argtypes = [H, C.c_void_p, C.c_void_p]
     L.rfb200_finalize.argtypes = [H, C.c_void_p]
@@ -260,6 +261,10 @@ class Reconstructor:
 
     def reduce_p2p(self, root=0):
         self._check(self._L.rfb200_reduce_p2p(self._h, int(root)))
+
+    def ipc_release(self):
+        """unmap the peers' accumulators; the ranks must wait for each other between this call and close()"""
+        self._check(self._L.rfb200_ipc_release(self._h))
 
     def accumulator_ptrs(self):
         v, w, n = C.c_void_p(), C.c_void_p(), C.c_int64()

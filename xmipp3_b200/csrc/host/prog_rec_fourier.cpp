@@ -46,10 +46,32 @@ struct Api {
     int (*nccl_unique_id)(void*) = nullptr;
     int (*nccl_init)(rfb200_handle, const void*, int32_t, int32_t) = nullptr;
     int (*reduce_nccl)(rfb200_handle, int32_t) = nullptr;
+    int (*ipc_export)(rfb200_handle, void*) = nullptr;
+    int (*ipc_import)(rfb200_handle, int32_t, const void*) = nullptr;
+    int (*reduce_p2p)(rfb200_handle, int32_t) = nullptr;
+    int (*ipc_release)(rfb200_handle) = nullptr;
     int (*sync)(rfb200_handle) = nullptr;
     int (*reset)(rfb200_handle) = nullptr;
     int (*warmup)(rfb200_handle) = nullptr;
 };
+
+// small files in the private rendezvous directory: how the forked ranks hand each other a few bytes
+bool publishFile(const std::string& name, const void* data, size_t bytes) {
+    const std::string tmp = name + ".tmp";
+    const int wfd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);   // never through a pre-existing file or symlink
+    const bool wrote = wfd >= 0 && write(wfd, data, bytes) == (ssize_t)bytes;
+    if (wfd >= 0) close(wfd);
+    return wrote && rename(tmp.c_str(), name.c_str()) == 0;
+}
+bool collectFile(const std::string& name, void* data, size_t bytes, int timeoutSeconds = 120) {
+    auto tStart = std::chrono::steady_clock::now();
+    for (;;) {
+        std::ifstream f(name, std::ios::binary);
+        if (f && f.read((char*)data, bytes) && f.gcount() == (std::streamsize)bytes) return true;
+        if (std::chrono::steady_clock::now() - tStart > std::chrono::seconds(timeoutSeconds)) return false;
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+}
 
 std::string selfDir() {
     Dl_info info;
@@ -93,6 +115,10 @@ Api loadApi() {
     BIND(nccl_unique_id, "rfb200_nccl_unique_id")
     BIND(nccl_init, "rfb200_nccl_init")
     BIND(reduce_nccl, "rfb200_reduce_nccl")
+    BIND(ipc_export, "rfb200_ipc_export")
+    BIND(ipc_import, "rfb200_ipc_import")
+    BIND(reduce_p2p, "rfb200_reduce_p2p")
+    BIND(ipc_release, "rfb200_ipc_release")
     BIND(sync, "rfb200_sync")
     BIND(reset, "rfb200_reset")
     BIND(warmup, "rfb200_warmup")
@@ -492,6 +518,12 @@ void ProgRecFourierB200::runRanks() {
     }
     unlink(tmpl);
     unlink((std::string(tmpl) + ".tmp").c_str());
+    for (size_t k = 0; k < pids.size(); ++k)        // files of the opt-in peer-memory reduce
+        for (const char* ext : {".ipc", ".p2p", ".closed"}) {
+            const std::string f = std::string(tmpl) + ext + std::to_string(k);
+            unlink(f.c_str());
+            unlink((f + ".tmp").c_str());
+        }
     rmdir(dirTmpl);
     if (failed) throw ProgramError("a GPU rank failed (exit code " + std::to_string(failed) + ")");
 }
@@ -556,6 +588,7 @@ void ProgRecFourierB200::run() {
     cfg.device = device;
     cfg.max_batch = bufferSize;
     rfb200_handle h = nullptr;
+    bool useP2P = false;           // peer-memory reduce instead of ncclReduce (decided by all ranks together below)
     int rc = api.create(&cfg, &h);
     if (rc != RFB200_OK) throw ProgramError(std::string("GPU initialisation failed: ") + api.last_error(nullptr));
     if (worldSize > 1) {
@@ -594,6 +627,27 @@ void ProgRecFourierB200::run() {
             std::string msg = std::string("NCCL initialisation failed: ") + api.last_error(h);
             api.destroy(h);
             throw ProgramError(msg);
+        }
+        // Peer-memory reduce (rfb200_reduce_p2p), opt-in with RFB200_REDUCE=p2p (on NVSwitch systems NCCL's in-switch
+        // reduction is as fast or faster): every rank publishes the IPC handles of its accumulators next to
+        // the rendezvous file and maps everybody else's; then every rank publishes whether that worked, and the ranks use
+        // the peer-memory kernel only if all of them can (they must all take the same collective).
+        const char* redEnv = getenv("RFB200_REDUCE");
+        if (redEnv && std::string(redEnv) == "p2p") {
+            char blob[RFB200_IPC_BYTES];
+            char ok = api.ipc_export(h, blob) == RFB200_OK ? 1 : 0;
+            if (!publishFile(idFile + ".ipc" + std::to_string(rank), blob, sizeof blob)) ok = 0;
+            for (int k = 0; k < worldSize && ok; ++k) {
+                if (k == rank) continue;
+                char peer[RFB200_IPC_BYTES];
+                if (!collectFile(idFile + ".ipc" + std::to_string(k), peer, sizeof peer) || api.ipc_import(h, k, peer) != RFB200_OK) ok = 0;
+            }
+            publishFile(idFile + ".p2p" + std::to_string(rank), &ok, 1);
+            useP2P = true;
+            for (int k = 0; k < worldSize; ++k) {
+                char theirs = 0;
+                if (!collectFile(idFile + ".p2p" + std::to_string(k), &theirs, 1) || !theirs) useP2P = false;
+            }
         }
     }
 
@@ -738,7 +792,7 @@ void ProgRecFourierB200::run() {
             joinWarm();
             if (worldSize == 1) return;
             PhaseTimer acc{tReduce, std::chrono::steady_clock::now()};
-            rc = api.reduce_nccl(h, 0);
+            rc = useP2P ? api.reduce_p2p(h, 0) : api.reduce_nccl(h, 0);
             if (rc != RFB200_OK) throw ProgramError(std::string("reduce failed: ") + api.last_error(h));
             if (rank != 0 && api.reset(h) != RFB200_OK) throw ProgramError(std::string("reset failed: ") + api.last_error(h));
         };
@@ -784,6 +838,13 @@ void ProgRecFourierB200::run() {
         api.host_free(buf[1]);
         closeImageCache();
         throw;
+    }
+    if (useP2P) {
+        // nobody frees accumulators that a peer still has mapped: unmap, tell the others, wait for them
+        api.ipc_release(h);
+        char one = 1;
+        publishFile(idFile + ".closed" + std::to_string(rank), &one, 1);
+        for (int k = 0; k < worldSize; ++k) collectFile(idFile + ".closed" + std::to_string(k), &one, 1, 60);
     }
     api.destroy(h);
     api.host_free(buf[0]);

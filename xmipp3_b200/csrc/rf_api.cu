@@ -1388,6 +1388,20 @@ int rfb200_ipc_import(rfb200_handle h, int32_t rank, const void* in256) {
     return RFB200_OK;
 }
 
+int rfb200_ipc_release(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));
+    for (auto& p : h->peers) {
+        if (!p.open) continue;
+        cudaIpcCloseMemHandle(p.V);
+        cudaIpcCloseMemHandle(p.W);
+        if (p.W2) cudaIpcCloseMemHandle(p.W2);
+        p = rfb200_handle_s::Peer{};
+    }
+    return RFB200_OK;
+}
+
 int rfb200_reduce_p2p(rfb200_handle h, int32_t root) {
 #if RFB200_HAVE_NCCL_H
     if (!h) return RFB200_ERR_ARG;
