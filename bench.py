@@ -299,6 +299,29 @@ def measure_strong_scaling(r, host, box, world, rank, total, barrier_all, max_ov
             "includes": "H2D from pinned host memory, insertion, reduce onto rank 0 (N>1: %s), normalise + 3-D IFFT + D2H of the map" % ("peer-memory kernel over NVLink" if (p2p and os.environ.get("RFB200_BENCH_REDUCE") == "p2p") else "ncclReduce")}
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and therefore first-touch its pinned batches) on the CPUs of the NUMA node its GPU hangs off, as NCCL
+    and the multi-GPU CLI do for their threads: with eight ranks pulling 25-55 GB/s each out of host memory, buffers
+    that sit on the other socket halve the H2D rate.  Best effort: any missing sysfs entry leaves the affinity alone."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": open(dev + "/numa_node").read().strip(), "cpus": len(cpus)}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    return None
+
+
 def setup_p2p(r, dev, world, rank):
     """Peer-memory reduce: every rank exports the IPC handles of its accumulators, all ranks import all others.  True when
     every rank succeeded.  Opt-in: RFB200_BENCH_REDUCE=p2p uses rfb200_reduce_p2p wherever the bench reduces, =both keeps
@@ -473,6 +496,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("RFB200_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -681,7 +705,7 @@ def main():
                "h2d_bytes_per_step": int(B * box * box * 4 + B * 24 * 8),
                "d2h_bytes_per_step": int(8 + (box ** 3 * 4) // K),
                "includes": "H2D from pinned host memory, per-step 8-byte read-back (collected one step late: pipelined host loop), final reduce (N>1), normalise + 3-D IFFT + D2H of the volume"}
-        extra = {"e2e_insert_call_ms_per_step": 1e3 * t_call_ins / K, "e2e_result_call_ms_per_step": 1e3 * t_call_sum / K,
+        extra = {"numa_binding": numa, "e2e_insert_call_ms_per_step": 1e3 * t_call_ins / K, "e2e_result_call_ms_per_step": 1e3 * t_call_sum / K,
                  "e2e_insert_s": t_ins - t0, "e2e_reduce_s": t_red - t_ins, "e2e_finalize_s": t1 - t_red}
         if rank == 0 and vol is not None:
             extra["volume_finite"] = bool(np.isfinite(vol).all())
