@@ -21,7 +21,7 @@
  *     crop + gridding correction on the CPU:
  *     reconstruct_fourier_gpu.cpp:683-767,879-932)            rfb200_finalize
  *   MPI_Reduce per row (parallel_adapt_cuda/
- *     mpi_reconstruct_fourier_gpu.cpp:250-268)                rfb200_reduce_nccl
+ *     mpi_reconstruct_fourier_gpu.cpp:250-268)                rfb200_reduce_nccl (or rfb200_reduce_p2p)
  *   releaseWrapper :81 / releaseTempVolumeGPU :106 /
  *   releaseBlobTable :132 / deleteStreams :93 / unpinMemory :136   rfb200_destroy
  *
