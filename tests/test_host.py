@@ -142,6 +142,38 @@ def test_reads_reference_image_fixtures():
         assert np.array_equal(s, m)
     assert np.array_equal(io.read_spider(REF_IMG + "/smallStack.stk"), np.stack(
         [_host.read_image("%d@%s/smallStack.stk" % (k, REF_IMG), 64, 64) for k in range(1, 5)]))
+    # ... and as IMAGIC (.hed + .img), addressed through either file
+    assert np.array_equal(_host.read_image(REF_IMG + "/singleImage.hed", 3, 3), a)
+    assert np.array_equal(_host.read_image(REF_IMG + "/singleImage.img", 3, 3), a)
+    assert _host.image_info(REF_IMG + "/smallStack.hed") == (64, 64, 1, 4)
+    for k in range(1, 5):
+        assert np.array_equal(_host.read_image("%d@%s/smallStack.hed" % (k, REF_IMG), 64, 64),
+                              _host.read_image("%d@%s/smallStack.stk" % (k, REF_IMG), 64, 64))
+
+
+def test_imagic_stack_types_and_byte_order(tmp_path):
+    """IMAGIC stacks written here: REAL, INTG (16-bit) and PACK (unsigned bytes), little and big endian headers."""
+    rng = np.random.default_rng(5)
+    n, ny, nx = 3, 6, 5
+    data = {"REAL": rng.normal(size=(n, ny, nx)).astype(np.float32),
+            "INTG": rng.integers(-3000, 3000, size=(n, ny, nx)).astype(np.int16),
+            "PACK": rng.integers(0, 256, size=(n, ny, nx)).astype(np.uint8)}
+    for typ, arr in data.items():
+        for order in ("<", ">"):
+            base = str(tmp_path / ("s_%s_%s" % (typ, "le" if order == "<" else "be")))
+            hed = np.zeros((n, 256), dtype=order + "i4")
+            for k in range(n):
+                hed[k, 0], hed[k, 1], hed[k, 12], hed[k, 13] = k + 1, n - 1, ny, nx
+            raw = hed.tobytes()
+            raw = b"".join(raw[1024 * k:1024 * k + 56] + typ.encode() + raw[1024 * k + 60:1024 * (k + 1)] for k in range(n))
+            open(base + ".hed", "wb").write(raw)
+            arr.astype(arr.dtype.newbyteorder(order)).tofile(base + ".img")
+            assert _host.image_info(base + ".hed") == (nx, ny, 1, n)
+            for k in range(n):
+                got = _host.read_image("%d@%s.img" % (k + 1, base), nx, ny)
+                assert np.array_equal(got, arr[k].astype(np.float32)), (typ, order, k)
+    with pytest.raises(Exception):
+        _host.read_image(str(tmp_path / "missing.hed"), nx, ny)
 
 
 def test_cli_parsing_defaults_and_errors():

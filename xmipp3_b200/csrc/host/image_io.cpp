@@ -82,10 +82,57 @@ void preadAll(int fd, void* buf, size_t n, off_t off, const std::string& what) {
     }
 }
 
+// IMAGIC stack: <base>.hed holds one 1024-byte record of 256 32-bit words per image (word 0: image number, 1: number of
+// following images, 12: lines, 13: pixels per line, 14: type "REAL" / "INTG" / "PACK"), <base>.img the images back to
+// back without headers.  Decoded into the MRC reader's terms (headerless data, mode 2 / 1 / 100), so reading an image is
+// the same single pread (xmippCore: rwIMAGIC.cpp; fixtures resources/test/image/smallStack.hed, singleImage.hed).
+void openImagic(OpenFile& f, const std::string& path) {
+    const size_t dot = path.rfind('.');
+    const std::string base = dot == std::string::npos ? path : path.substr(0, dot);
+    const std::string hed = base + ".hed", img = base + ".img";
+    int hfd = open(hed.c_str(), O_RDONLY);
+    if (hfd < 0) throw std::runtime_error("cannot open IMAGIC header file " + hed);
+    int32_t w[256];
+    const bool got = pread(hfd, w, sizeof w, 0) == (ssize_t)sizeof w;
+    close(hfd);
+    if (!got) throw std::runtime_error(hed + ": not an IMAGIC header file");
+    auto sane = [](int32_t v) { return v > 0 && v < 100000; };
+    if (!(sane(w[12]) && sane(w[13]))) {
+        f.swap = true;
+        for (int i = 0; i < 256; ++i)
+            if (i != 14) w[i] = (int32_t)bswap32((uint32_t)w[i]);      // word 14 is four characters
+    }
+    if (!(sane(w[12]) && sane(w[13])) || w[1] < 0) throw std::runtime_error(hed + ": bad IMAGIC header");
+    char type[5] = {0, 0, 0, 0, 0};
+    memcpy(type, &w[14], 4);
+    const std::string t(type);
+    if (t == "REAL") f.mrcMode = 2;
+    else if (t == "INTG") f.mrcMode = 1;
+    else if (t == "PACK") f.mrcMode = 100;        // unsigned bytes
+    else throw std::runtime_error(hed + ": unsupported IMAGIC data type '" + t + "'");
+    f.fd = open(img.c_str(), O_RDONLY);
+    if (f.fd < 0) throw std::runtime_error("cannot open IMAGIC data file " + img);
+    f.kind = Kind::MRC;
+    f.dataOffset = 0;
+    f.isStack = true;
+    f.info.nx = w[13];
+    f.info.ny = w[12];
+    f.info.nz = 1;
+    f.info.nImages = (size_t)w[1] + 1;
+    struct stat st;
+    const size_t bytes = f.mrcMode == 2 ? 4 : f.mrcMode == 1 ? 2 : 1;
+    if (fstat(f.fd, &st) != 0 || (size_t)st.st_size < f.info.nImages * (size_t)f.info.nx * f.info.ny * bytes)
+        throw std::runtime_error(img + ": shorter than its header file says");
+}
+
 FilePtr openFile(const std::string& path, const std::string& fmt) {
     auto fp = std::make_shared<OpenFile>();      // owns the descriptor from here on: every throw below closes it
     OpenFile& f = *fp;
     f.path = path;
+    if (fmt == "hed" || fmt == "img") {
+        openImagic(f, path);
+        return fp;
+    }
     f.fd = open(path.c_str(), O_RDONLY);
     if (f.fd < 0) throw std::runtime_error("cannot open image file " + path);
     struct stat st;
@@ -276,7 +323,7 @@ void readImage2D(const ImageSource& f, size_t idx, float* out, int nx, int ny) {
         if (f.swap) for (size_t i = 0; i < count; ++i) out[i] = swapf(out[i]);
         return;
     }
-    int bytes = (f.mrcMode == 0) ? 1 : (f.mrcMode == 1 || f.mrcMode == 6 || f.mrcMode == 12) ? 2 : 4;
+    int bytes = (f.mrcMode == 0 || f.mrcMode == 100) ? 1 : (f.mrcMode == 1 || f.mrcMode == 6 || f.mrcMode == 12) ? 2 : 4;
     off_t off = (off_t)(f.dataOffset + k * count * bytes);
     if (f.mrcMode == 2) {
         preadAll(f.fd, out, count * 4, off, spec);
@@ -287,6 +334,7 @@ void readImage2D(const ImageSource& f, size_t idx, float* out, int nx, int ny) {
     preadAll(f.fd, raw.data(), raw.size(), off, spec);
     for (size_t i = 0; i < count; ++i) {
         if (f.mrcMode == 0) out[i] = (float)(int8_t)raw[i];
+        else if (f.mrcMode == 100) out[i] = (float)raw[i];
         else if (f.mrcMode == 1 || f.mrcMode == 6) {
             uint16_t v;
             memcpy(&v, &raw[2 * i], 2);
