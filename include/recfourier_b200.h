@@ -146,6 +146,14 @@ int rfb200_reduce_nccl(rfb200_handle h, int32_t root);
 int rfb200_ipc_export(rfb200_handle h, void* out_blob);
 int rfb200_ipc_import(rfb200_handle h, int32_t rank, const void* peer_blob);
 int rfb200_reduce_p2p(rfb200_handle h, int32_t root);
+/* The same reduce without NCCL, for host programs that can make their ranks wait for each other themselves (MPI_Barrier, a
+ * file rendezvous): rfb200_set_ranks instead of rfb200_nccl_init, then per reduce
+ *     rfb200_reduce_p2p_prepare(h);  BARRIER;  rfb200_reduce_p2p_run(h, root);  BARRIER;
+ * prepare returns when this rank's accumulators are final, run when its slice of the sums has been stored in the root's
+ * memory.  Nothing of NCCL is loaded or set up (its connection set-up costs 0.1 - 1.5 s, more than a short run). */
+int rfb200_set_ranks(rfb200_handle h, int32_t n_ranks, int32_t rank);
+int rfb200_reduce_p2p_prepare(rfb200_handle h);
+int rfb200_reduce_p2p_run(rfb200_handle h, int32_t root);
 /* Unmaps the peers' accumulators (after the last rfb200_reduce_p2p).  A process must not destroy a handle whose
  * accumulators another process still has mapped: every rank calls this, the host program makes the ranks wait for
  * each other, then the handles may be destroyed in any order. */

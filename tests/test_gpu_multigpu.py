@@ -53,13 +53,21 @@ def _worker(rank, world, N, n, tmp, p2p=False):
         while not os.path.exists(idfile):
             time.sleep(0.05)
         uid = open(idfile, "rb").read()
-    r.nccl_init(uid, world, rank)
+    if p2p == "host":
+        r.set_ranks(world, rank)          # no NCCL at all: the ranks order themselves (here: through files)
+    else:
+        r.nccl_init(uid, world, rank)
     if p2p:
         for k, blob in enumerate(_exchange(tmp, "ipc", rank, world, r.ipc_export())):
             if k != rank:
                 r.ipc_import(k, blob)
     r.insert(d["images"][b:e], p[b:e])
-    if p2p:
+    if p2p == "host":
+        r.reduce_p2p_prepare()
+        _exchange(tmp, "b0", rank, world, b"1")
+        r.reduce_p2p_run(0)
+        _exchange(tmp, "b1", rank, world, b"1")
+    elif p2p:
         r.reduce_p2p(0)
     else:
         r.reduce(0)
@@ -97,6 +105,24 @@ def test_two_gpu_peer_memory_reduce_matches_single_gpu():
     N, n = 64, 400
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_worker, args=(2, N, n, tmp, True), nprocs=2, join=True)
+        vol2 = np.load(os.path.join(tmp, "vol.npy"))
+    d = synth.make_dataset(n, N, seed=7, ctf=True)
+    cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], **d["ctf"])
+    r = Reconstructor(N, use_ctf=True, sampling=1.5, device=0)
+    r.insert(d["images"], make_particles(n, **cols))
+    vol1 = r.finalize()
+    r.close()
+    assert synth.rel_l2(vol2, vol1) <= 2e-5
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_two_gpu_peer_memory_reduce_without_nccl():
+    """rfb200_set_ranks + rfb200_reduce_p2p_prepare / _run with the host program's own barriers: no communicator."""
+    import torch.multiprocessing as mp
+    from xmipp3_b200._lib import Reconstructor, make_particles
+    N, n = 64, 400
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(2, N, n, tmp, "host"), nprocs=2, join=True)
         vol2 = np.load(os.path.join(tmp, "vol.npy"))
     d = synth.make_dataset(n, N, seed=7, ctf=True)
     cols = dict(rot=d["rot"], tilt=d["tilt"], psi=d["psi"], **d["ctf"])

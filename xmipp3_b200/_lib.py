@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "rfb200_insert_batch", "rfb200_insert_batch_device", "rfb200_sync", "rfb200_reset",
     "rfb200_nccl_unique_id", "rfb200_nccl_init", "rfb200_reduce_nccl", "rfb200_accumulator_ptrs",
     "rfb200_ipc_export", "rfb200_ipc_import", "rfb200_reduce_p2p", "rfb200_ipc_release",
+    "rfb200_set_ranks", "rfb200_reduce_p2p_prepare", "rfb200_reduce_p2p_run",
     "rfb200_export_accumulators", "rfb200_finalize", "rfb200_get_timings",
     "rfb200_halfset_push", "rfb200_halfset_merge", "rfb200_timer_start", "rfb200_timer_stop", "rfb200_weight_sum", "rfb200_get_streams",
     "rfb200_debug_slice_dims", "rfb200_debug_get_slice", "rfb200_weight_sum_begin", "rfb200_weight_sum_end",
@@ -110,6 +111,9 @@ def load(build=True):
     L.rfb200_ipc_import.argtypes = [H, C.c_int32, C.c_void_p]
     L.rfb200_reduce_p2p.argtypes = [H, C.c_int32]
     L.rfb200_ipc_release.argtypes = [H]
+    L.rfb200_set_ranks.argtypes = [H, C.c_int32, C.c_int32]
+    L.rfb200_reduce_p2p_prepare.argtypes = [H]
+    L.rfb200_reduce_p2p_run.argtypes = [H, C.c_int32]
     L.rfb200_accumulator_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.rfb200_export_accumulators.argtypes = [H, C.c_void_p, C.c_void_p]
     L.rfb200_finalize.argtypes = [H, C.c_void_p]
@@ -261,6 +265,16 @@ class Reconstructor:
 
     def reduce_p2p(self, root=0):
         self._check(self._L.rfb200_reduce_p2p(self._h, int(root)))
+
+    # host-ordered form (no NCCL): set_ranks; per reduce: reduce_p2p_prepare, BARRIER, reduce_p2p_run, BARRIER
+    def set_ranks(self, n_ranks, rank):
+        self._check(self._L.rfb200_set_ranks(self._h, int(n_ranks), int(rank)))
+
+    def reduce_p2p_prepare(self):
+        self._check(self._L.rfb200_reduce_p2p_prepare(self._h))
+
+    def reduce_p2p_run(self, root=0):
+        self._check(self._L.rfb200_reduce_p2p_run(self._h, int(root)))
 
     def ipc_release(self):
         """unmap the peers' accumulators; the ranks must wait for each other between this call and close()"""

@@ -1,6 +1,7 @@
 // prog_rec_fourier.cpp — see prog_rec_fourier.h
 #include "prog_rec_fourier.h"
 
+#include <dirent.h>
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <libgen.h>
@@ -50,6 +51,9 @@ struct Api {
     int (*ipc_import)(rfb200_handle, int32_t, const void*) = nullptr;
     int (*reduce_p2p)(rfb200_handle, int32_t) = nullptr;
     int (*ipc_release)(rfb200_handle) = nullptr;
+    int (*set_ranks)(rfb200_handle, int32_t, int32_t) = nullptr;
+    int (*reduce_p2p_prepare)(rfb200_handle) = nullptr;
+    int (*reduce_p2p_run)(rfb200_handle, int32_t) = nullptr;
     int (*sync)(rfb200_handle) = nullptr;
     int (*reset)(rfb200_handle) = nullptr;
     int (*warmup)(rfb200_handle) = nullptr;
@@ -119,6 +123,9 @@ Api loadApi() {
     BIND(ipc_import, "rfb200_ipc_import")
     BIND(reduce_p2p, "rfb200_reduce_p2p")
     BIND(ipc_release, "rfb200_ipc_release")
+    BIND(set_ranks, "rfb200_set_ranks")
+    BIND(reduce_p2p_prepare, "rfb200_reduce_p2p_prepare")
+    BIND(reduce_p2p_run, "rfb200_reduce_p2p_run")
     BIND(sync, "rfb200_sync")
     BIND(reset, "rfb200_reset")
     BIND(warmup, "rfb200_warmup")
@@ -516,14 +523,13 @@ void ProgRecFourierB200::runRanks() {
                 if (q > 0) kill(q, SIGTERM);
         }
     }
-    unlink(tmpl);
-    unlink((std::string(tmpl) + ".tmp").c_str());
-    for (size_t k = 0; k < pids.size(); ++k)        // files of the opt-in peer-memory reduce
-        for (const char* ext : {".ipc", ".p2p", ".closed"}) {
-            const std::string f = std::string(tmpl) + ext + std::to_string(k);
-            unlink(f.c_str());
-            unlink((f + ".tmp").c_str());
+    if (DIR* d = opendir(dirTmpl)) {                  // the rendezvous file and the small files of the peer-memory reduce
+        while (dirent* e = readdir(d)) {
+            const std::string n = e->d_name;
+            if (n != "." && n != "..") unlink((std::string(dirTmpl) + "/" + n).c_str());
         }
+        closedir(d);
+    }
     rmdir(dirTmpl);
     if (failed) throw ProgramError("a GPU rank failed (exit code " + std::to_string(failed) + ")");
 }
@@ -591,7 +597,48 @@ void ProgRecFourierB200::run() {
     bool useP2P = false;           // peer-memory reduce instead of ncclReduce (decided by all ranks together below)
     int rc = api.create(&cfg, &h);
     if (rc != RFB200_OK) throw ProgramError(std::string("GPU initialisation failed: ") + api.last_error(nullptr));
-    if (worldSize > 1) {
+    const char* redEnv = getenv("RFB200_REDUCE");
+    const bool wantP2P = worldSize > 1 && redEnv && std::string(redEnv) == "p2p";
+    // barrier over the forked ranks through the private rendezvous directory (one small file per rank and barrier)
+    int barrierSeq = 0;
+    auto fileBarrier = [&] {
+        const std::string base = idFile + ".b" + std::to_string(barrierSeq++) + "_";
+        char one = 1;
+        if (!publishFile(base + std::to_string(rank), &one, 1)) throw ProgramError("cannot write into the rendezvous directory");
+        for (int k = 0; k < worldSize; ++k)
+            if (!collectFile(base + std::to_string(k), &one, 1, 7 * 24 * 3600)) throw ProgramError("timed out waiting for rank " + std::to_string(k));
+    };
+    if (wantP2P) {
+        // Peer-memory reduce, opt-in with RFB200_REDUCE=p2p: NO NCCL at all (its communicator and connection set-up cost
+        // 0.1 - 1.5 s, more than a short run).  Every rank publishes the IPC handles of its accumulators next to the
+        // rendezvous file and maps everybody else's, the ranks order themselves with file barriers around the kernel
+        // (rfb200_reduce_p2p_prepare / _run).  On NVSwitch systems NCCL's in-switch reduction moves the bytes a little
+        // faster; what this path saves is the set-up.
+        if (api.set_ranks(h, worldSize, rank) != RFB200_OK) {
+            std::string msg = std::string("set_ranks failed: ") + api.last_error(h);
+            api.destroy(h);
+            throw ProgramError(msg);
+        }
+        char blob[RFB200_IPC_BYTES];
+        char ok = api.ipc_export(h, blob) == RFB200_OK ? 1 : 0;
+        if (!publishFile(idFile + ".ipc" + std::to_string(rank), blob, sizeof blob)) ok = 0;
+        for (int k = 0; k < worldSize && ok; ++k) {
+            if (k == rank) continue;
+            char peer[RFB200_IPC_BYTES];
+            if (!collectFile(idFile + ".ipc" + std::to_string(k), peer, sizeof peer) || api.ipc_import(h, k, peer) != RFB200_OK) ok = 0;
+        }
+        publishFile(idFile + ".p2p" + std::to_string(rank), &ok, 1);
+        useP2P = true;
+        for (int k = 0; k < worldSize; ++k) {
+            char theirs = 0;
+            if (!collectFile(idFile + ".p2p" + std::to_string(k), &theirs, 1) || !theirs) useP2P = false;
+        }
+        if (!useP2P) {
+            std::string msg = std::string("RFB200_REDUCE=p2p: the GPUs cannot map each other's memory (") + api.last_error(h) + "); run without it";
+            api.destroy(h);
+            throw ProgramError(msg);
+        }
+    } else if (worldSize > 1) {
         // rendezvous: rank 0 publishes the 128-byte ncclUniqueId in idFile (written aside, then renamed), the others
         // wait for it (the MPI program broadcasts its job ranges the same way, mpi_reconstruct_fourier_gpu.cpp:150-200)
         char id[128];
@@ -627,27 +674,6 @@ void ProgRecFourierB200::run() {
             std::string msg = std::string("NCCL initialisation failed: ") + api.last_error(h);
             api.destroy(h);
             throw ProgramError(msg);
-        }
-        // Peer-memory reduce (rfb200_reduce_p2p), opt-in with RFB200_REDUCE=p2p (on NVSwitch systems NCCL's in-switch
-        // reduction is as fast or faster): every rank publishes the IPC handles of its accumulators next to
-        // the rendezvous file and maps everybody else's; then every rank publishes whether that worked, and the ranks use
-        // the peer-memory kernel only if all of them can (they must all take the same collective).
-        const char* redEnv = getenv("RFB200_REDUCE");
-        if (redEnv && std::string(redEnv) == "p2p") {
-            char blob[RFB200_IPC_BYTES];
-            char ok = api.ipc_export(h, blob) == RFB200_OK ? 1 : 0;
-            if (!publishFile(idFile + ".ipc" + std::to_string(rank), blob, sizeof blob)) ok = 0;
-            for (int k = 0; k < worldSize && ok; ++k) {
-                if (k == rank) continue;
-                char peer[RFB200_IPC_BYTES];
-                if (!collectFile(idFile + ".ipc" + std::to_string(k), peer, sizeof peer) || api.ipc_import(h, k, peer) != RFB200_OK) ok = 0;
-            }
-            publishFile(idFile + ".p2p" + std::to_string(rank), &ok, 1);
-            useP2P = true;
-            for (int k = 0; k < worldSize; ++k) {
-                char theirs = 0;
-                if (!collectFile(idFile + ".p2p" + std::to_string(k), &theirs, 1) || !theirs) useP2P = false;
-            }
         }
     }
 
@@ -792,7 +818,15 @@ void ProgRecFourierB200::run() {
             joinWarm();
             if (worldSize == 1) return;
             PhaseTimer acc{tReduce, std::chrono::steady_clock::now()};
-            rc = useP2P ? api.reduce_p2p(h, 0) : api.reduce_nccl(h, 0);
+            if (useP2P) {
+                rc = api.reduce_p2p_prepare(h);                 // this rank's accumulators are final
+                if (rc == RFB200_OK) {
+                    fileBarrier();
+                    rc = api.reduce_p2p_run(h, 0);              // its slice of the sums is in rank 0's memory
+                }
+                if (rc == RFB200_OK) fileBarrier();
+            } else
+                rc = api.reduce_nccl(h, 0);
             if (rc != RFB200_OK) throw ProgramError(std::string("reduce failed: ") + api.last_error(h));
             if (rank != 0 && api.reset(h) != RFB200_OK) throw ProgramError(std::string("reset failed: ") + api.last_error(h));
         };
@@ -842,9 +876,7 @@ void ProgRecFourierB200::run() {
     if (useP2P) {
         // nobody frees accumulators that a peer still has mapped: unmap, tell the others, wait for them
         api.ipc_release(h);
-        char one = 1;
-        publishFile(idFile + ".closed" + std::to_string(rank), &one, 1);
-        for (int k = 0; k < worldSize; ++k) collectFile(idFile + ".closed" + std::to_string(k), &one, 1, 60);
+        fileBarrier();
     }
     api.destroy(h);
     api.host_free(buf[0]);

@@ -1402,20 +1402,16 @@ int rfb200_ipc_release(rfb200_handle h) {
     return RFB200_OK;
 }
 
-int rfb200_reduce_p2p(rfb200_handle h, int32_t root) {
-#if RFB200_HAVE_NCCL_H
-    if (!h) return RFB200_ERR_ARG;
-    if (!h->comm) return fail(h, RFB200_ERR_STATE, "rfb200_nccl_init has not been called (its communicator orders the ranks)");
-    if (!g_nccl.AllReduce) return fail(h, RFB200_ERR_NCCL, "ncclAllReduce not found in libnccl");
+namespace {
+int check_peers(rfb200_handle h, int32_t root) {
     if (root < 0 || root >= h->nRanks || h->nRanks > kMaxP2PRanks) return RFB200_ERR_ARG;
     for (int k = 0; k < h->nRanks; ++k)
         if (k != h->rank && ((int)h->peers.size() <= k || !h->peers[k].open))
-            return fail(h, RFB200_ERR_STATE, "rfb200_reduce_p2p: rfb200_ipc_import has not been called for every other rank");
-    RF_CUDA(h, cudaSetDevice(h->cfg.device));
-    if (int rcf = flush_deficit(h)) return rcf;
-    StageTimer t(h, Stage::REDUCE, h->compute);
-    // every rank has finished inserting (and folding its damped weights) before anybody reads its accumulators
-    if (int rcb = rank_barrier(h)) return rcb;
+            return fail(h, RFB200_ERR_STATE, "peer-memory reduce: rfb200_ipc_import has not been called for every other rank");
+    return RFB200_OK;
+}
+// the kernels of the peer-memory reduce: this rank's slice of V, W (and the un-modulated weights) out of every rank's memory
+int p2p_kernels(rfb200_handle h, int32_t root) {
     auto one = [&](auto member, void* mine, size_t nFloat4) -> int {
         P2PArgs a{};
         for (int k = 0; k < h->nRanks; ++k) a.src[k] = reinterpret_cast<const float4*>(k == h->rank ? mine : (void*)(h->peers[k].*member));
@@ -1427,13 +1423,59 @@ int rfb200_reduce_p2p(rfb200_handle h, int32_t root) {
     int rc = one(&rfb200_handle_s::Peer::V, h->dVb, h->nBlocked / 2);
     if (!rc) rc = one(&rfb200_handle_s::Peer::W, h->dWb, h->nBlocked / 4);
     if (!rc && h->dWb2) rc = one(&rfb200_handle_s::Peer::W2, h->dWb2, h->nBlocked / 4);
-    if (rc) return rc;
+    return rc;
+}
+}  // namespace
+
+int rfb200_reduce_p2p(rfb200_handle h, int32_t root) {
+#if RFB200_HAVE_NCCL_H
+    if (!h) return RFB200_ERR_ARG;
+    if (!h->comm) return fail(h, RFB200_ERR_STATE, "rfb200_nccl_init has not been called (its communicator orders the ranks)");
+    if (!g_nccl.AllReduce) return fail(h, RFB200_ERR_NCCL, "ncclAllReduce not found in libnccl");
+    if (int rcp = check_peers(h, root)) return rcp;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
+    StageTimer t(h, Stage::REDUCE, h->compute);
+    // every rank has finished inserting (and folding its damped weights) before anybody reads its accumulators
+    if (int rcb = rank_barrier(h)) return rcb;
+    if (int rc = p2p_kernels(h, root)) return rc;
     // the root may use the sums, and nobody may change its accumulators, once every rank's slice has been written
     return rank_barrier(h);
 #else
     (void)root;
     return h ? fail(h, RFB200_ERR_NCCL, "built without nccl.h") : RFB200_ERR_NCCL;
 #endif
+}
+
+// ---- the same reduce for host programs that order their ranks themselves (MPI_Barrier, files): no NCCL involved
+int rfb200_set_ranks(rfb200_handle h, int32_t n_ranks, int32_t rank) {
+    if (!h || n_ranks < 1 || n_ranks > kMaxP2PRanks || rank < 0 || rank >= n_ranks) return RFB200_ERR_ARG;
+#if RFB200_HAVE_NCCL_H
+    if (h->comm) return fail(h, RFB200_ERR_STATE, "rfb200_set_ranks: the handle already belongs to an NCCL communicator");
+#endif
+    h->nRanks = n_ranks;
+    h->rank = rank;
+    return RFB200_OK;
+}
+
+int rfb200_reduce_p2p_prepare(rfb200_handle h) {
+    if (!h) return RFB200_ERR_ARG;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (int rcf = flush_deficit(h)) return rcf;
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));       // this rank's accumulators are final
+    return RFB200_OK;
+}
+
+int rfb200_reduce_p2p_run(rfb200_handle h, int32_t root) {
+    if (!h) return RFB200_ERR_ARG;
+    if (int rcp = check_peers(h, root)) return rcp;
+    RF_CUDA(h, cudaSetDevice(h->cfg.device));
+    {
+        StageTimer t(h, Stage::REDUCE, h->compute);
+        if (int rc = p2p_kernels(h, root)) return rc;
+    }
+    RF_CUDA(h, cudaStreamSynchronize(h->compute));       // this rank's slice has been written into the root's memory
+    return RFB200_OK;
 }
 
 int rfb200_accumulator_ptrs(rfb200_handle h, void** d_V, void** d_W, int64_t* n_blocked) {
