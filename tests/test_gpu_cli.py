@@ -108,10 +108,10 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("collective", ["nccl", "p2p"])
+@pytest.mark.parametrize("collective", ["nccl", "p2p", "auto"])
 def test_cli_two_gpus_prepare_fsc(tmp_path, oracle_mod, monkeypatch, collective):
     """--gpus 2: the program forks one rank per GPU, each inserts a contiguous shard, one reduce per map (ncclReduce, or
-    with RFB200_REDUCE=p2p the peer-memory kernel over CUDA IPC mappings); full map and both half-set maps must equal the
+    with RFB200_REDUCE=p2p / auto the peer-memory kernel over CUDA IPC mappings, no NCCL); full map and both half-set maps must equal the
     oracle's (and hence the single-GPU program's)."""
     monkeypatch.setenv("RFB200_REDUCE", collective)
     N, n = 32, 61

@@ -597,8 +597,15 @@ void ProgRecFourierB200::run() {
     bool useP2P = false;           // peer-memory reduce instead of ncclReduce (decided by all ranks together below)
     int rc = api.create(&cfg, &h);
     if (rc != RFB200_OK) throw ProgramError(std::string("GPU initialisation failed: ") + api.last_error(nullptr));
+    // RFB200_REDUCE: unset / "auto" = peer-memory reduce when every GPU can map every other one, else NCCL;
+    // "p2p" = peer memory or fail; "nccl" = the two ncclReduce calls
     const char* redEnv = getenv("RFB200_REDUCE");
-    const bool wantP2P = worldSize > 1 && redEnv && std::string(redEnv) == "p2p";
+    const std::string redMode = redEnv && *redEnv ? redEnv : "auto";
+    if (redMode != "auto" && redMode != "p2p" && redMode != "nccl") {
+        api.destroy(h);
+        throw ProgramError("RFB200_REDUCE must be auto, p2p or nccl");
+    }
+    const bool wantP2P = worldSize > 1 && redMode != "nccl";
     // barrier over the forked ranks through the private rendezvous directory (one small file per rank and barrier)
     int barrierSeq = 0;
     auto fileBarrier = [&] {
@@ -609,11 +616,11 @@ void ProgRecFourierB200::run() {
             if (!collectFile(base + std::to_string(k), &one, 1, 7 * 24 * 3600)) throw ProgramError("timed out waiting for rank " + std::to_string(k));
     };
     if (wantP2P) {
-        // Peer-memory reduce, opt-in with RFB200_REDUCE=p2p: NO NCCL at all (its communicator and connection set-up cost
+        // Peer-memory reduce (the default when it is possible): NO NCCL at all (its communicator and connection set-up cost
         // 0.1 - 1.5 s, more than a short run).  Every rank publishes the IPC handles of its accumulators next to the
         // rendezvous file and maps everybody else's, the ranks order themselves with file barriers around the kernel
         // (rfb200_reduce_p2p_prepare / _run).  On NVSwitch systems NCCL's in-switch reduction moves the bytes a little
-        // faster; what this path saves is the set-up.
+        // faster (about a millisecond at 8 GPUs); what this path saves is the set-up.
         if (api.set_ranks(h, worldSize, rank) != RFB200_OK) {
             std::string msg = std::string("set_ranks failed: ") + api.last_error(h);
             api.destroy(h);
@@ -634,11 +641,16 @@ void ProgRecFourierB200::run() {
             if (!collectFile(idFile + ".p2p" + std::to_string(k), &theirs, 1) || !theirs) useP2P = false;
         }
         if (!useP2P) {
-            std::string msg = std::string("RFB200_REDUCE=p2p: the GPUs cannot map each other's memory (") + api.last_error(h) + "); run without it";
-            api.destroy(h);
-            throw ProgramError(msg);
+            if (redMode == "p2p") {
+                std::string msg = std::string("RFB200_REDUCE=p2p: the GPUs cannot map each other's memory (") + api.last_error(h) + ")";
+                api.destroy(h);
+                throw ProgramError(msg);
+            }
+            api.ipc_release(h);        // whatever was mapped: nobody frees memory a peer still has open
+            fileBarrier();
         }
-    } else if (worldSize > 1) {
+    }
+    if (worldSize > 1 && !useP2P) {
         // rendezvous: rank 0 publishes the 128-byte ncclUniqueId in idFile (written aside, then renamed), the others
         // wait for it (the MPI program broadcasts its job ranges the same way, mpi_reconstruct_fourier_gpu.cpp:150-200)
         char id[128];
