@@ -1357,6 +1357,9 @@ int rank_barrier(rfb200_handle h) {
 
 int rfb200_ipc_export(rfb200_handle h, void* out256) {
     if (!h || !out256) return RFB200_ERR_ARG;
+    // the kernel moves 16-byte vectors: the blocked layout of the exact path is a multiple of 2048 voxels, the (S+1)^3
+    // temporary volume of --fast need not be; callers then stay with ncclReduce (the CLI's auto mode does by itself)
+    if (h->nBlocked % 4 != 0) return fail(h, RFB200_ERR_UNSUPPORTED, "peer-memory reduce: the accumulators of this handle are not a multiple of 4 elements (--fast); use rfb200_reduce_nccl");
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     IpcBlob b;
     std::memset(&b, 0, sizeof b);
@@ -1372,6 +1375,7 @@ int rfb200_ipc_export(rfb200_handle h, void* out256) {
 
 int rfb200_ipc_import(rfb200_handle h, int32_t rank, const void* in256) {
     if (!h || !in256 || rank < 0 || rank >= kMaxP2PRanks) return RFB200_ERR_ARG;
+    if (h->nBlocked % 4 != 0) return fail(h, RFB200_ERR_UNSUPPORTED, "peer-memory reduce: not available for --fast handles");
     RF_CUDA(h, cudaSetDevice(h->cfg.device));
     IpcBlob b;
     std::memcpy(&b, in256, sizeof b);
