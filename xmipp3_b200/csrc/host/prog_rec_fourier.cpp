@@ -481,6 +481,7 @@ void ProgRecFourierB200::runRanks() {
             rank = r;
             worldSize = n;
             idFile = tmpl;
+            privateRendezvous = true;
             // the ranks share the host: every rank gets its slice of the loader threads and of the cores (the reference's
             // MPI program leaves this to mpirun's binding)
             {
@@ -605,7 +606,10 @@ void ProgRecFourierB200::run() {
         api.destroy(h);
         throw ProgramError("RFB200_REDUCE must be auto, p2p or nccl");
     }
-    const bool wantP2P = worldSize > 1 && redMode != "nccl";
+    // With an external launcher the rendezvous file may sit in a directory that outlives the run: stale barrier files of
+    // an earlier run would let a rank read its peers too early, so "auto" means NCCL there and peer memory must be asked
+    // for (with a fresh RFB200_ID_FILE path per run).
+    const bool wantP2P = worldSize > 1 && (redMode == "p2p" || (redMode == "auto" && privateRendezvous));
     // barrier over the forked ranks through the private rendezvous directory (one small file per rank and barrier)
     int barrierSeq = 0;
     auto fileBarrier = [&] {

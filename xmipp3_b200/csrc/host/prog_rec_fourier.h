@@ -54,6 +54,7 @@ public:
     int gpus = 1;                       // --gpus <n | all>
     int rank = 0, worldSize = 1;        // set by --gpus or the environment
     std::string idFile;                 // rendezvous file for the 128-byte ncclUniqueId
+    bool privateRendezvous = false;     // idFile lies in a fresh directory of our own launcher (no stale files possible)
 
     static std::string usage();
     // parse argv (throws ProgramError on unknown / malformed options)
